@@ -1,0 +1,76 @@
+"""ctypes binding of libagenda_b200.so (the C ABI declared in include/agenda_b200.h).
+
+There is NO fallback: if the shared library has not been built, or a tensor is not on a CUDA device, the call
+raises.  Build with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a, in-tree).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libagenda_b200.so")
+
+F32, BF16 = 0, 1
+
+
+class AgendaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libagenda_b200 error {code}: {message}")
+        self.code = code
+
+
+# name -> (argtypes); every entry point returns int.  Mirrors include/agenda_b200.h one to one.
+_SIGNATURES = {
+    "agenda_attn_self_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                             c_void_p],
+    "agenda_attn_self_fwd_variant": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
+                                     c_void_p],
+    "agenda_attn_self_fwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p],
+    "agenda_attn_cross_fwd_heat": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int, c_void_p],
+    "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "agenda_heat_finalize": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "agenda_heat_normalize_u8": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "agenda_resize_bicubic_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "agenda_heat_to_u8_image": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "agenda_stack_heatmaps_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "agenda_heat_postprocess_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p],
+    "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+}
+EXPORTS = ["agenda_version", "agenda_last_error", "agenda_device_ok"] + list(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the library; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built (run __graft_entry__.build()). "
+            "agenda_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.agenda_version.restype = c_int
+    lib.agenda_version.argtypes = []
+    lib.agenda_last_error.restype = c_char_p
+    lib.agenda_last_error.argtypes = []
+    lib.agenda_device_ok.restype = c_int
+    lib.agenda_device_ok.argtypes = []
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise AgendaError(rc, lib.agenda_last_error().decode("utf-8", "replace"))

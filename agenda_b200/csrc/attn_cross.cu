@@ -1,0 +1,35 @@
+// agenda_attn_cross_fwd_heat: cross-attention + heat-map epilogue dispatcher (data_generation/hook.py:108-114 and
+// _unravel_attn, hook.py:28-56).
+#include "common.cuh"
+
+namespace agenda {
+constexpr int kMaxTokens = 128;
+struct TokenList {
+  int n;
+  int idx[kMaxTokens];
+};
+int attn_common_checks(const char* who, const void* q, const void* k, const void* v, void* out, int dtype, int B,
+                       int H, int N, int M, int d);
+int build_token_list(const char* who, const int32_t* token_idx, int T, int M, TokenList* tl);
+int attn_cross_f32(const void* q, const void* k, const void* v, void* out, int dtype, int B, int H, int N, int M,
+                   int d, float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream);
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" int agenda_attn_cross_fwd_heat(const void* q, const void* k, const void* v, void* out, int dtype, int B,
+                                          int H, int N, int M, int d, float scale, const int32_t* token_idx, int T,
+                                          int b_first, float* maps, int accumulate, void* stream) {
+  int rc = attn_common_checks("attn_cross_fwd_heat", q, k, v, out, dtype, B, H, N, M, d);
+  if (rc != AGENDA_OK) return rc;
+  if (b_first < 0 || b_first > B) return fail(AGENDA_ERR_BAD_SHAPE, "attn_cross_fwd_heat: b_first=%d, B=%d", b_first, B);
+  TokenList tl;
+  tl.n = 0;
+  if (maps != nullptr) {
+    rc = build_token_list("attn_cross_fwd_heat", token_idx, T, M, &tl);
+    if (rc != AGENDA_OK) return rc;
+    if (reinterpret_cast<uintptr_t>(maps) & 3) return fail(AGENDA_ERR_MISALIGNED, "attn_cross_fwd_heat: maps");
+  }
+  return attn_cross_f32(q, k, v, out, dtype, B, H, N, M, d, scale, tl, b_first, tl.n ? maps : nullptr, accumulate,
+                        stream);
+}

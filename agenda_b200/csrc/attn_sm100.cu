@@ -1,0 +1,518 @@
+// K1: fused self-attention  O = softmax(scale * Q K^T) V  for sm_100a — tcgen05 tensor cores, TMEM accumulators,
+// TMA-fed shared-memory tiles, warp-specialised, flash-style online softmax (the [B*H,N,N] probability tensor that
+// the reference materialises at data_generation/hook.py:108 never exists).
+//
+// Layout: q/k/v/out are [B, N, H*d] bf16, token-major — exactly what to_q/to_k/to_v produce (hook.py:93,101-102);
+// head_to_batch_dim/batch_to_head_dim (hook.py:104-106,115) are folded into a 4-D TMA tensor map
+// (d, H, N, B) whose box is (64 elems, 1 head, BLOCK rows, 1 batch).  Head dims 40/80/160 are zero-padded to the
+// 64-element (128-byte) swizzle atom by TMA out-of-bounds fill, so no padded copy of Q/K/V is ever made; the MMAs
+// only run over round16(d) (48/80/160) of K-extent / N-extent.
+//
+// CTA = one (batch, head, 128-query tile).  6 warps:
+//   warps 0-3  softmax warpgroup: thread r owns query row r (tcgen05.ld 32x32b: warp w <-> TMEM lanes 32w..32w+31)
+//   warp 4     TMA producer (Q once; K_j, V_j through 2-stage mbarrier rings)
+//   warp 5     TMEM allocator + single-thread tcgen05.mma issuer
+// TMEM (512 columns): S[0] | S[1] (BLOCK_N fp32 columns each, double buffered so QK_{j+1} overlaps softmax_j) | O.
+// P (bf16) goes back to the tensor core either through TMEM (aliasing the S buffer it came from; TS-form MMA) or
+// through a 128B-swizzled shared-memory tile (SS-form) — template switch kPTmem.
+// MMA issue order: QK_0, QK_1, PV_0, QK_2, PV_1, ...
+// O is rescaled lazily (only when a row max grows by more than 2^8), by the softmax warpgroup itself.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace agenda {
+
+namespace sm100 {
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;
+constexpr int kSoftmaxThreads = 128;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+// ------------------------------------------------------------------ PTX wrappers ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+#define AGENDA_R8(a, o) "%" #a, "%" #o
+// 32 lanes x 32 columns of 32-bit: thread t of the warp gets TMEM lane (base_lane + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(r);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]),
+      "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp field layout) ----
+// shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // version
+  d |= static_cast<uint64_t>(2) << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: kind::f16, A/B = BF16, D = F32, M x N, A K-major, B K-major (b_mn=0) or MN-major (b_mn=1)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn) << 16) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+template <int D>
+struct Cfg {
+  static constexpr int kD = D;
+  static constexpr int kDP = (D + 15) / 16 * 16;        // MMA extent over the head dim
+  static constexpr int kChunks = (D + 63) / 64;         // 64-element (128 B) swizzle atoms per row
+  static constexpr int kBlockN = (D <= 80) ? 128 : 64;  // keys per KV tile
+  static constexpr int kPChunks = kBlockN / 64;
+  static constexpr int kQBytes = kChunks * kBlockM * 128;
+  static constexpr int kKVBytes = kChunks * kBlockN * 128;  // one K (or V) stage
+  static constexpr int kPBytes = kPChunks * kBlockM * 128;  // one P buffer (SS variant)
+  static constexpr int kColS0 = 0, kColS1 = kBlockN, kColO = 2 * kBlockN;
+  static_assert(kColO + kDP <= 512, "TMEM overflow");
+};
+
+struct Barriers {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], p_full[2], pv_done[2];
+  uint32_t tmem_base;
+};
+
+template <int D, bool kPTmem>
+constexpr size_t smem_bytes() {
+  using C = Cfg<D>;
+  return 1024 /*align slack*/ + C::kQBytes + 4 * C::kKVBytes + (kPTmem ? 0 : 2 * C::kPBytes) + sizeof(Barriers) + 64;
+}
+
+template <int D, bool kPTmem>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_self_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv_k,
+                       const __grid_constant__ CUtensorMap map_kv_v, __nv_bfloat16* __restrict__ out, int H, int N,
+                       float scale_log2) {
+  using C = Cfg<D>;
+  constexpr int BN = C::kBlockN;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + C::kQBytes;          // 2 stages
+  unsigned char* sV = sK + 2 * C::kKVBytes;     // 2 stages
+  unsigned char* sP = sV + 2 * C::kKVBytes;     // 2 buffers (SS variant only)
+  Barriers* bars = reinterpret_cast<Barriers*>(sP + (kPTmem ? 0 : 2 * C::kPBytes));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kBlockM;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int n_tiles = (N + BN - 1) / BN;
+
+  if (tid == 4 * 32) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv_k); tma_prefetch_desc(&map_kv_v);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+      mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], kSoftmaxThreads);
+      mbar_init(&bars->pv_done[s], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_expect_tx(&bars->q_full, C::kQBytes);
+      for (int c = 0; c < C::kChunks; ++c) tma_load_4d(&map_q, &bars->q_full, sQ + c * kBlockM * 128, c * 64, h, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->k_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->k_full[s], C::kKVBytes);
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(&map_kv_k, &bars->k_full[s], sK + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
+        mbar_wait(&bars->v_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->v_full[s], C::kKVBytes);
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(&map_kv_v, &bars->v_full[s], sV + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kBlockM, BN, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kBlockM, C::kDP, 1);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      auto issue_pv = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->p_full[s], ph);
+        mbar_wait(&bars->v_full[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          // B = V tile, MN-major: 16 keys per MMA = 2 swizzle atoms of 8 rows (SBO 1024 B); d > 64 continues in the
+          // next 64-column chunk (LBO = BN*128 B)
+          const uint64_t bdesc = make_sdesc(v_addr + s * C::kKVBytes + kk * 2048, BN * 128, 1024);
+          if (kPTmem) {
+            umma_ts(tmem + C::kColO, tmem + (s ? C::kColS1 : C::kColS0) + kk * 8, bdesc, idesc_pv, (j | kk) != 0);
+          } else {
+            const uint64_t adesc = make_sdesc(p_addr + s * C::kPBytes + (kk >> 2) * kBlockM * 128 + (kk & 3) * 32, 16, 1024);
+            umma_ss(tmem + C::kColO, adesc, bdesc, idesc_pv, (j | kk) != 0);
+          }
+        }
+        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->pv_done[s]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->k_full[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < C::kDP / 16; ++kk) {
+          const uint64_t adesc = make_sdesc(q_addr + (kk >> 2) * kBlockM * 128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_sdesc(k_addr + s * C::kKVBytes + (kk >> 2) * BN * 128 + (kk & 3) * 32, 16, 1024);
+          umma_ss(tmem + (s ? C::kColS1 : C::kColS0), adesc, bdesc, idesc_qk, kk != 0);
+        }
+        umma_commit(&bars->k_empty[s]);
+        umma_commit(&bars->s_full[s]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(n_tiles - 1);
+    }
+  } else {
+    // ============================== softmax warpgroup (thread == query row) ==============================
+    const int row = tid;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float m_used = -INFINITY;  // running max actually used for scaling (log2 units, scale folded in)
+    float l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&bars->s_full[s], ph);
+      tc_fence_after();
+      float sv[BN];
+      const uint32_t s_taddr = tmem + lane_base + (s ? C::kColS1 : C::kColS0);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
+      tmem_wait_ld();
+      const int kv_left = N - j * BN;  // keys valid in this tile
+      if (kv_left < BN) {
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (i >= kv_left) sv[i] = -INFINITY;
+      }
+      float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+      for (int i = 4; i < BN; i += 4) {
+        mx0 = fmaxf(mx0, sv[i]); mx1 = fmaxf(mx1, sv[i + 1]); mx2 = fmaxf(mx2, sv[i + 2]); mx3 = fmaxf(mx3, sv[i + 3]);
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // lazy rescale: only move the reference max when it grew by more than 2^8
+      const bool need = m_new > m_used + kRescaleThreshold;
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        // O must be quiescent: PV_{j-1} finished (it was triggered by our own p_full arrival of tile j-1)
+        mbar_wait(&bars->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const float m_next = need ? m_new : m_used;
+        const float f = ex2(m_used - m_next);
+        l_run *= f;
+        m_used = m_next;
+#pragma unroll
+        for (int c = 0; c < C::kDP / 16; ++c) {
+          float o[16];
+          tmem_ld16(tmem + lane_base + C::kColO + c * 16, o);
+          tmem_wait_ld();
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(o[i] * f);
+          tmem_st16(tmem + lane_base + C::kColO + c * 16, u);
+        }
+        tmem_wait_st();
+      }
+      // P = 2^(s*scale_log2 - m_used), row sum, bf16
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < BN; i += 2) {
+        sv[i] = ex2(fmaf(sv[i], scale_log2, -m_used));
+        sv[i + 1] = ex2(fmaf(sv[i + 1], scale_log2, -m_used));
+        sum0 += sv[i]; sum1 += sv[i + 1];
+      }
+      l_run += sum0 + sum1;
+      if (kPTmem) {
+        // P overwrites the first BN/2 columns of the S buffer it was computed from (2 bf16 per 32-bit column)
+        if (j >= 2) {
+          // nothing to wait for: PV_{j-2} read P from this buffer before QK_j (in-order MMA pipe) overwrote it
+        }
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = pack_bf16(sv[c * 32 + 2 * i], sv[c * 32 + 2 * i + 1]);
+          tmem_st16(s_taddr + c * 16, u);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+      } else {
+        // the P buffer of tile j-2 must have been consumed by PV_{j-2}
+        if (j >= 2) mbar_wait(&bars->pv_done[s], ((j >> 1) + 1) & 1);
+        unsigned char* prow = sP + s * C::kPBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) {  // 16-byte chunks of 8 keys
+          uint4 pk;
+          pk.x = pack_bf16(sv[c * 8 + 0], sv[c * 8 + 1]); pk.y = pack_bf16(sv[c * 8 + 2], sv[c * 8 + 3]);
+          pk.z = pack_bf16(sv[c * 8 + 4], sv[c * 8 + 5]); pk.w = pack_bf16(sv[c * 8 + 6], sv[c * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + (c >> 3) * kBlockM * 128 + (((c & 7) ^ (row & 7)) << 4)) = pk;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+      }
+      mbar_arrive(&bars->p_full[s]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait(&bars->pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int n = q0 + row;
+    __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + h * D;
+#pragma unroll
+    for (int c = 0; c < C::kDP / 16; ++c) {
+      float o[16];
+      tmem_ld16(tmem + lane_base + C::kColO + c * 16, o);
+      tmem_wait_ld();
+      if (n < N) {
+        uint4 lo, hi;
+        lo.x = pack_bf16(o[0] * inv_l, o[1] * inv_l); lo.y = pack_bf16(o[2] * inv_l, o[3] * inv_l);
+        lo.z = pack_bf16(o[4] * inv_l, o[5] * inv_l); lo.w = pack_bf16(o[6] * inv_l, o[7] * inv_l);
+        hi.x = pack_bf16(o[8] * inv_l, o[9] * inv_l); hi.y = pack_bf16(o[10] * inv_l, o[11] * inv_l);
+        hi.z = pack_bf16(o[12] * inv_l, o[13] * inv_l); hi.w = pack_bf16(o[14] * inv_l, o[15] * inv_l);
+        if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+        if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace sm100
+
+// ------------------------------------------------------------------ host side ---------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// [B, N, H*d] bf16 viewed as (d, H, N, B); box (64, 1, rows, 1), 128-byte swizzle, zero fill out of bounds.
+static int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t C = static_cast<cuuint64_t>(H) * d;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(d) * 2, C * 2, static_cast<cuuint64_t>(N) * C * 2};
+  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+  return AGENDA_OK;
+}
+
+template <int D, bool kPTmem>
+static int launch_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
+                        cudaStream_t stream) {
+  using C = sm100::Cfg<D>;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, sm100::kBlockM)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  constexpr size_t smem = sm100::smem_bytes<D, kPTmem>();
+  auto kern = sm100::attn_self_sm100_kernel<D, kPTmem>;
+  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid((N + sm100::kBlockM - 1) / sm100::kBlockM, B * H);
+  kern<<<grid, sm100::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
+                                                scale * 1.4426950408889634f);
+  AGENDA_LAUNCH_CHECK("attn_self_sm100_kernel");
+  return AGENDA_OK;
+}
+
+int attn_common_checks(const char* who, const void* q, const void* k, const void* v, void* out, int dtype, int B,
+                       int H, int N, int M, int d);
+
+// variant: 0 = P through TMEM (TS-form PV MMA), 1 = P through shared memory (SS-form)
+int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
+                    int variant, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_self_fwd: q/k/v/out must be 16-byte aligned");
+#define AGENDA_DISPATCH(DD)                                                                                \
+  case DD:                                                                                                 \
+    return variant == 0 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \
+                        : launch_sm100<DD, false>(q, k, v, out, B, H, N, scale, st);
+  switch (d) {
+    AGENDA_DISPATCH(40)
+    AGENDA_DISPATCH(64)
+    AGENDA_DISPATCH(80)
+    AGENDA_DISPATCH(160)
+    default:
+      return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: head dim %d not in {40,64,80,160}", d);
+  }
+#undef AGENDA_DISPATCH
+}
+
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out, int dtype, int B, int H,
+                                    int N, int d, float scale, void* stream) {
+  int rc = attn_common_checks("attn_self_fwd", q, k, v, out, dtype, B, H, N, N, d);
+  if (rc != AGENDA_OK) return rc;
+  if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: tensor-core path takes bf16 (dtype=1)");
+  return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
+}
+
+// Test hook: same contract, explicit P-operand variant (0 = TMEM, 1 = shared memory).
+extern "C" int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
+                                            int d, float scale, int variant, void* stream) {
+  int rc = attn_common_checks("attn_self_fwd_variant", q, k, v, out, AGENDA_BF16, B, H, N, N, d);
+  if (rc != AGENDA_OK) return rc;
+  return attn_self_sm100(q, k, v, out, B, H, N, d, scale, variant, stream);
+}

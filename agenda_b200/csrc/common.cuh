@@ -1,0 +1,65 @@
+// Shared helpers for libagenda_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/agenda_b200.h"
+
+namespace agenda {
+
+// thread-local last-error text (agenda_last_error())
+char* last_error_buf();
+int fail(int code, const char* fmt, ...);
+
+inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return AGENDA_OK;
+  return fail(AGENDA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define AGENDA_CUDA(call)                                       \
+  do {                                                          \
+    int _rc = ::agenda::check_cuda((call), #call);              \
+    if (_rc != AGENDA_OK) return _rc;                           \
+  } while (0)
+
+#define AGENDA_LAUNCH_CHECK(name)                               \
+  do {                                                          \
+    int _rc = ::agenda::check_cuda(cudaGetLastError(), name);   \
+    if (_rc != AGENDA_OK) return _rc;                           \
+  } while (0)
+
+inline int num_sms() {
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n > 0 ? n : 148;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// numpy's `(h - mn) / ((mx - mn) + 1e-8f)` in fp32 with IEEE rounding and no FMA contraction
+// (data_generation/data_generation.py:82).
+__device__ __forceinline__ float np_normalize(float h, float mn, float denom) {
+  return __fdiv_rn(__fsub_rn(h, mn), denom);
+}
+__device__ __forceinline__ float np_denominator(float mn, float mx) {
+  return __fadd_rn(__fsub_rn(mx, mn), 1e-8f);
+}
+
+}  // namespace agenda

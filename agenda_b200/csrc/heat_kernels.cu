@@ -1,0 +1,133 @@
+// K3: streaming form of compute_global_heat_map (reference data_generation/hook.py:59-81).
+//   acc += clamp(bicubic_upsample(map), min=0)   per (layer, step) map;   out = acc / count at the end.
+// HBM-bound: per plane read h*w*4 B (stays in L1/L2 for the 16 taps) and read-modify-write L*L*4 B twice.
+#include "common.cuh"
+
+namespace agenda {
+
+// torch get_cubic_upsample_coefficients (A = -0.75) in fp32, taps for source offsets -1,0,+1,+2.
+__device__ __forceinline__ void cubic_taps(float t, float w[4]) {
+  const float A = -0.75f;
+  float x = t + 1.0f;
+  w[0] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+  w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+  float u = 1.0f - t;
+  w[2] = ((A + 2.0f) * u - (A + 3.0f)) * u * u + 1.0f;
+  x = u + 1.0f;
+  w[3] = ((A * x - 5.0f * A) * x + 8.0f * A) * x - 4.0f * A;
+}
+
+// area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=true) + border-replicated indices
+__device__ __forceinline__ void cubic_src(int dst, float scale, int n_in, int idx[4], float w[4]) {
+  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  float fl = floorf(src);
+  cubic_taps(src - fl, w);
+  int i0 = static_cast<int>(fl);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) idx[j] = min(max(i0 - 1 + j, 0), n_in - 1);
+}
+
+// One thread -> 4 consecutive output pixels of one row (float4 read-modify-write of acc, coalesced).
+__global__ void __launch_bounds__(256) heat_upsample_accum_kernel(const float* __restrict__ maps,
+                                                                  float* __restrict__ acc, int n_planes,
+                                                                  int h, int w, int L) {
+  const int quads_per_row = L >> 2;
+  const long long total = static_cast<long long>(n_planes) * L * quads_per_row;
+  const float sy = static_cast<float>(h) / static_cast<float>(L);
+  const float sx = static_cast<float>(w) / static_cast<float>(L);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int qx = static_cast<int>(i % quads_per_row);
+    const long long r = i / quads_per_row;
+    const int y = static_cast<int>(r % L);
+    const long long plane = r / L;
+    const float* __restrict__ src = maps + plane * h * w;
+    float4* dst = reinterpret_cast<float4*>(acc + (plane * L + y) * L) + qx;
+    float4 a = *dst;
+    float v[4];
+    if (h == L && w == L) {  // scale 1: torch returns the input bit-exactly
+      const float4 s = *reinterpret_cast<const float4*>(src + static_cast<long long>(y) * w + qx * 4);
+      v[0] = s.x; v[1] = s.y; v[2] = s.z; v[3] = s.w;
+    } else {
+      int iy[4]; float wy[4];
+      cubic_src(y, sy, h, iy, wy);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        int ix[4]; float wx[4];
+        cubic_src(qx * 4 + p, sx, w, ix, wx);
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* row = src + iy[j] * w;
+          // horizontal taps first, then the 4 rows (torch CPU kernel order)
+          float rsum = __ldg(row + ix[0]) * wx[0] + __ldg(row + ix[1]) * wx[1] + __ldg(row + ix[2]) * wx[2] +
+                       __ldg(row + ix[3]) * wx[3];
+          o += rsum * wy[j];
+        }
+        v[p] = o;
+      }
+    }
+    a.x += fmaxf(v[0], 0.f);  // .clamp_(min=0), hook.py:72
+    a.y += fmaxf(v[1], 0.f);
+    a.z += fmaxf(v[2], 0.f);
+    a.w += fmaxf(v[3], 0.f);
+    *dst = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) heat_finalize_kernel(const float* __restrict__ acc,
+                                                            float* __restrict__ out, long long n4,
+                                                            long long n, float count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  for (; i < n4; i += stride) {
+    float4 a = reinterpret_cast<const float4*>(acc)[i];
+    a.x = __fdiv_rn(a.x, count); a.y = __fdiv_rn(a.y, count);
+    a.z = __fdiv_rn(a.z, count); a.w = __fdiv_rn(a.w, count);
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+  // tail (n not a multiple of 4)
+  for (long long j = n4 * 4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < n; j += stride)
+    out[j] = __fdiv_rn(acc[j], count);
+}
+
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" int agenda_heat_upsample_accum(const float* maps, float* acc, int n_planes, int h, int w, int L,
+                                          void* stream) {
+  if (!maps || !acc) return fail(AGENDA_ERR_NULL_POINTER, "heat_upsample_accum: null pointer");
+  if (n_planes < 0 || h <= 0 || w <= 0 || L <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: bad shape");
+  if (L % 4 != 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: latent_hw must be a multiple of 4 (got %d)", L);
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || ((h == L && w == L) && (reinterpret_cast<uintptr_t>(maps) & 15)))
+    return fail(AGENDA_ERR_MISALIGNED, "heat_upsample_accum: buffers must be 16-byte aligned");
+  if (n_planes == 0) return AGENDA_OK;
+  const long long total = static_cast<long long>(n_planes) * L * (L / 4);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  heat_upsample_accum_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      maps, acc, n_planes, h, w, L);
+  AGENDA_LAUNCH_CHECK("heat_upsample_accum_kernel");
+  return AGENDA_OK;
+}
+
+extern "C" int agenda_heat_finalize(const float* acc, float* out, int64_t n_elems, int count, void* stream) {
+  if (!acc || !out) return fail(AGENDA_ERR_NULL_POINTER, "heat_finalize: null pointer");
+  if (n_elems < 0 || count < 1) return fail(AGENDA_ERR_BAD_SHAPE, "heat_finalize: need n_elems>=0, count>=1");
+  if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(AGENDA_ERR_MISALIGNED, "heat_finalize: buffers must be 16-byte aligned");
+  if (n_elems == 0) return AGENDA_OK;
+  const long long n4 = n_elems / 4;
+  const int threads = 256;
+  long long blocks = (n4 + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  heat_finalize_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      acc, out, n4, n_elems, static_cast<float>(count));
+  AGENDA_LAUNCH_CHECK("heat_finalize_kernel");
+  return AGENDA_OK;
+}

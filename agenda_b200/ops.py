@@ -1,0 +1,194 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, compute in libagenda_b200.so.
+
+PyTorch is used for device memory and streams only.  Every function enqueues on torch's current stream and
+raises if handed a CPU tensor (there is no CPU path in the product).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"agenda_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"agenda_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError(f"agenda_b200: unsupported attention dtype {t.dtype} (float32 or bfloat16)")
+
+
+# ------------------------------------------------------------------ attention (hook.py:104-115) ---------------
+
+def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+              precision: str = "bf16") -> torch.Tensor:
+    """softmax(scale * q k^T) v per head.  q/k/v [B,N,H*d] token-major (to_q/to_k/to_v outputs).
+
+    precision="bf16": tcgen05 tensor-core kernel (inputs are cast to bf16 if needed, fp32 softmax/accumulate).
+    precision="fp32": exact fp32 CUDA-core kernel.
+    """
+    q = _dev(q, "q")
+    B, N, C = q.shape
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    if precision == "bf16":
+        odt = q.dtype
+        qb, kb, vb = (_dev(t, n).to(torch.bfloat16) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+        out = torch.empty_like(qb)
+        _lib.call("agenda_attn_self_fwd", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), _lib.BF16,
+                  B, heads, N, d, scale, _stream())
+        return out if odt == torch.bfloat16 else out.to(odt)
+    if precision != "fp32":
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    k, v = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype)
+    out = torch.empty_like(q)
+    _lib.call("agenda_attn_self_fwd_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
+              B, heads, N, d, scale, _stream())
+    return out
+
+
+def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, maps: Optional[torch.Tensor],
+                    token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
+                    scale: Optional[float] = None) -> torch.Tensor:
+    """Cross-attention + heat epilogue (hook.py:108-114 and _unravel_attn hook.py:28-56).
+
+    maps: fp32 [B-b_first, T, N] written (accumulate=False) or added to (accumulate=True), T = len(token_idx) or
+    M when token_idx is None; pass maps=None to skip the epilogue.  Returns out [B,N,H*d]."""
+    q = _dev(q, "q")
+    k, v = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype)
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    out = torch.empty_like(q)
+    if maps is not None:
+        maps = _dev(maps, "maps", torch.float32)
+        T = M if token_idx is None else len(token_idx)
+        if tuple(maps.shape[:2]) != (B - b_first, T) or maps[0, 0].numel() != N:
+            raise ValueError(f"maps must be [{B - b_first},{T},{N}] (any trailing shape of {N} elements), "
+                             f"got {tuple(maps.shape)}")
+        if not maps.is_contiguous():
+            raise ValueError("maps must be contiguous (it is written in place)")
+        idx = None if token_idx is None else (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
+        mp = maps.data_ptr()
+    else:
+        T, idx, mp = 0, None, None
+    _lib.call("agenda_attn_cross_fwd_heat", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
+              B, heads, N, M, d, scale, idx, T, int(b_first), mp, int(bool(accumulate)), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ heat maps (hook.py:59-81) -----------------
+
+def heat_upsample_accum(maps: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc[..., L, L] += clamp(bicubic(maps[..., h, w] -> L x L), min=0)  (hook.py:72), in place."""
+    maps, acc = _dev(maps, "maps", torch.float32), _dev(acc, "acc", torch.float32)
+    if not acc.is_contiguous():
+        raise ValueError("acc must be contiguous")
+    h, w = maps.shape[-2:]
+    L = acc.shape[-1]
+    n = maps.numel() // (h * w)
+    if acc.shape[-2] != L or acc.numel() != n * L * L:
+        raise ValueError(f"acc {tuple(acc.shape)} does not match maps {tuple(maps.shape)}")
+    _lib.call("agenda_heat_upsample_accum", maps.data_ptr(), acc.data_ptr(), n, h, w, L, _stream())
+
+
+def heat_finalize(acc: torch.Tensor, count: int) -> torch.Tensor:
+    """acc / count (the mean over the (layer x step) list, hook.py:79)."""
+    acc = _dev(acc, "acc", torch.float32)
+    out = torch.empty_like(acc)
+    _lib.call("agenda_heat_finalize", acc.data_ptr(), out.data_ptr(), acc.numel(), int(count), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ post-processing ----------------------------
+
+def heat_normalize_u8(heat: torch.Tensor) -> torch.Tensor:
+    """data_generation.py:82 + astype(uint8): heat fp32 [..., h, w] -> u8 same shape, per-map min-max."""
+    heat = _dev(heat, "heat", torch.float32)
+    h, w = heat.shape[-2:]
+    out = torch.empty(heat.shape, dtype=torch.uint8, device=heat.device)
+    _lib.call("agenda_heat_normalize_u8", heat.data_ptr(), out.data_ptr(), heat.numel() // (h * w), h * w, _stream())
+    return out
+
+
+def resize_bicubic_u8(img: torch.Tensor, size) -> torch.Tensor:
+    """PIL Image.resize((W,H)) default filter for mode 'L' (data_generation.py:85), bit-exact.  img u8 [...,h,w]."""
+    img = _dev(img, "img", torch.uint8)
+    Ho, Wo = (size, size) if isinstance(size, int) else size
+    h, w = img.shape[-2:]
+    n = img.numel() // (h * w)
+    out = torch.empty(img.shape[:-2] + (Ho, Wo), dtype=torch.uint8, device=img.device)
+    _lib.call("agenda_resize_bicubic_u8", img.data_ptr(), out.data_ptr(), n, h, w, Ho, Wo, _stream())
+    return out
+
+
+def heat_to_u8_image(heat: torch.Tensor, size) -> torch.Tensor:
+    """data_generation.py:82-85 fused: fp32 [...,h,w] -> min-max -> u8 -> PIL-bicubic resize -> u8 [...,Ho,Wo]."""
+    heat = _dev(heat, "heat", torch.float32)
+    Ho, Wo = (size, size) if isinstance(size, int) else size
+    h, w = heat.shape[-2:]
+    n = heat.numel() // (h * w)
+    out = torch.empty(heat.shape[:-2] + (Ho, Wo), dtype=torch.uint8, device=heat.device)
+    _lib.call("agenda_heat_to_u8_image", heat.data_ptr(), out.data_ptr(), n, h, w, Ho, Wo, _stream())
+    return out
+
+
+def stack_heatmaps_u8(obj: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor):
+    """postprocess_heatmap.py:44-46: returns (stack u8 [...,H,W,3], inv_bg u8 [...,H,W])."""
+    obj, fg, bg = (_dev(t, n, torch.uint8) for t, n in ((obj, "obj"), (fg, "fg"), (bg, "bg")))
+    if not (obj.shape == fg.shape == bg.shape):
+        raise ValueError("obj/fg/bg shapes differ")
+    H, W = obj.shape[-2:]
+    n = obj.numel() // (H * W)
+    stack = torch.empty(obj.shape + (3,), dtype=torch.uint8, device=obj.device)
+    inv = torch.empty_like(obj)
+    _lib.call("agenda_stack_heatmaps_u8", obj.data_ptr(), fg.data_ptr(), bg.data_ptr(), stack.data_ptr(),
+              inv.data_ptr(), n, H, W, _stream())
+    return stack, inv
+
+
+def heat_postprocess_stack(heat: torch.Tensor, size):
+    """a7+a8 fused for (object, fg, bg) triples: heat fp32 [n,3,h,w] -> (planes u8 [n,3,Ho,Wo], stack u8
+    [n,Ho,Wo,3], inv_bg u8 [n,Ho,Wo])."""
+    heat = _dev(heat, "heat", torch.float32)
+    if heat.dim() != 4 or heat.shape[1] != 3:
+        raise ValueError("heat must be [n,3,h,w]")
+    Ho, Wo = (size, size) if isinstance(size, int) else size
+    n, _, h, w = heat.shape
+    planes = torch.empty((n, 3, Ho, Wo), dtype=torch.uint8, device=heat.device)
+    stack = torch.empty((n, Ho, Wo, 3), dtype=torch.uint8, device=heat.device)
+    inv = torch.empty((n, Ho, Wo), dtype=torch.uint8, device=heat.device)
+    _lib.call("agenda_heat_postprocess_stack", heat.data_ptr(), planes.data_ptr(), stack.data_ptr(), inv.data_ptr(),
+              n, h, w, Ho, Wo, _stream())
+    return planes, stack, inv
+
+
+def ccl_bbox(heat: torch.Tensor, thr: float = 0.5, max_boxes: int = 256, want_labels: bool = True):
+    """Threshold + 4-connected components + boxes.  heat fp32 [n,H,W] ->
+    (labels int32 [n,H,W] or None, counts int32 [n], boxes int32 [n,max_boxes,5] = x,y,w,h,area)."""
+    heat = _dev(heat, "heat", torch.float32)
+    if heat.dim() == 2:
+        heat = heat[None]
+    n, H, W = heat.shape
+    labels = torch.empty((n, H, W), dtype=torch.int32, device=heat.device) if want_labels else None
+    counts = torch.empty((n,), dtype=torch.int32, device=heat.device)
+    boxes = torch.zeros((n, max_boxes, 5), dtype=torch.int32, device=heat.device)
+    _lib.call("agenda_ccl_bbox", heat.data_ptr(), float(thr), labels.data_ptr() if want_labels else None,
+              counts.data_ptr(), boxes.data_ptr(), int(max_boxes), n, H, W, _stream())
+    return labels, counts, boxes

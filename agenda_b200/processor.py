@@ -1,0 +1,121 @@
+"""Drop-in for the reference's `UNetCrossAttentionHooker` (data_generation/hook.py:14-122).
+
+Same plug-in surface — a diffusers AttnProcessor callable
+    proc(attn, hidden_states, encoder_hidden_states=None, attention_mask=None) -> Tensor[B,N,C]
+installed with `unet.set_attn_processor(proc)` (finetune_sd_token.py:755-757) — and the same extra surface
+(`cross_attn_maps`, `is_train`, `latent_hw`, `clear()`, `compute_global_heat_map()`), but the work happens in
+hand-written sm_100a kernels behind the C ABI:
+
+  * hook.py:104-115 (head_to_batch_dim, baddbmm, softmax, bmm, batch_to_head_dim) -> one fused attention kernel;
+    the [B*H,N,M] probability tensor is never materialised.
+  * hook.py:28-56 (`_unravel_attn`: permute, 77-iteration Python loop, stack, mean over heads) -> the cross-attention
+    kernel's epilogue: selected-token probabilities are summed over heads on chip and leave as [B',T,N] fp32.
+  * hook.py:59-81 (`compute_global_heat_map`: bicubic -> clamp -> stack -> mean) -> streaming: every call adds
+    clamp(bicubic(map)) into one persistent [B',T,L,L] fp32 buffer (directly from the attention epilogue when the
+    layer is already at latent resolution), `compute_global_heat_map()` divides by the number of maps.
+
+Differences from the reference, by design:
+  * `tokens=[...]` restricts the heat maps to the listed key-token rows (the reference always keeps all 77 and its
+    callers then read a handful, data_generation.py:74-77).  `tokens=None` keeps all of them, as the reference does.
+  * `cross_attn_maps` is only populated when `record_maps=True` (the reference's list costs 415 MB/image at 50
+    steps); aggregation never needs it.
+  * forward only: `is_train=True` keeps both batch halves (hook.py:48-49) but no autograd graph is built
+    (training is out of scope, SURVEY.md §8 f N3).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+class UNetCrossAttentionHooker:
+    def __init__(self, is_train: bool = True, latent_hw: int = 64, tokens: Optional[Sequence[int]] = None,
+                 precision: str = "bf16", record_maps: bool = False):
+        self.cross_attn_maps: List[torch.Tensor] = []
+        self.is_train = is_train
+        self.latent_hw = latent_hw
+        self.tokens = None if tokens is None else [int(t) for t in tokens]
+        self.precision = precision
+        self.record_maps = record_maps
+        self._acc: Optional[torch.Tensor] = None  # [B', T, L, L] fp32 running sum of clamp(bicubic(map))
+        self._count = 0
+
+    # ---- hook.py:25-26 -------------------------------------------------------------------------------------
+    def clear(self):
+        self.cross_attn_maps.clear()
+        if self._acc is not None:
+            self._acc.zero_()
+        self._count = 0
+
+    @property
+    def num_maps(self) -> int:
+        return self._count
+
+    # ---- hook.py:59-81 -------------------------------------------------------------------------------------
+    def compute_global_heat_map(self) -> torch.Tensor:
+        """[B', T, latent_hw, latent_hw] fp32 (T = 77 rows, or len(tokens))."""
+        if self._count == 0 or self._acc is None:
+            raise RuntimeError('No heat maps found.')
+        return ops.heat_finalize(self._acc, self._count)
+
+    def _accumulate(self, b_kept: int, n_tok: int, device) -> torch.Tensor:
+        L = self.latent_hw
+        if self._acc is None or self._acc.shape != (b_kept, n_tok, L, L) or self._acc.device != device:
+            if self._count:
+                raise RuntimeError("heat-map batch/token shape changed between calls; call clear() first")
+            self._acc = torch.zeros((b_kept, n_tok, L, L), dtype=torch.float32, device=device)
+        return self._acc
+
+    # ---- hook.py:83-122 ------------------------------------------------------------------------------------
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
+        batch_size, sequence_length, _ = hidden_states.shape
+        attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
+        if attention_mask is not None:
+            raise NotImplementedError("agenda_b200: attention masks are not supported (the SD UNet passes none)")
+        query = attn.to_q(hidden_states)
+
+        is_cross_attn = encoder_hidden_states is not None
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif attn.norm_cross is not None:
+            encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
+
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        heads = attn.heads
+        scale = float(attn.scale)
+
+        if is_cross_attn:
+            M = key.shape[1]
+            n_tok = M if self.tokens is None else len(self.tokens)
+            b_first = 0 if self.is_train else batch_size // 2  # hook.py:48-49: drop the unconditional half
+            h = w = int(math.sqrt(sequence_length))
+            acc = self._accumulate(batch_size - b_first, n_tok, query.device)
+            if h == self.latent_hw and not self.record_maps:
+                # bicubic at scale 1 is the identity and probabilities are >= 0: accumulate from the epilogue
+                hidden_states = ops.attn_cross_heat(query, key, value, heads, acc, self.tokens, b_first,
+                                                    accumulate=True, scale=scale)
+            else:
+                maps = torch.empty((batch_size - b_first, n_tok, h, w), dtype=torch.float32, device=query.device)
+                hidden_states = ops.attn_cross_heat(query, key, value, heads, maps, self.tokens, b_first,
+                                                    accumulate=False, scale=scale)
+                ops.heat_upsample_accum(maps, acc)
+                if self.record_maps:
+                    self.cross_attn_maps.append(maps)
+            self._count += 1
+        else:
+            hidden_states = ops.attn_self(query, key, value, heads, scale=scale, precision=self.precision)
+
+        # linear proj
+        hidden_states = attn.to_out[0](hidden_states)
+        # dropout
+        hidden_states = attn.to_out[1](hidden_states)
+        return hidden_states
+
+
+# descriptive alias used in the docs
+B200CrossAttnProcessor = UNetCrossAttentionHooker

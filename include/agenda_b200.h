@@ -1,0 +1,126 @@
+/* agenda_b200.h — C ABI of libagenda_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the AGenDA heat-map data-generation hot path.  The reference
+ * (humansensinglab/AGenDA) is pure Python and has no FFI of its own; each entry point below
+ * replaces the Python code cited beside it (paths relative to the reference root).  The
+ * Python binding a maintainer adds on the reference side is a ctypes stub — see INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no framework types; device pointers unless stated "host".
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, nothing synchronises,
+ *     nothing allocates device memory, no global state is kept (TMA descriptors are built per call
+ *     on the host and passed by value to the kernel).
+ *   - returns 0 (AGENDA_OK) or a negative error code; agenda_last_error() gives a thread-local
+ *     human-readable message for the last failure on the calling thread.
+ *   - re-entrant across streams and devices (uses the calling thread's current device).
+ */
+#ifndef AGENDA_B200_H_
+#define AGENDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGENDA_OK 0
+#define AGENDA_ERR_NULL_POINTER (-1)
+#define AGENDA_ERR_BAD_SHAPE (-2)
+#define AGENDA_ERR_UNSUPPORTED (-3)
+#define AGENDA_ERR_MISALIGNED (-4)
+#define AGENDA_ERR_CUDA (-5)
+
+/* element types of Q/K/V/O */
+#define AGENDA_F32 0
+#define AGENDA_BF16 1
+
+/* ABI version (major*1000 + minor). */
+int agenda_version(void);
+/* Thread-local message for the last non-zero return on this thread ("" if none). */
+const char* agenda_last_error(void);
+/* 1 if the calling thread's current device is compute capability 10.x, else 0 (or a negative error). */
+int agenda_device_ok(void);
+
+/* ---- a2: attention core of UNetCrossAttentionHooker.__call__ (data_generation/hook.py:104-115) --------
+ * q [B,N,H*d], k/v [B,M,H*d], out [B,N,H*d]; row-major, token-major: head h owns columns [h*d,(h+1)*d)
+ * (this IS the layout to_q/to_k/to_v produce at hook.py:93,101-102 — head_to_batch_dim/batch_to_head_dim
+ * (hook.py:104-106,115) are folded into the kernels' addressing).  scale = d**-0.5 in the reference.
+ *
+ * Self-attention (encoder_hidden_states is None): flash-style fused softmax(scale*QK^T)V on tcgen05 tensor
+ * cores fed by TMA, fp32 softmax/accumulate.  dtype BF16 only; d in {40,64,80,160}; N>=1.  Replaces
+ * torch.baddbmm + softmax + torch.bmm (hook.py:108,114) without materialising [B*H,N,N].
+ */
+int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out, int dtype,
+                         int B, int H, int N, int d, float scale, void* stream);
+
+/* Test hook: agenda_attn_self_fwd (bf16) with the P operand routed explicitly: variant 0 = through TMEM (TS-form
+ * tcgen05.mma, the default), 1 = through a 128B-swizzled shared-memory tile (SS-form). */
+int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
+                                 int d, float scale, int variant, void* stream);
+
+/* Same contract in full fp32 on the CUDA cores (any d<=160, dtype F32 or BF16 inputs): the exact-precision
+ * path used for fp32 pipelines and for parity checks. */
+int agenda_attn_self_fwd_f32(const void* q, const void* k, const void* v, void* out, int dtype,
+                             int B, int H, int N, int d, float scale, void* stream);
+
+/* Cross-attention with the heat-map epilogue (hook.py:108-114 + _unravel_attn, hook.py:28-56).
+ * Besides out, writes for every kept batch element b >= b_first (b_first = B/2 when is_train is False,
+ * hook.py:48-49, else 0) and every selected key token t:
+ *     maps[b-b_first, t, n] (=|+=) mean over heads of softmax(scale*q k^T)[b, head, n, token_idx[t]]
+ * maps is fp32 [B-b_first, T, N].  token_idx: HOST int32[T], or NULL for "all M tokens in order" (T==M), the
+ * reference's behaviour.  accumulate!=0 adds into maps (used when N == latent_hw^2, where hook.py:72's
+ * bicubic resize is the identity and the clamp a no-op, so the epilogue accumulates straight into the
+ * persistent heat buffer); accumulate==0 overwrites (native-resolution scratch for
+ * agenda_heat_upsample_accum).  Softmax and the head mean are fp32.  M <= 128.
+ */
+int agenda_attn_cross_fwd_heat(const void* q, const void* k, const void* v, void* out, int dtype,
+                               int B, int H, int N, int M, int d, float scale,
+                               const int32_t* token_idx, int T, int b_first,
+                               float* maps, int accumulate, void* stream);
+
+/* ---- a4: compute_global_heat_map (data_generation/hook.py:59-81), streaming form ----------------------
+ * acc[i, y, x] += max(0, bicubic(maps[i])[y, x]) for i < n_planes; maps fp32 [n_planes,h,w] -> acc fp32
+ * [n_planes,L,L].  Bicubic = torch F.interpolate(mode='bicubic', align_corners=False): A=-0.75,
+ * src=(dst+0.5)*h/L-0.5, border-replicated taps. */
+int agenda_heat_upsample_accum(const float* maps, float* acc, int n_planes, int h, int w, int L,
+                               void* stream);
+/* out[i] = acc[i] / count  (torch.mean over the (layer x step) list, hook.py:79).  count>=1. */
+int agenda_heat_finalize(const float* acc, float* out, int64_t n_elems, int count, void* stream);
+
+/* ---- a7: data_generation/data_generation.py:82-85 --------------------------------------------------------
+ * u8 = uint8(trunc((h-min)/((max-min)+1e-8f)*255)) per map, all fp32, IEEE round-to-nearest, no FMA
+ * contraction (bit-exact with numpy).  heat fp32 [n,hw] -> out u8 [n,hw]. */
+int agenda_heat_normalize_u8(const float* heat, uint8_t* out, int n, int hw, void* stream);
+/* PIL Image.resize default (BICUBIC, a=-0.5, 8-bit two-pass fixed point, 22 fractional bits), bit-exact.
+ * in u8 [n,Hi,Wi] -> out u8 [n,Ho,Wo]. */
+int agenda_resize_bicubic_u8(const uint8_t* in, uint8_t* out, int n, int Hi, int Wi, int Ho, int Wo,
+                             void* stream);
+/* Fused normalise -> u8 -> resize: heat fp32 [n,Hi,Wi] -> out u8 [n,Ho,Wo]. */
+int agenda_heat_to_u8_image(const float* heat, uint8_t* out, int n, int Hi, int Wi, int Ho, int Wo,
+                            void* stream);
+
+/* ---- a8: data_generation/postprocess_heatmap.py:44-46 ----------------------------------------------------
+ * inv = 255 - bg; stack[...,0]=obj, [...,1]=fg, [...,2]=inv.  u8 [n,H,W] x3 -> stack u8 [n,H,W,3], inv u8
+ * [n,H,W] (inv may be NULL). */
+int agenda_stack_heatmaps_u8(const uint8_t* obj, const uint8_t* fg, const uint8_t* bg, uint8_t* stack,
+                             uint8_t* inv, int n, int H, int W, void* stream);
+/* a7+a8 fused for the (object, fg-token, bg-token) triple: heat fp32 [n,3,Hi,Wi] -> planes u8 [n,3,Ho,Wo]
+ * (the three daam_{word}_heatmaps PNG payloads; may be NULL), stack u8 [n,Ho,Wo,3], inv u8 [n,Ho,Wo] (may
+ * be NULL). */
+int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes, uint8_t* stack, uint8_t* inv, int n,
+                                  int Hi, int Wi, int Ho, int Wo, void* stream);
+
+/* ---- a9: threshold / connected components / bbox (NOT in the reference; spec SURVEY.md §8 a9) ------------
+ * Per map: nrm=(h-min)/((max-min)+1e-8f) fp32; mask = nrm > thr; 4-connectivity; labels 1..K in raster order
+ * of each component's first pixel (scipy.ndimage.label numbering); boxes[k] = {x, y, w, h, area}.
+ * heat fp32 [n,H,W]; labels int32 [n,H,W] (may be NULL); counts int32 [n] (= K, even when K > max_boxes);
+ * boxes int32 [n,max_boxes,5] (only the first min(K,max_boxes) rows are written).
+ * One thread-block cluster per map, the map resident in distributed shared memory: H*W*4 bytes must fit
+ * 16 CTAs x ~200 KB; otherwise AGENDA_ERR_UNSUPPORTED. */
+int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, int32_t* counts, int32_t* boxes,
+                    int max_boxes, int n, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGENDA_B200_H_ */

@@ -1,0 +1,172 @@
+"""GPU parity (through the C ABI) of the heat-map aggregation and post-processing kernels against the oracle and the
+golden vectors produced by the reference.  Integer/byte outputs must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hook_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from agenda_b200 import ops as _ops
+    return _ops
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---------------------------------------------------------------- a4: hook.py:59-81 ---------------------------
+
+def test_global_heat_map_golden(ops, golden_dir):
+    g = _g(golden_dir, "hook_global.npz")
+    acc = torch.zeros((1, 5, 64, 64), device="cuda")
+    for i in range(6):
+        ops.heat_upsample_accum(cuda(g[f"map{i}"]), acc)
+    out = ops.heat_finalize(acc, 6).cpu().numpy()
+    np.testing.assert_allclose(out, g["global"], rtol=0, atol=1e-5)  # stated tolerance 1e-4; we hold 1e-5
+    acc = torch.zeros((1, 2, 96, 96), device="cuda")
+    for i in range(4):
+        ops.heat_upsample_accum(cuda(g[f"l96_map{i}"]), acc)
+    np.testing.assert_allclose(ops.heat_finalize(acc, 4).cpu().numpy(), g["l96_global"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("h,L", [(8, 64), (16, 64), (32, 64), (64, 64), (12, 96), (24, 64), (7, 20)])
+def test_upsample_accum_vs_oracle(ops, h, L):
+    rng = np.random.default_rng(h * 100 + L)
+    m = (rng.standard_normal((3, 2, h, h)) * 0.3).astype(np.float32)  # signed: exercises the clamp
+    acc0 = rng.random((3, 2, L, L), dtype=np.float32)
+    acc = cuda(acc0)
+    ops.heat_upsample_accum(cuda(m), acc)
+    ref = acc0 + np.maximum(O.bicubic_upsample(m, L), 0)
+    np.testing.assert_allclose(acc.cpu().numpy(), ref, rtol=0, atol=2e-6)
+
+
+# ---------------------------------------------------------------- a7 / a8 ---------------------------------------
+
+def test_normalize_resize_stack_golden(ops, golden_dir):
+    g = _g(golden_dir, "post.npz")
+    heat = cuda(g["heat"])
+    u8 = ops.heat_normalize_u8(heat)
+    assert np.array_equal(u8.cpu().numpy(), g["u8"])
+    assert np.array_equal(ops.resize_bicubic_u8(u8, 112).cpu().numpy(), g["png112"])
+    assert np.array_equal(ops.heat_to_u8_image(heat, 112).cpu().numpy(), g["png112"])
+    assert np.array_equal(ops.resize_bicubic_u8(u8[0], 200).cpu().numpy(), g["png64to200"])
+    assert np.array_equal(ops.resize_bicubic_u8(u8[0], 48).cpu().numpy(), g["png64to48"])
+    png = cuda(g["png112"])
+    stack, inv = ops.stack_heatmaps_u8(png[0], png[4], png[5])
+    assert np.array_equal(stack.cpu().numpy(), g["stack"]) and np.array_equal(inv.cpu().numpy(), g["inv_bg"])
+    planes, stack2, inv2 = ops.heat_postprocess_stack(heat[[0, 4, 5]][None], 112)
+    assert np.array_equal(planes.cpu().numpy()[0], g["png112"][[0, 4, 5]])
+    assert np.array_equal(stack2.cpu().numpy()[0], g["stack"]) and np.array_equal(inv2.cpu().numpy()[0], g["inv_bg"])
+
+
+@pytest.mark.parametrize("shape,size", [((5, 64, 64), (112, 112)), ((2, 96, 96), (112, 112)), ((3, 64, 64), (64, 64)),
+                                        ((2, 64, 64), (33, 97)), ((2, 17, 40), (112, 5)), ((1, 128, 128), (64, 64))])
+def test_resize_matches_pil(ops, shape, size):
+    rng = np.random.default_rng(sum(shape) + sum(size))
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    out = ops.resize_bicubic_u8(cuda(img), size).cpu().numpy()
+    from PIL import Image
+    for i in range(shape[0]):
+        ref = np.asarray(Image.fromarray(img[i]).resize((size[1], size[0])))
+        assert np.array_equal(out[i], ref)
+
+
+def test_normalize_random_and_stack_sizes(ops):
+    rng = np.random.default_rng(11)
+    heat = (rng.standard_normal((64, 64, 64)) ** 2).astype(np.float32)
+    heat[3] *= 1e-7
+    heat[5] = 3.0
+    got = ops.heat_normalize_u8(cuda(heat)).cpu().numpy()
+    for i in range(heat.shape[0]):
+        assert np.array_equal(got[i], O.normalize_u8(heat[i])), i
+    full = ops.heat_to_u8_image(cuda(heat), 112).cpu().numpy()
+    for i in range(0, 64, 7):
+        assert np.array_equal(full[i], O.heat_to_png_array(heat[i], 112)), i
+    for (n, H, W) in [(4, 112, 112), (3, 7, 5), (1, 1, 1)]:
+        a, b, c = (rng.integers(0, 256, (n, H, W), dtype=np.uint8) for _ in range(3))
+        st, inv = ops.stack_heatmaps_u8(cuda(a), cuda(b), cuda(c))
+        for i in range(n):
+            rs, ri = O.stack_heatmaps(a[i], b[i], c[i])
+            assert np.array_equal(st[i].cpu().numpy(), rs) and np.array_equal(inv[i].cpu().numpy(), ri)
+
+
+# ---------------------------------------------------------------- a9: CCL + bbox --------------------------------
+
+def _check_ccl(ops, heat, thr=0.5, max_boxes=512):
+    labels, counts, boxes = ops.ccl_bbox(cuda(heat), thr, max_boxes=max_boxes)
+    labels, counts, boxes = labels.cpu().numpy(), counts.cpu().numpy(), boxes.cpu().numpy()
+    for i in range(heat.shape[0]):
+        rl, rb = O.ccl_bbox(heat[i], thr)
+        assert counts[i] == rb.shape[0], (i, counts[i], rb.shape[0])
+        assert np.array_equal(labels[i], rl), i
+        k = min(rb.shape[0], max_boxes)
+        assert np.array_equal(boxes[i, :k], rb[:k]), i
+
+
+def test_ccl_synthetic_512(ops):
+    _check_ccl(ops, O.synthetic_heatmaps(12, 512, seed=0))
+
+
+@pytest.mark.parametrize("size", [64, 112, 256])
+def test_ccl_synthetic_small(ops, size):
+    _check_ccl(ops, O.synthetic_heatmaps(6, size, seed=size))
+
+
+def test_ccl_edge_cases(ops):
+    rng = np.random.default_rng(5)
+    H = W = 512
+    empty = np.full((H, W), 0.3, np.float32)                 # constant map -> n = 0 everywhere -> no component
+    full = np.zeros((H, W), np.float32); full[0, 0] = -1.0    # everything but one pixel is foreground
+    checker = ((np.indices((H, W)).sum(0) & 1) * 1.0).astype(np.float32)  # worst case: H*W/2 components
+    stripes_v = np.zeros((H, W), np.float32); stripes_v[:, ::2] = 1.0     # columns spanning every strip
+    stripes_h = np.zeros((H, W), np.float32); stripes_h[::2, :] = 1.0
+    spiral = np.zeros((H, W), np.float32)
+    for k in range(0, 250, 4):                                 # nested rectangles joined into one long snake
+        spiral[k, k:W - k] = 1; spiral[H - 1 - k, k:W - k] = 1; spiral[k:H - k, k] = 1; spiral[k:H - k, W - 1 - k] = 1
+        spiral[k + 1:k + 4, k + 2] = 1
+    noise = rng.random((H, W), dtype=np.float32)              # salt and pepper around the threshold
+    nan = rng.random((H, W), dtype=np.float32); nan[100, 100] = np.nan
+    heat = np.stack([empty, full, checker, stripes_v, stripes_h, spiral, noise, nan])
+    _check_ccl(ops, heat, 0.5, max_boxes=64)
+
+
+@pytest.mark.parametrize("H,W", [(61, 45), (1, 1), (1, 300), (300, 1), (33, 32), (200, 1000), (1024, 512), (96, 96)])
+def test_ccl_ragged_shapes(ops, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    heat = rng.random((3, H, W), dtype=np.float32)
+    heat[1] = (heat[1] > 0.35) * 1.0  # dense blobs
+    _check_ccl(ops, heat, 0.5, max_boxes=128)
+
+
+def test_ccl_threshold_values_and_no_labels(ops):
+    heat = O.synthetic_heatmaps(3, 128, seed=9)
+    for thr in (0.0, 0.25, 0.9, 1.0):
+        _check_ccl(ops, heat, thr)
+    _, counts, boxes = ops.ccl_bbox(cuda(heat), 0.5, max_boxes=64, want_labels=False)
+    for i in range(3):
+        rl, rb = O.ccl_bbox(heat[i], 0.5)
+        assert counts[i].item() == rb.shape[0]
+        assert np.array_equal(boxes[i, :rb.shape[0]].cpu().numpy(), rb)
+
+
+def test_errors_are_loud(ops):
+    from agenda_b200._lib import AgendaError
+    with pytest.raises(RuntimeError):
+        ops.heat_normalize_u8(torch.zeros(4, 4))  # CPU tensor: no fallback
+    with pytest.raises(AgendaError):
+        ops.ccl_bbox(torch.zeros((1, 4096, 4096), device="cuda"))  # does not fit a cluster's shared memory
+    with pytest.raises(AgendaError):
+        ops.heat_upsample_accum(torch.zeros((1, 8, 8), device="cuda"), torch.zeros((1, 30, 30), device="cuda"))
