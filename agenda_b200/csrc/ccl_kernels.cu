@@ -327,7 +327,8 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
       if (v & kRankFlag) id = v & ~kRankFlag;
       else { id = *CL.slot(v) & ~kRankFlag; L[i] = kRankFlag | id; }
       if (mybox && static_cast<int>(id) <= n_box) {
-        const int len = __ffs(~(m >> lane)) - 1;
+        const uint32_t run_end = ~(m >> lane);  // first zero at/after this lane; a full segment from lane 0 has none
+        const int len = run_end ? __ffs(run_end) - 1 : 32;
         int32_t* b = mybox + (id - 1) * 5;
         atomicMin(b + 0, x); atomicMin(b + 1, r0 + y);
         atomicMax(b + 2, x + len - 1); atomicMax(b + 3, r0 + y);

@@ -162,9 +162,9 @@ struct ResizeSmem {
 __host__ __device__ inline size_t resize_smem_bytes(int Hi, int Wi, int Ho, int Wo, int out_planes) {
   const int ksx = pil_ksize(Wi, Wo), ksy = pil_ksize(Hi, Ho);
   size_t ints = static_cast<size_t>(2 * Wo + Wo * ksx + 2 * Ho + Ho * ksy);
-  size_t bytes = ints * 4 + static_cast<size_t>(Hi) * Wi + static_cast<size_t>(Hi) * Wo +
-                 static_cast<size_t>(out_planes) * Ho * Wo;
-  return (bytes + 15) & ~static_cast<size_t>(15);
+  auto al = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
+  return al(ints * 4) + al(static_cast<size_t>(Hi) * Wi) + al(static_cast<size_t>(Hi) * Wo) +
+         al(static_cast<size_t>(out_planes) * Ho * Wo);
 }
 __device__ inline ResizeSmem carve(unsigned char* base, int Hi, int Wi, int Ho, int Wo, int ksx, int ksy) {
   ResizeSmem s;
@@ -173,9 +173,10 @@ __device__ inline ResizeSmem carve(unsigned char* base, int Hi, int Wi, int Ho, 
   s.kx = p; p += Wo * ksx;
   s.by = p; p += 2 * Ho;
   s.ky = p; p += Ho * ksy;
-  s.in = reinterpret_cast<uint8_t*>(p);
-  s.tmp = s.in + Hi * Wi;
-  s.out = s.tmp + Hi * Wo;
+  auto al = [](uintptr_t v) { return (v + 15) & ~static_cast<uintptr_t>(15); };
+  s.in = reinterpret_cast<uint8_t*>(al(reinterpret_cast<uintptr_t>(p)));
+  s.tmp = reinterpret_cast<uint8_t*>(al(reinterpret_cast<uintptr_t>(s.in + Hi * Wi)));
+  s.out = reinterpret_cast<uint8_t*>(al(reinterpret_cast<uintptr_t>(s.tmp + Hi * Wo)));
   return s;
 }
 

@@ -1,0 +1,120 @@
+"""The hot path end to end, as one callable: (UNet attention hidden states, prompt context) -> heat maps ->
+u8 stacks + boxes.  This is the public API `bench.py` measures and the generation driver
+(`agenda_b200/data_generation.py`) uses.
+
+One `HeatmapPipeline.run_*` call == what the reference does for a batch of images between
+`with daam.trace(pipeline)` and the PNG writes (data_generation.py:57-86) plus `postprocess_heatmap.py:44-46`,
+with the attention processor of hook.py:83-122 doing the capture — minus the non-attention UNet layers, which
+are out of scope (SURVEY.md §8 f N4): the 32 attention calls of every denoising step are fed synthetic hidden
+states of the right shapes.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .processor import UNetCrossAttentionHooker
+from .sd_attention import AttentionStack, BlockSpec, sd15_blocks, sd21_blocks
+
+
+class HeatmapPipeline:
+    def __init__(self, blocks: Optional[List[BlockSpec]] = None, context_dim: int = 768,
+                 tokens: Sequence[int] = (5, 6, 7), num_steps: int = 50, latent_hw: int = 64, image_size: int = 112,
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", thr: float = 0.5, max_boxes: int = 64,
+                 seed: int = 0, precision: str = "bf16", use_cuda_graph: bool = True):
+        self.device = torch.device(device)
+        self.blocks = blocks if blocks is not None else sd15_blocks(latent_hw)
+        self.stack = AttentionStack(self.blocks, context_dim, seed).to(device=self.device, dtype=dtype)
+        self.tokens = list(tokens)
+        if len(self.tokens) < 3:
+            raise ValueError("need at least (object, fg, bg) token indices")
+        self.num_steps = num_steps
+        self.latent_hw = latent_hw
+        self.image_size = image_size
+        self.dtype = dtype
+        self.thr = thr
+        self.max_boxes = max_boxes
+        self.proc = UNetCrossAttentionHooker(is_train=False, latent_hw=latent_hw, tokens=self.tokens,
+                                             precision=precision)
+        self.stack.set_attn_processor(self.proc)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._graph_key = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def make_inputs(self, n_images: int, seed: int = 0, pinned_host: bool = False):
+        """Synthetic inputs for `n_images` (UNet batch = 2*n_images with classifier-free guidance)."""
+        hs, ctx = self.stack.make_inputs(2 * n_images, "cpu", self.dtype, seed)
+        if pinned_host:
+            return {k: v.pin_memory() for k, v in hs.items()}, ctx.pin_memory()
+        return {k: v.to(self.device) for k, v in hs.items()}, ctx.to(self.device)
+
+    @torch.no_grad()
+    def run_device(self, hs: Dict, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """All tensors on the device.  Returns heat [n,T,L,L] fp32, planes u8 [n,3,S,S], stack u8 [n,S,S,3], inv u8
+        [n,S,S], counts int32 [n], boxes int32 [n,max_boxes,5] (x,y,w,h,area on the object-token map)."""
+        proc = self.proc
+        proc.clear()
+        key = (tuple((k, v.data_ptr()) for k, v in sorted(hs.items())), ctx.data_ptr())
+        if self.use_cuda_graph:
+            if self._graph is None or self._graph_key != key:
+                # warm the allocator/cuBLAS handles outside capture, then capture one denoising step's 32 calls
+                self.stack(hs, ctx)
+                proc.clear()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.stack(hs, ctx)
+                self._graph, self._graph_key = g, key
+                self._maps_per_step = proc.num_maps
+                proc.clear()
+            for _ in range(self.num_steps):
+                self._graph.replay()
+            proc._count = self._maps_per_step * self.num_steps
+        else:
+            for _ in range(self.num_steps):
+                self.stack(hs, ctx)
+        heat = proc.compute_global_heat_map()                       # hook.py:59-81
+        planes, stack, inv = ops.heat_postprocess_stack(heat[:, :3].contiguous(), self.image_size)
+        _, counts, boxes = ops.ccl_bbox(heat[:, 0].contiguous(), self.thr, self.max_boxes, want_labels=False)
+        return {"heat": heat, "planes": planes, "stack": stack, "inv": inv, "counts": counts, "boxes": boxes}
+
+    @torch.no_grad()
+    def run_host(self, hs_host: Dict, ctx_host: torch.Tensor, staging: Optional[Dict] = None) -> Dict:
+        """Host buffers in (pinned), host buffers out: H2D of the step's inputs, the hot path, D2H of the results.
+        `staging` (from make_staging) provides persistent device/pinned buffers so the CUDA graph stays valid."""
+        if staging is None:
+            staging = self.make_staging(hs_host, ctx_host)
+        for k, v in hs_host.items():
+            staging["hs"][k].copy_(v, non_blocking=True)
+        staging["ctx"].copy_(ctx_host, non_blocking=True)
+        out = self.run_device(staging["hs"], staging["ctx"])
+        host = staging["out"]
+        for name in ("stack", "inv", "planes", "counts", "boxes", "heat"):
+            if name not in host:
+                host[name] = torch.empty(out[name].shape, dtype=out[name].dtype).pin_memory()
+            host[name].copy_(out[name], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
+
+    def make_staging(self, hs_host: Dict, ctx_host: torch.Tensor) -> Dict:
+        return {"hs": {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in hs_host.items()},
+                "ctx": torch.empty(ctx_host.shape, dtype=ctx_host.dtype, device=self.device), "out": {}}
+
+    @staticmethod
+    def h2d_bytes(hs_host: Dict, ctx_host: torch.Tensor) -> int:
+        return sum(v.numel() * v.element_size() for v in hs_host.values()) + ctx_host.numel() * ctx_host.element_size()
+
+    @staticmethod
+    def d2h_bytes(host_out: Dict) -> int:
+        return sum(v.numel() * v.element_size() for v in host_out.values())
+
+
+def sd15_pipeline(**kw) -> HeatmapPipeline:
+    return HeatmapPipeline(sd15_blocks(kw.pop("latent_hw", 64)), 768, latent_hw=64, **kw)
+
+
+def sd21_pipeline(**kw) -> HeatmapPipeline:
+    return HeatmapPipeline(sd21_blocks(96), 1024, latent_hw=96, **kw)
