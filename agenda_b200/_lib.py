@@ -30,6 +30,9 @@ _SIGNATURES = {
                                  c_void_p],
     "agenda_attn_cross_fwd_heat": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int, c_void_p],
+    "agenda_attn_cross_fwd_heat_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int,
+                                       c_void_p],
     "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_heat_finalize": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "agenda_heat_normalize_u8": [c_void_p, c_void_p, c_int, c_int, c_void_p],
@@ -69,8 +72,22 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+launches = 0          # number of kernel launches issued through the C ABI (every entry point launches exactly one)
+event_sink = None     # bench.py: {entry_point_name: [(start_event, end_event, args), ...]} to time single kernels
+
+
 def call(name: str, *args) -> None:
+    global launches
     lib = load()
+    sink = event_sink.get(name) if event_sink is not None else None
+    if sink is not None:
+        import torch
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise AgendaError(rc, lib.agenda_last_error().decode("utf-8", "replace"))
+    launches += 1
+    if sink is not None:
+        end.record()
+        sink.append((start, end, args))

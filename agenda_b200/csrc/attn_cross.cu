@@ -3,16 +3,13 @@
 #include "common.cuh"
 
 namespace agenda {
-constexpr int kMaxTokens = 128;
-struct TokenList {
-  int n;
-  int idx[kMaxTokens];
-};
 int attn_common_checks(const char* who, const void* q, const void* k, const void* v, void* out, int dtype, int B,
                        int H, int N, int M, int d);
 int build_token_list(const char* who, const int32_t* token_idx, int T, int M, TokenList* tl);
 int attn_cross_f32(const void* q, const void* k, const void* v, void* out, int dtype, int B, int H, int N, int M,
                    int d, float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream);
+int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
+                     float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream);
 }  // namespace agenda
 
 using namespace agenda;
@@ -29,6 +26,27 @@ extern "C" int agenda_attn_cross_fwd_heat(const void* q, const void* k, const vo
     rc = build_token_list("attn_cross_fwd_heat", token_idx, T, M, &tl);
     if (rc != AGENDA_OK) return rc;
     if (reinterpret_cast<uintptr_t>(maps) & 3) return fail(AGENDA_ERR_MISALIGNED, "attn_cross_fwd_heat: maps");
+  }
+  float* mp = tl.n ? maps : nullptr;
+  // bf16 activations: tcgen05 tensor-core kernel (products of bf16 operands are exact in its fp32 accumulators, so
+  // the heat maps keep fp32-softmax accuracy).  fp32 activations: the exact fp32 CUDA-core kernel.
+  if (dtype == AGENDA_BF16 && M <= 80 && (d == 40 || d == 64 || d == 80 || d == 160))
+    return attn_cross_sm100(q, k, v, out, B, H, N, M, d, scale, tl, b_first, mp, accumulate, stream);
+  return attn_cross_f32(q, k, v, out, dtype, B, H, N, M, d, scale, tl, b_first, mp, accumulate, stream);
+}
+
+// Test hook: force the fp32 CUDA-core kernel regardless of dtype.
+extern "C" int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, void* out, int dtype, int B,
+                                              int H, int N, int M, int d, float scale, const int32_t* token_idx,
+                                              int T, int b_first, float* maps, int accumulate, void* stream) {
+  int rc = attn_common_checks("attn_cross_fwd_heat_f32", q, k, v, out, dtype, B, H, N, M, d);
+  if (rc != AGENDA_OK) return rc;
+  if (b_first < 0 || b_first > B) return fail(AGENDA_ERR_BAD_SHAPE, "attn_cross_fwd_heat_f32: b_first=%d", b_first);
+  TokenList tl;
+  tl.n = 0;
+  if (maps != nullptr) {
+    rc = build_token_list("attn_cross_fwd_heat_f32", token_idx, T, M, &tl);
+    if (rc != AGENDA_OK) return rc;
   }
   return attn_cross_f32(q, k, v, out, dtype, B, H, N, M, d, scale, tl, b_first, tl.n ? maps : nullptr, accumulate,
                         stream);

@@ -1,0 +1,283 @@
+// K2: fused cross-attention + heat-map epilogue for sm_100a (tcgen05 / TMEM / TMA).
+//
+//   out  = softmax(scale * Q K^T) V                                    (data_generation/hook.py:108,114)
+//   maps[b', t, n] (=|+=) mean_h softmax(...)[b, h, n, token_idx[t]]    (_unravel_attn, hook.py:28-56)
+//
+// The key axis is the 77-token prompt: ONE KV tile (padded to 80 by TMA zero fill), so there is no online softmax.
+// CTA = one (batch element, 128-query tile) and loops over ALL heads, which makes the head mean a deterministic
+// in-register sum (no atomics, no [B*H,N,77] probability tensor, no 77-iteration Python loop):
+//   warps 0-3  softmax warpgroup, thread r <-> query row r: S row (80 fp32) from TMEM, exp2, normalise, add the row
+//              into a per-thread 80-float heat accumulator, write P (bf16) back into TMEM over S; then drain the
+//              previous head's O (TMEM -> bf16 -> global) while the tensor core runs this head's P V.
+//   warp 4     TMA producer: (Q_h, K_h, V_h) per head through a 2/3-stage mbarrier ring
+//   warp 5     TMEM allocator + tcgen05.mma issuer: QK_0, QK_1, PV_0, QK_2, PV_1, ...
+// TMEM: S/P[2] (96 columns each) | O[2] (round16(d) columns each).
+// At the end each thread parks its accumulator in its own shared-memory row and emits the selected token columns:
+// consecutive threads = consecutive pixels, so every token plane is written with coalesced 128-byte stores.
+#include "sm100_common.cuh"
+
+namespace agenda {
+
+
+namespace sm100 {
+
+constexpr int kXBlockM = 128;
+constexpr int kXThreads = 192;
+constexpr int kXMPad = 80;      // 77 prompt tokens padded to a multiple of 16
+constexpr int kXSlot = 96;      // TMEM columns reserved per S/P buffer
+constexpr int kHeatLd = 81;     // padded accumulator row in shared memory (bank-conflict free)
+
+template <int D>
+struct XCfg {
+  static constexpr int kDP = (D + 15) / 16 * 16;
+  static constexpr int kChunks = (D + 63) / 64;
+  static constexpr int kStages = (D <= 80) ? 3 : 2;
+  static constexpr int kQBytes = kChunks * kXBlockM * 128;
+  static constexpr int kKVBytes = kChunks * kXMPad * 128;
+  static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
+  static constexpr int kColO = 2 * kXSlot;
+  static_assert(kColO + 2 * kDP <= 512, "TMEM overflow");
+  static_assert(kStages * kStageBytes >= kXBlockM * kHeatLd * 4, "heat staging does not fit");
+};
+
+struct XBarriers {
+  uint64_t in_full[3], in_empty[3];
+  uint64_t s_full[2], p_full[2], pv_done[2], o_free[2];
+  uint32_t tmem_base;
+};
+
+template <int D>
+constexpr size_t x_smem_bytes() {
+  return 1024 + XCfg<D>::kStages * XCfg<D>::kStageBytes + sizeof(XBarriers) + 64;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kXThreads, 1)
+attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                        const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out,
+                        float* __restrict__ maps, const TokenList tl, int H, int N, int M, int b_first,
+                        int accumulate, float scale_log2) {
+  using C = XCfg<D>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  XBarriers* bars = reinterpret_cast<XBarriers*>(smem + C::kStages * C::kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * kXBlockM;
+  const int b = blockIdx.y;
+  const bool want_heat = (maps != nullptr) && (b >= b_first);
+
+  if (tid == 4 * 32) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    for (int s = 0; s < 3; ++s) { mbar_init(&bars->in_full[s], 1); mbar_init(&bars->in_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->s_full[s], 1); mbar_init(&bars->p_full[s], 128);
+      mbar_init(&bars->pv_done[s], 1); mbar_init(&bars->o_free[s], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      for (int h = 0; h < H; ++h) {
+        const int st = h % C::kStages;
+        const uint32_t ph = (h / C::kStages) & 1;
+        unsigned char* sQ = smem + st * C::kStageBytes;
+        unsigned char* sK = sQ + C::kQBytes;
+        unsigned char* sV = sK + C::kKVBytes;
+        mbar_wait(&bars->in_empty[st], ph ^ 1);
+        mbar_expect_tx(&bars->in_full[st], C::kStageBytes);
+        for (int c = 0; c < C::kChunks; ++c) {
+          tma_load_4d(&map_q, &bars->in_full[st], sQ + c * kXBlockM * 128, c * 64, h, q0, b);
+          tma_load_4d(&map_k, &bars->in_full[st], sK + c * kXMPad * 128, c * 64, h, 0, b);
+          tma_load_4d(&map_v, &bars->in_full[st], sV + c * kXMPad * 128, c * 64, h, 0, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kXBlockM, kXMPad, 0);
+      constexpr uint32_t idesc_pv = make_idesc(kXBlockM, C::kDP, 1);
+      auto issue_pv = [&](int h) {
+        const int sb = h & 1, st = h % C::kStages;
+        const uint32_t ph = (h >> 1) & 1;
+        mbar_wait(&bars->p_full[sb], ph);
+        mbar_wait(&bars->o_free[sb], ph ^ 1);  // O[sb] drained by the epilogue of head h-2
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem + st * C::kStageBytes + C::kQBytes + C::kKVBytes);
+#pragma unroll
+        for (int kk = 0; kk < kXMPad / 16; ++kk) {
+          const uint64_t bdesc = make_sdesc(v_addr + kk * 2048, kXMPad * 128, 1024);
+          umma_ts(tmem + C::kColO + sb * C::kDP, tmem + sb * kXSlot + kk * 8, bdesc, idesc_pv, kk != 0);
+        }
+        umma_commit(&bars->in_empty[st]);
+        umma_commit(&bars->pv_done[sb]);
+      };
+      for (int h = 0; h < H; ++h) {
+        const int sb = h & 1, st = h % C::kStages;
+        mbar_wait(&bars->in_full[st], (h / C::kStages) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(smem + st * C::kStageBytes);
+        const uint32_t k_addr = q_addr + C::kQBytes;
+#pragma unroll
+        for (int kk = 0; kk < C::kDP / 16; ++kk) {
+          const uint64_t adesc = make_sdesc(q_addr + (kk >> 2) * kXBlockM * 128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_sdesc(k_addr + (kk >> 2) * kXMPad * 128 + (kk & 3) * 32, 16, 1024);
+          umma_ss(tmem + sb * kXSlot, adesc, bdesc, idesc_qk, kk != 0);
+        }
+        umma_commit(&bars->s_full[sb]);
+        if (h > 0) issue_pv(h - 1);
+      }
+      issue_pv(H - 1);
+    }
+  } else {
+    // ============================== softmax warpgroup (thread == query row) ==============================
+    const int row = tid;
+    const int n = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    float acc[kXMPad];
+#pragma unroll
+    for (int i = 0; i < kXMPad; ++i) acc[i] = 0.f;
+
+    auto drain_o = [&](int g) {  // O of head g: TMEM -> bf16 -> global
+      const int ob = g & 1;
+      mbar_wait(&bars->pv_done[ob], (g >> 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + g * D;
+#pragma unroll
+      for (int c = 0; c < C::kDP / 16; ++c) {
+        float o[16];
+        tmem_ld16(tmem + lane_base + C::kColO + ob * C::kDP + c * 16, o);
+        tmem_wait_ld();
+        if (n < N) {
+          uint4 lo, hi;
+          lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
+          hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
+          if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+          if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->o_free[ob]);
+    };
+
+    for (int h = 0; h < H; ++h) {
+      const int sb = h & 1;
+      mbar_wait(&bars->s_full[sb], (h >> 1) & 1);
+      tc_fence_after();
+      float sv[kXSlot];
+      const uint32_t s_taddr = tmem + lane_base + sb * kXSlot;
+      tmem_ld32(s_taddr, sv);
+      tmem_ld32(s_taddr + 32, sv + 32);
+      tmem_ld16(s_taddr + 64, sv + 64);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < kXMPad; ++i)
+        if (i >= M) sv[i] = -INFINITY;
+      float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+      for (int i = 4; i < kXMPad; i += 4) {
+        mx0 = fmaxf(mx0, sv[i]); mx1 = fmaxf(mx1, sv[i + 1]); mx2 = fmaxf(mx2, sv[i + 2]); mx3 = fmaxf(mx3, sv[i + 3]);
+      }
+      const float m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < kXMPad; i += 2) {
+        sv[i] = ex2(fmaf(sv[i], scale_log2, -m));
+        sv[i + 1] = ex2(fmaf(sv[i + 1], scale_log2, -m));
+        sum0 += sv[i]; sum1 += sv[i + 1];
+      }
+      const float inv_l = 1.0f / (sum0 + sum1);
+#pragma unroll
+      for (int i = 0; i < kXMPad; ++i) sv[i] *= inv_l;  // normalised probabilities: PV needs no later division
+      if (want_heat) {
+#pragma unroll
+        for (int i = 0; i < kXMPad; ++i) acc[i] += sv[i];
+      }
+#pragma unroll
+      for (int i = kXMPad; i < kXSlot; ++i) sv[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < kXSlot / 32; ++c) {
+        uint32_t u[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = pack_bf16(sv[c * 32 + 2 * i], sv[c * 32 + 2 * i + 1]);
+        tmem_st16(s_taddr + c * 16, u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[sb]);
+      if (h > 0) drain_o(h - 1);
+    }
+    drain_o(H - 1);
+
+    // ---- heat epilogue: mean over heads, selected token columns, coalesced per token plane ----
+    if (want_heat) {
+      // all MMAs and TMA loads of this CTA have completed (pv_done of the last head was observed)
+      float* srow = reinterpret_cast<float*>(smem) + row * kHeatLd;
+#pragma unroll
+      for (int i = 0; i < kXMPad; ++i) srow[i] = acc[i];
+      const float inv_h = 1.0f / static_cast<float>(H);
+      float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n;
+      if (n < N) {
+        for (int t = 0; t < tl.n; ++t) {
+          const float val = srow[tl.idx[t]] * inv_h;
+          float* ptr = dst + static_cast<long long>(t) * N;
+          *ptr = accumulate ? (*ptr + val) : val;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace sm100
+
+template <int D>
+static int launch_cross(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, float scale,
+                        const TokenList& tl, int b_first, float* maps, int accumulate, cudaStream_t stream) {
+  using C = sm100::XCfg<D>;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, sm100::kXBlockM)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, M, D, sm100::kXMPad)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, M, D, sm100::kXMPad)) != AGENDA_OK) return rc;
+  constexpr size_t smem = sm100::x_smem_bytes<D>();
+  auto kern = sm100::attn_cross_sm100_kernel<D>;
+  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid((N + sm100::kXBlockM - 1) / sm100::kXBlockM, B);
+  kern<<<grid, sm100::kXThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), maps, tl, H, N, M,
+                                                 b_first, accumulate, scale * 1.4426950408889634f);
+  AGENDA_LAUNCH_CHECK("attn_cross_sm100_kernel");
+  return AGENDA_OK;
+}
+
+// bf16 tensor-core path; returns AGENDA_ERR_UNSUPPORTED for shapes it does not cover.
+int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
+                     float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M > sm100::kXMPad) return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross (tensor-core path): M=%d > %d", M, sm100::kXMPad);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_cross_fwd_heat: q/k/v/out must be 16-byte aligned");
+  switch (d) {
+    case 40: return launch_cross<40>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);
+    case 64: return launch_cross<64>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);
+    case 80: return launch_cross<80>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);
+    case 160: return launch_cross<160>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);
+    default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross (tensor-core path): head dim %d not in {40,64,80,160}", d);
+  }
+}
+
+}  // namespace agenda

@@ -16,12 +16,6 @@ constexpr int kRPW = kTQ / kWarps;  // rows per warp
 constexpr int kTK = 128;       // keys per shared-memory tile
 constexpr int kMaxD = 160;
 constexpr int kMaxDJ = kMaxD / 32;  // output columns per lane
-constexpr int kMaxTokens = 128;
-
-struct TokenList {
-  int n;
-  int idx[kMaxTokens];
-};
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -37,6 +37,13 @@ inline int num_sms() {
   return n > 0 ? n : 148;
 }
 
+constexpr int kMaxTokens = 128;
+// heat-map token selection, passed to kernels by value
+struct TokenList {
+  int n;
+  int idx[kMaxTokens];
+};
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));

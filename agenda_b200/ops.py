@@ -64,7 +64,7 @@ def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 
 def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, maps: Optional[torch.Tensor],
                     token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
-                    scale: Optional[float] = None) -> torch.Tensor:
+                    scale: Optional[float] = None, force_f32_kernel: bool = False) -> torch.Tensor:
     """Cross-attention + heat epilogue (hook.py:108-114 and _unravel_attn hook.py:28-56).
 
     maps: fp32 [B-b_first, T, N] written (accumulate=False) or added to (accumulate=True), T = len(token_idx) or
@@ -88,7 +88,7 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
         mp = maps.data_ptr()
     else:
         T, idx, mp = 0, None, None
-    _lib.call("agenda_attn_cross_fwd_heat", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
+    _lib.call("agenda_attn_cross_fwd_heat_f32" if force_f32_kernel else "agenda_attn_cross_fwd_heat", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
               B, heads, N, M, d, scale, idx, T, int(b_first), mp, int(bool(accumulate)), _stream())
     return out
 

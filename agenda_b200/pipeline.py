@@ -65,8 +65,11 @@ class HeatmapPipeline:
                 proc.clear()
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                from . import _lib
+                l0 = _lib.launches
                 with torch.cuda.graph(g):
                     self.stack(hs, ctx)
+                self._graph_launches = _lib.launches - l0  # C-ABI kernel nodes captured per denoising step
                 self._graph, self._graph_key = g, key
                 self._maps_per_step = proc.num_maps
                 proc.clear()
@@ -91,6 +94,7 @@ class HeatmapPipeline:
             staging["hs"][k].copy_(v, non_blocking=True)
         staging["ctx"].copy_(ctx_host, non_blocking=True)
         out = self.run_device(staging["hs"], staging["ctx"])
+        self.last_device_out = out
         host = staging["out"]
         for name in ("stack", "inv", "planes", "counts", "boxes", "heat"):
             if name not in host:

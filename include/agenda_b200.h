@@ -78,6 +78,13 @@ int agenda_attn_cross_fwd_heat(const void* q, const void* k, const void* v, void
                                const int32_t* token_idx, int T, int b_first,
                                float* maps, int accumulate, void* stream);
 
+/* Test hook: same contract, forcing the exact fp32 CUDA-core kernel (bf16 inputs otherwise take the tcgen05
+ * tensor-core kernel; fp32 inputs always take the fp32 kernel). */
+int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, void* out, int dtype,
+                                   int B, int H, int N, int M, int d, float scale,
+                                   const int32_t* token_idx, int T, int b_first,
+                                   float* maps, int accumulate, void* stream);
+
 /* ---- a4: compute_global_heat_map (data_generation/hook.py:59-81), streaming form ----------------------
  * acc[i, y, x] += max(0, bicubic(maps[i])[y, x]) for i < n_planes; maps fp32 [n_planes,h,w] -> acc fp32
  * [n_planes,L,L].  Bicubic = torch F.interpolate(mode='bicubic', align_corners=False): A=-0.75,

@@ -70,6 +70,36 @@ def test_cross_attention_heat_f32(ops, B, N, H, d, T, is_train):
     assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize("B,N,H,d,T", [(2, 64, 2, 40, None), (4, 256, 8, 40, [1, 5, 76]), (2, 100, 3, 64, [0]),
+                                        (2, 16, 1, 160, [3, 4]), (2, 1024, 8, 80, [7, 9, 11]), (2, 4096, 8, 40, [5, 6, 7]),
+                                        (4, 576, 5, 64, [1, 2, 3, 4]), (2, 256, 8, 160, None), (2, 130, 2, 40, [76])])
+@pytest.mark.parametrize("is_train", [False, True])
+def test_cross_attention_heat_tensor_core(ops, B, N, H, d, T, is_train):
+    """bf16 activations -> tcgen05 kernel.  Oracle runs in fp32 on the same bf16-rounded inputs; heat maps must hold
+    the fp32 tolerance (1e-4) because bf16 x bf16 products are exact in the fp32 accumulators."""
+    M = 77
+    q, k, v = _qkv(B, N, M, H, d, seed=N * 5 + d, gain=1.5)
+    q, k, v = q.bfloat16(), k.bfloat16(), (v * 0.25).bfloat16()
+    ref, p = O.attention_core(q.float(), k.float(), v.float(), H)
+    b_first = 0 if is_train else B // 2
+    toks = list(range(M)) if T is None else T
+    ref_maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)[:, toks]
+    maps = torch.full((B - b_first, len(toks), N), 7.0, device="cuda")
+    out = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=False).float().cpu()
+    assert (out - ref).abs().max().item() < TOL_BF16_OUT
+    assert (maps.cpu() - ref_maps).abs().max().item() < 2e-6  # well inside TOL_HEAT
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=True)
+    assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 4e-6
+    # the fp32 CUDA-core kernel agrees on the same inputs
+    maps32 = torch.empty_like(maps)
+    out32 = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps32, T, b_first, force_f32_kernel=True).float().cpu()
+    assert (out32 - ref).abs().max().item() < TOL_BF16_OUT
+    assert (maps32.cpu() - ref_maps).abs().max().item() < 2e-6
+    # no heat requested
+    out_nh = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, None).float().cpu()
+    assert torch.equal(out_nh, out)
+
+
 def _golden_modules(g, name, tag, ctx_dim):
     from agenda_b200.sd_attention import SDAttention
     heads = int(g[f"{name}_heads"])
