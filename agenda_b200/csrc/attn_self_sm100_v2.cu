@@ -1,0 +1,404 @@
+// K1 (v2): fused self-attention for sm_100a with TWO 128-query tiles per CTA and two softmax warpgroups that
+// ping-pong on the MUFU/FMA pipes while the tensor core serves the other tile (FlashAttention-4 style schedule).
+//
+// At SD-1.x head dims (d = 40) a 128x128 score tile costs only ~384 tensor-pipe cycles (QK^T with K-extent 48 +
+// PV with N-extent 48) but 16384 exponentials = 1024 MUFU cycles per SM, so the kernel is exponent-bound, not
+// tensor-bound.  The schedule therefore keeps the MUFU busy: while warpgroup A runs softmax on S_A(j), the tensor
+// core computes S_B(j) / P_B V(j-1), and vice versa.  Per-element instruction count is cut with packed fp32x2 math
+// (FFMA2 / FADD2), 3-input max (FMNMX3) and the P tile going back to the tensor core through TMEM (TS-form MMA).
+//
+// 10 warps: 0-3 softmax WG A (query rows q0..q0+127), 4-7 softmax WG B (q0+128..q0+255), 8 TMA producer,
+// 9 TMEM allocator + MMA issuer.  TMEM: S_A | S_B (BLOCK_N fp32 columns each) | P_A | P_B (BLOCK_N/2 columns of
+// packed bf16 pairs) | O_A | O_B.  P has its own columns so that QK(t, j+1) can be issued as soon as the softmax
+// warpgroup has pulled S(t, j) into registers (s_free), i.e. the next score tile is computed WHILE the current one
+// is being exponentiated, and PV(t, j) runs under softmax(t, j+1): the softmax warpgroups never wait on the MMA.
+// MMA order: QK_A(0) QK_B(0) | QK_A(1) PV_A(0) QK_B(1) PV_B(0) | QK_A(2) PV_A(1) ...
+#include "sm100_common.cuh"
+
+namespace agenda {
+namespace sm100 {
+
+constexpr int kV2Threads = 320;
+constexpr float kV2RescaleThreshold = 8.0f;
+
+template <int D>
+struct V2Cfg {
+  static constexpr int kDP = (D + 15) / 16 * 16;
+  static constexpr int kChunks = (D + 63) / 64;
+  static constexpr int kBlockN = (D <= 80) ? 128 : 64;
+  // d = 80 with 128-key tiles has no TMEM room for separate P columns (2*128 + 2*64 + 2*80 > 512): there P
+  // overwrites the S buffer it came from and QK(t, j+1) is issued after PV(t, j) (in-order MMA pipe).
+  static constexpr bool kAliasP = (3 * kBlockN + 2 * kDP > 512);
+  static constexpr int kStages = (kChunks * kBlockN * 128 * 2 * 3 + 2 * kChunks * 128 * 128 <= 200 * 1024) ? 3 : 2;
+  static constexpr int kQTileBytes = kChunks * 128 * 128;
+  static constexpr int kKVBytes = kChunks * kBlockN * 128;
+  static constexpr int kColS = 0;                                   // + t * kBlockN
+  static constexpr int kColP = kAliasP ? 0 : 2 * kBlockN;            // + t * (kAliasP ? kBlockN : kBlockN / 2)
+  static constexpr int kPStride = kAliasP ? kBlockN : kBlockN / 2;
+  static constexpr int kColO = kAliasP ? 2 * kBlockN : 3 * kBlockN;  // + t * kDP
+  static_assert(kColO + 2 * kDP <= 512, "TMEM overflow");
+};
+
+struct V2Barriers {
+  uint64_t q_full;
+  uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
+  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
+  uint32_t tmem_base;
+};
+
+template <int D>
+constexpr size_t v2_smem_bytes() {
+  using C = V2Cfg<D>;
+  return 1024 + 2 * C::kQTileBytes + 2 * C::kStages * C::kKVBytes + sizeof(V2Barriers) + 64;
+}
+
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// 2^x for a packed pair on the FMA/ALU pipes instead of the MUFU (FlashAttention-4's trick: at small head dims the
+// 16 exp/clk/SM MUFU is the kernel's bottleneck, so a fraction of the exponentials is moved to idle FMA lanes).
+// x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a cubic minimax polynomial (max rel. error 7.5e-5, far below
+// the bf16 rounding of P); 2^n by adding n to the exponent field.  x is clamped to >= -126 so the add cannot wrap.
+struct Ex2Emu {
+  uint64_t magic2, negmagic2, minus1_2, c0_2, c1_2, c2_2, c3_2;
+  __device__ __forceinline__ Ex2Emu() {
+    magic2 = pack_f32x2(12582912.f, 12582912.f);
+    negmagic2 = pack_f32x2(-12582912.f, -12582912.f);
+    minus1_2 = pack_f32x2(-1.f, -1.f);
+    c0_2 = pack_f32x2(0.9999280572f, 0.9999280572f);
+    c1_2 = pack_f32x2(0.6932609677f, 0.6932609677f);
+    c2_2 = pack_f32x2(0.2426111251f, 0.2426111251f);
+    c3_2 = pack_f32x2(0.0551716648f, 0.0551716648f);
+  }
+  __device__ __forceinline__ void operator()(uint64_t x2, float& r0, float& r1) const {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x2 = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t t2 = fadd2(x2, magic2);             // low mantissa bits of t = round(x)
+    const uint64_t nf2 = fadd2(t2, negmagic2);         // round(x) as a float
+    const uint64_t f2 = ffma2(nf2, minus1_2, x2);      // x - round(x)
+    uint64_t p2 = ffma2(c3_2, f2, c2_2);
+    p2 = ffma2(p2, f2, c1_2);
+    p2 = ffma2(p2, f2, c0_2);
+    float t0, t1, p0, p1;
+    unpack_f32x2(t2, t0, t1);
+    unpack_f32x2(p2, p0, p1);
+    r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+  }
+};
+
+// kEmu: share of exponential pairs evaluated by Ex2Emu: 0 none, 2 -> 50 %, 3 -> 37.5 %, 4 -> 25 %, 8 -> 12.5 %
+template <int D, int kEmu>
+__global__ void __launch_bounds__(kV2Threads, 1)
+attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                          const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
+                          float scale_log2) {
+  using C = V2Cfg<D>;
+  constexpr int BN = C::kBlockN;
+  constexpr int ST = C::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;                               // 2 query tiles
+  unsigned char* sK = sQ + 2 * C::kQTileBytes;            // ST stages
+  unsigned char* sV = sK + ST * C::kKVBytes;              // ST stages
+  V2Barriers* bars = reinterpret_cast<V2Barriers*>(sV + ST * C::kKVBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * 256;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int n_tiles = (N + BN - 1) / BN;
+
+  if (tid == 8 * 32) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    mbar_init(&bars->q_full, 1);
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128);
+      mbar_init(&bars->p_full[t], 128); mbar_init(&bars->pv_done[t], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 8) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_expect_tx(&bars->q_full, 2 * C::kQTileBytes);
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(&map_q, &bars->q_full, sQ + t * C::kQTileBytes + c * 128 * 128, c * 64, h, q0 + t * 128, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST;
+        const uint32_t ph = (j / ST) & 1;
+        mbar_wait(&bars->k_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->k_full[s], C::kKVBytes);
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(&map_k, &bars->k_full[s], sK + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
+        mbar_wait(&bars->v_empty[s], ph ^ 1);
+        mbar_expect_tx(&bars->v_full[s], C::kKVBytes);
+        for (int c = 0; c < C::kChunks; ++c)
+          tma_load_4d(&map_v, &bars->v_full[s], sV + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(128, BN, 0);
+      constexpr uint32_t idesc_pv = make_idesc(128, C::kDP, 1);
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      auto issue_qk = [&](int t, int j) {
+        const int s = j % ST;
+#pragma unroll
+        for (int kk = 0; kk < C::kDP / 16; ++kk) {
+          const uint64_t adesc = make_sdesc(q_addr + t * C::kQTileBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_sdesc(k_addr + s * C::kKVBytes + (kk >> 2) * BN * 128 + (kk & 3) * 32, 16, 1024);
+          umma_ss(tmem + C::kColS + t * BN, adesc, bdesc, idesc_qk, kk != 0);
+        }
+        umma_commit(&bars->s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {
+        const int s = j % ST;
+        mbar_wait(&bars->p_full[t], j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t bdesc = make_sdesc(v_addr + s * C::kKVBytes + kk * 2048, BN * 128, 1024);
+          umma_ts(tmem + C::kColO + t * C::kDP, tmem + C::kColP + t * C::kPStride + kk * 8, bdesc, idesc_pv, (j | kk) != 0);
+        }
+        umma_commit(&bars->pv_done[t]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&bars->k_empty[0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % ST, s1 = (j + 1) % ST;
+        const bool more = (j + 1 < n_tiles);
+        if (more) mbar_wait(&bars->k_full[s1], ((j + 1) / ST) & 1);
+        for (int t = 0; t < 2; ++t) {
+          if (!C::kAliasP && more) {
+            mbar_wait(&bars->s_free[t], j & 1);  // S(t, j) is in the softmax warpgroup's registers
+            tc_fence_after();
+            issue_qk(t, j + 1);
+            if (t == 1) umma_commit(&bars->k_empty[s1]);
+          }
+          if (t == 0) mbar_wait(&bars->v_full[s], (j / ST) & 1);
+          issue_pv(t, j);
+          if (C::kAliasP && more) {  // P(t, j) lives in S(t): the next score tile must follow PV(t, j)
+            issue_qk(t, j + 1);
+            if (t == 1) umma_commit(&bars->k_empty[s1]);
+          }
+        }
+        umma_commit(&bars->v_empty[s]);
+      }
+    }
+  } else {
+    // ============================== softmax warpgroups (thread == query row) ==============================
+    const int t = warp >> 2;  // which query tile / warpgroup
+    const int row = tid & 127;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t s_taddr = tmem + lane_base + C::kColS + t * BN;
+    const uint32_t p_taddr = tmem + lane_base + C::kColP + t * C::kPStride;
+    const Ex2Emu ex2_emu;
+    const uint32_t o_taddr = tmem + lane_base + C::kColO + t * C::kDP;
+    float m_used = -INFINITY;
+    float l_run = 0.f;
+    const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&bars->s_full[t], j & 1);
+      tc_fence_after();
+      float sv[BN];
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
+      tmem_wait_ld();
+      if (!C::kAliasP) {
+        tc_fence_before();
+        mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S(t) with QK(t, j+1) now
+      }
+      const int kv_left = N - j * BN;
+      if (kv_left < BN) {
+#pragma unroll
+        for (int i = 0; i < BN; ++i)
+          if (i >= kv_left) sv[i] = -INFINITY;
+      }
+      float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
+      float mx2 = fmax3(sv[6], sv[7], sv[8]), mx3 = fmax3(sv[9], sv[10], sv[11]);
+#pragma unroll
+      for (int i = 12; i + 8 <= BN; i += 8) {
+        mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+        mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]); mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
+      }
+      // BN = 128: elements 12..123 covered above, 124..127 here; BN = 64: 12..59 above, 60..63 here
+      mx0 = fmax3(mx0, sv[BN - 4], sv[BN - 3]);
+      mx1 = fmax3(mx1, sv[BN - 2], sv[BN - 1]);
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      const bool need = m_new > m_used + kV2RescaleThreshold;
+      if (j > 0) {
+        // PV(t, j-1) must have drained P(t) (single buffer) and left O(t) quiescent before we touch either
+        mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float m_next = need ? m_new : m_used;
+        const float f = ex2(m_used - m_next);
+        l_run *= f;
+        m_used = m_next;
+#pragma unroll
+        for (int c = 0; c < C::kDP / 16; ++c) {
+          float o[16];
+          tmem_ld16(o_taddr + c * 16, o);
+          tmem_wait_ld();
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(o[i] * f);
+          tmem_st16(o_taddr + c * 16, u);
+        }
+        tmem_wait_st();
+      }
+      const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+      uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = sum2a;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t u[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const int e = c * 32 + 2 * i;
+          float a0, a1, b0, b1;
+          const uint64_t xa = ffma2(pack_f32x2(sv[e], sv[e + 1]), scale2, negm2);
+          const uint64_t xb = ffma2(pack_f32x2(sv[e + 2], sv[e + 3]), scale2, negm2);
+          unpack_f32x2(xa, a0, a1);
+          a0 = ex2(a0); a1 = ex2(a1);
+          // 16 pairs per 32-column chunk; pair b of iteration ib = i/2 is emulated according to kEmu:
+          // 2 -> every b pair (50 % of all exponentials), 3 -> ib % 3 != 2 (37.5 %), 4 -> even ib (25 %), 8 -> ib % 4 == 0
+          const int ib = i >> 1;
+          const bool emu_b = (kEmu == 2) || (kEmu == 3 && (ib % 3) != 2) || (kEmu == 4 && (ib & 1) == 0) ||
+                             (kEmu == 8 && (ib & 3) == 0);
+          if (emu_b) {
+            ex2_emu(xb, b0, b1);
+          } else {
+            unpack_f32x2(xb, b0, b1);
+            b0 = ex2(b0); b1 = ex2(b1);
+          }
+          sum2a = fadd2(sum2a, pack_f32x2(a0, a1));
+          sum2b = fadd2(sum2b, pack_f32x2(b0, b1));
+          u[i] = pack_bf16(a0, a1);
+          u[i + 1] = pack_bf16(b0, b1);
+        }
+        tmem_st16(p_taddr + c * 16, u);  // P as packed bf16 pairs
+      }
+      float s0, s1, s2, s3;
+      unpack_f32x2(sum2a, s0, s1);
+      unpack_f32x2(sum2b, s2, s3);
+      l_run += (s0 + s1) + (s2 + s3);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[t]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait(&bars->pv_done[t], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int n = q0 + t * 128 + row;
+    __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + h * D;
+#pragma unroll
+    for (int c = 0; c < C::kDP / 16; ++c) {
+      float o[16];
+      tmem_ld16(o_taddr + c * 16, o);
+      tmem_wait_ld();
+      if (n < N) {
+        uint4 lo, hi;
+        lo.x = pack_bf16(o[0] * inv_l, o[1] * inv_l); lo.y = pack_bf16(o[2] * inv_l, o[3] * inv_l);
+        lo.z = pack_bf16(o[4] * inv_l, o[5] * inv_l); lo.w = pack_bf16(o[6] * inv_l, o[7] * inv_l);
+        hi.x = pack_bf16(o[8] * inv_l, o[9] * inv_l); hi.y = pack_bf16(o[10] * inv_l, o[11] * inv_l);
+        hi.z = pack_bf16(o[12] * inv_l, o[13] * inv_l); hi.w = pack_bf16(o[14] * inv_l, o[15] * inv_l);
+        if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+        if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace sm100
+
+template <int D, int kEmu>
+static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
+                     cudaStream_t stream) {
+  using C = sm100::V2Cfg<D>;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  constexpr size_t smem = sm100::v2_smem_bytes<D>();
+  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu>;
+  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid((N + 255) / 256, B * H);
+  kern<<<grid, sm100::kV2Threads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
+                                                  scale * 1.4426950408889634f);
+  AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");
+  return AGENDA_OK;
+}
+
+// emu: 0 = every exponential on the MUFU; 2/3/4/8 = 50/37.5/25/12.5 % of them on the FMA pipe
+int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
+                       int emu, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define AGENDA_V2(DD)                                                                   \
+  case DD:                                                                              \
+    switch (emu) {                                                                      \
+      case 0: return launch_v2<DD, 0>(q, k, v, out, B, H, N, scale, st);                \
+      case 2: return launch_v2<DD, 2>(q, k, v, out, B, H, N, scale, st);                \
+      case 3: return launch_v2<DD, 3>(q, k, v, out, B, H, N, scale, st);                \
+      case 8: return launch_v2<DD, 8>(q, k, v, out, B, H, N, scale, st);                \
+      default: return launch_v2<DD, 4>(q, k, v, out, B, H, N, scale, st);               \
+    }
+  switch (d) {
+    AGENDA_V2(40)
+    AGENDA_V2(64)
+    AGENDA_V2(80)
+    AGENDA_V2(160)
+    default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: head dim %d not in {40,64,80,160}", d);
+  }
+#undef AGENDA_V2
+}
+
+}  // namespace agenda

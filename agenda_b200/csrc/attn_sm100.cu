@@ -334,16 +334,23 @@ static int launch_sm100(const void* q, const void* k, const void* v, void* out, 
 int attn_common_checks(const char* who, const void* q, const void* k, const void* v, void* out, int dtype, int B,
                        int H, int N, int M, int d);
 
-// variant: 0 = P through TMEM (TS-form PV MMA), 1 = P through shared memory (SS-form)
+int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
+                       int emu, void* stream);
+
+// variant: 0 = two query tiles per CTA, ping-pong softmax warpgroups (v2; falls back to variant 1 when N <= 128),
+//          1 = one query tile per CTA, P through TMEM (TS-form PV MMA), 2 = same with P through shared memory (SS)
 int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
                     int variant, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_self_fwd: q/k/v/out must be 16-byte aligned");
+  // variants 10/12/13/14/18: v2 with 0 / 50 / 37.5 / 25 / 12.5 % of the exponentials emulated on the FMA pipe
+  if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, stream);
+  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, d == 80 ? 4 : 0, stream);
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
-    return variant == 0 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \
+    return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \
                         : launch_sm100<DD, false>(q, k, v, out, B, H, N, scale, st);
   switch (d) {
     AGENDA_DISPATCH(40)
@@ -368,7 +375,7 @@ extern "C" int agenda_attn_self_fwd(const void* q, const void* k, const void* v,
   return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
 }
 
-// Test hook: same contract, explicit P-operand variant (0 = TMEM, 1 = shared memory).
+// Test hook: same contract, explicit kernel variant (see attn_self_sm100).
 extern "C" int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                                             int d, float scale, int variant, void* stream) {
   int rc = attn_common_checks("attn_self_fwd_variant", q, k, v, out, AGENDA_BF16, B, H, N, N, d);

@@ -53,8 +53,9 @@ int agenda_device_ok(void);
 int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out, int dtype,
                          int B, int H, int N, int d, float scale, void* stream);
 
-/* Test hook: agenda_attn_self_fwd (bf16) with the P operand routed explicitly: variant 0 = through TMEM (TS-form
- * tcgen05.mma, the default), 1 = through a 128B-swizzled shared-memory tile (SS-form). */
+/* Test hook: agenda_attn_self_fwd (bf16) with an explicit kernel variant: 0 = default (two 128-query tiles per
+ * CTA, ping-pong softmax warpgroups, P through TMEM), 1 = one query tile per CTA with P through TMEM (TS-form
+ * tcgen05.mma), 2 = one query tile per CTA with P through a 128B-swizzled shared-memory tile (SS-form). */
 int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                                  int d, float scale, int variant, void* stream);
 

@@ -35,7 +35,7 @@ SHAPES = [  # B, N, H, d
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18])
 @pytest.mark.parametrize("B,N,H,d", SHAPES)
 def test_sm100_self_attention(lib, B, N, H, d, variant):
     g = torch.Generator().manual_seed(N * 7 + d + H)
@@ -49,7 +49,7 @@ def test_sm100_self_attention(lib, B, N, H, d, variant):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
     B, N, H, d = 1, 1024, 2, 40
