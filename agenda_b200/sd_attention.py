@@ -102,6 +102,9 @@ class AttentionStack(nn.Module):
         for b in blocks:
             self.attn1.append(SDAttention(b.channels, None, b.heads, b.dim_head))
             self.attn2.append(SDAttention(b.channels, context_dim, b.heads, b.dim_head))
+            # diffusers-style qualified names ("mid_block....attn2") for code that selects layers by name
+            self.attn1[-1].block_name = f"{b.name}.attn1"
+            self.attn2[-1].block_name = f"{b.name}.attn2"
         with torch.no_grad():
             for p in self.parameters():  # deterministic random init, independent of global RNG state
                 p.copy_(torch.empty_like(p).uniform_(-1, 1, generator=gen) * (p.shape[-1] ** -0.5))

@@ -204,7 +204,7 @@ def run_ours(args):
             return
         for name in ("counts", "boxes", "heat"):
             t = out[name].contiguous()
-            buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+            buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(buf, t)
 
     def barrier():

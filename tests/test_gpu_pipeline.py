@@ -1,0 +1,162 @@
+"""GPU: the reference-facing surfaces end to end — HeatmapPipeline (device + host-buffer API, CUDA graph), the
+daam-style trace shim, the host-buffer post-processing API and the two CLI mirrors — against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hook_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda_ok():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return True
+
+
+def _small_blocks():
+    from agenda_b200.sd_attention import BlockSpec
+    return [BlockSpec("down0", 16, 320, 8), BlockSpec("down1", 8, 640, 8), BlockSpec("mid", 4, 1280, 8),
+            BlockSpec("up3", 16, 320, 8)]
+
+
+def _oracle_heat(pipe, hs, ctx, steps, toks):
+    maps = []
+    for b, a2 in zip(pipe.blocks, pipe.stack.attn2):
+        x = hs[(b.hw, b.channels)].float().cpu()
+        w = [t.detach().float().cpu() for t in (a2.to_q.weight, a2.to_k.weight, a2.to_v.weight, a2.to_out[0].weight,
+                                                a2.to_out[0].bias)]
+        _, m = O.processor_call(x, ctx.float().cpu(), *w, b.heads, is_train=False)
+        maps.append(m)
+    return O.global_heat_map(maps * steps, pipe.latent_hw)[:, toks]
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipeline_matches_oracle(cuda_ok, graph):
+    from agenda_b200.pipeline import HeatmapPipeline
+    toks = [2, 5, 9]
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=toks, num_steps=3, latent_hw=16, image_size=112,
+                           use_cuda_graph=graph, max_boxes=32)
+    hs, ctx = pipe.make_inputs(2, seed=3)  # 2 images -> UNet batch 4
+    out = pipe.run_device(hs, ctx)
+    ref = _oracle_heat(pipe, hs, ctx, 3, toks)          # [2, 3, 16, 16]; the bf16 weights/inputs are shared
+    heat = out["heat"].cpu().numpy()
+    assert heat.shape == ref.shape
+    # q/k are produced by bf16 cuBLAS GEMMs on the device vs fp32 on the CPU: compare at bf16-projection accuracy
+    assert np.abs(heat - ref).max() < 2e-3 * ref.max() + 1e-5
+    # everything downstream of the heat map is integer/byte work: bit-exact given OUR fp32 heat map
+    for i in range(2):
+        planes = [O.heat_to_png_array(heat[i, t], 112) for t in range(3)]
+        rs, ri = O.stack_heatmaps(*planes)
+        assert np.array_equal(out["planes"][i].cpu().numpy(), np.stack(planes))
+        assert np.array_equal(out["stack"][i].cpu().numpy(), rs) and np.array_equal(out["inv"][i].cpu().numpy(), ri)
+        rl, rb = O.ccl_bbox(heat[i, 0], 0.5)
+        assert out["counts"][i].item() == len(rb)
+        assert np.array_equal(out["boxes"][i, :min(len(rb), 32)].cpu().numpy(), rb[:32])
+    # second run (graph replay) reproduces the first bit for bit
+    out2 = pipe.run_device(hs, ctx)
+    assert torch.equal(out2["heat"], out["heat"]) and torch.equal(out2["boxes"], out["boxes"])
+
+
+def test_pipeline_host_api_equals_device_api(cuda_ok):
+    from agenda_b200.pipeline import HeatmapPipeline
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=[1, 2, 3], num_steps=2, latent_hw=16, use_cuda_graph=True)
+    hs_h, ctx_h = pipe.make_inputs(2, seed=1, pinned_host=True)
+    assert all(v.is_pinned() for v in hs_h.values()) and ctx_h.is_pinned()
+    host = pipe.run_host(hs_h, ctx_h)
+    dev = pipe.run_device({k: v.cuda() for k, v in hs_h.items()}, ctx_h.cuda())
+    for k in ("heat", "stack", "inv", "counts", "boxes"):
+        assert torch.equal(host[k], dev[k].cpu()), k
+    assert pipe.h2d_bytes(hs_h, ctx_h) > 0 and pipe.d2h_bytes(host) > 0
+
+
+def test_trace_shim_end_to_end(cuda_ok):
+    """data_generation.py:57-77 call sequence against the shim."""
+    from agenda_b200.sd_attention import AttentionStack
+    from agenda_b200.trace import trace
+    blocks = _small_blocks()
+    stack = AttentionStack(blocks, 768, seed=1).cuda().bfloat16()
+
+    class Pipe:
+        unet = stack
+        tokenizer = None
+
+    hs, ctx = stack.make_inputs(2, "cuda", torch.bfloat16, seed=2)  # batch 1 image + CFG
+    with trace(Pipe(), tokens=[4, 7], latent_hw=16) as trc:
+        with torch.no_grad():
+            for _ in range(2):
+                stack(hs, ctx)
+        heat = trc.compute_global_heat_map()
+    hm = heat.compute_word_heat_map("cars", token_idx=[4, 7]).heatmap
+    assert hm.shape == (16, 16) and hm.dtype == torch.float32
+    one = heat.compute_word_heat_map("cars", token_idx=[7]).heatmap
+    assert torch.equal(one, heat.heat_maps[1])
+    assert all(m.processor is None for m in list(stack.attn1) + list(stack.attn2))  # restored
+    # daam mode: 3 of the 4 cross-attention layers (mid excluded)
+    with trace(Pipe(), tokens=[4], latent_hw=16, mode="daam") as trc:
+        for m in stack.attn1:
+            m.set_processor(trc.hooker)  # self-attention keeps "its own" processor in daam mode; give it one here
+        with torch.no_grad():
+            stack(hs, ctx)
+        assert trc.hooker.num_maps == 3
+
+
+def test_postprocess_host_api(cuda_ok):
+    from agenda_b200 import postprocess
+    rng = np.random.default_rng(0)
+    heat = rng.random((3, 64, 64), dtype=np.float32) ** 3
+    png = postprocess.heatmap_to_png_array(heat, 112)
+    for i in range(3):
+        assert np.array_equal(png[i], O.heat_to_png_array(heat[i], 112))
+    st, inv = postprocess.stack_heatmaps(png[0], png[1], png[2])
+    rs, ri = O.stack_heatmaps(png[0], png[1], png[2])
+    assert np.array_equal(st, rs) and np.array_equal(inv, ri)
+    big = O.synthetic_heatmaps(2, 256, seed=4)
+    labels, boxes = postprocess.ccl_bbox(big, 0.5)
+    for i in range(2):
+        rl, rb = O.ccl_bbox(big[i], 0.5)
+        assert np.array_equal(labels[i], rl) and np.array_equal(boxes[i], rb)
+    lab1, box1 = postprocess.ccl_bbox(big[0], 0.5)
+    assert np.array_equal(lab1, O.ccl_bbox(big[0], 0.5)[0])
+
+
+def test_cli_postprocess_heatmap(cuda_ok, tmp_path):
+    """The mirror of postprocess_heatmap.py writes the same PNG payloads as the reference's numpy lines."""
+    from PIL import Image
+    from agenda_b200 import postprocess_heatmap
+    rng = np.random.default_rng(1)
+    dirs = {k: tmp_path / f"daam_{k}_heatmaps" for k in ("cars", "fg", "bg")}
+    arrays = {}
+    for k, d in dirs.items():
+        d.mkdir()
+        for seed in (0, 1, 10):
+            a = rng.integers(0, 256, (112, 112), dtype=np.uint8)
+            arrays[(k, seed)] = a
+            Image.fromarray(a).save(d / f"{seed}.png")
+    n = postprocess_heatmap.main(["--save-dir", str(tmp_path), "--object-heatmap-path", "daam_cars_heatmaps",
+                                  "--fg-heatmap-path", "daam_fg_heatmaps", "--bg-heatmap-path", "daam_bg_heatmaps"])
+    assert n == 3
+    for seed in (0, 1, 10):
+        rs, ri = O.stack_heatmaps(arrays[("cars", seed)], arrays[("fg", seed)], arrays[("bg", seed)])
+        st = Image.open(tmp_path / "daam_stack_heatmaps" / f"{seed}.png")
+        assert st.mode == "RGB" and np.array_equal(np.asarray(st), rs)
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "daam_inv_heatmaps" / f"{seed}.png")), ri)
+
+
+def test_cli_data_generation_synthetic(cuda_ok, tmp_path):
+    from PIL import Image
+    from agenda_b200 import data_generation
+    n = data_generation.main(["--synthetic", "--save-dir", str(tmp_path), "--num-images", "3", "--batch-size", "2",
+                              "--num-inference-steps", "1", "--word_token_heatmaps", "cars", "fg", "bg",
+                              "--token-indices", "5", "6", "7", "--image-size", "112"])
+    assert n == 3
+    for word in ("cars", "fg", "bg"):
+        for seed in range(3):
+            im = Image.open(tmp_path / f"daam_{word}_heatmaps" / f"{seed}.png")
+            assert im.size == (112, 112) and im.mode == "L"
+            a = np.asarray(im)
+            assert a.max() > 200 and a.min() < 50  # min-max normalised
