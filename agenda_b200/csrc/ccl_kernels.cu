@@ -1,18 +1,26 @@
 // K6: threshold + 4-connected component labelling + bbox (spec: SURVEY.md §8 a9; not present in the reference).
 //
 // B200 design: ONE THREAD-BLOCK CLUSTER PER MAP, the whole fp32 map resident in distributed shared memory.
-//   * each CTA of the cluster bulk-copies (TMA engine, cp.async.bulk + mbarrier) its strip of R rows into smem,
-//   * min/max are reduced CTA-locally and exchanged through DSMEM, so the map is read from HBM exactly once
-//     even though normalisation needs the global min/max before the first pixel can be thresholded,
-//   * the strip buffer is then re-used IN PLACE as the union-find parent array (one u32 per pixel, labels are
-//     map-linear pixel indices, roots = smallest index of the component),
-//   * runs are seeded with warp ballots (one warp = 32 consecutive pixels of a row), merged vertically with
-//     shared-memory atomicMin union-find, strips are stitched through DSMEM atomics,
-//   * roots are numbered in raster order with ballot/popc scans (+ a DSMEM exchange of per-strip root counts),
-//     which reproduces scipy.ndimage.label's numbering bit-exactly,
-//   * labels go back to HBM once (coalesced), boxes via per-run global atomics.
+//   * each CTA of the cluster bulk-copies (TMA engine, cp.async.bulk + mbarrier) its strip of R rows into smem;
+//     min/max are reduced CTA-locally and exchanged through DSMEM, so the map is read from HBM exactly ONCE even
+//     though normalisation needs the global min/max before the first pixel can be thresholded;
+//   * the normalise-and-compare `((h-min)/((max-min)+1e-8f)) > thr` is monotone in h, so one warp finds, by a
+//     32-ary search over ordered float bit patterns (7 ballots), the smallest float that passes; every pixel then
+//     needs a single compare and the result is bit-identical to evaluating the IEEE division per pixel;
+//   * pixels are thresholded four at a time (float4) into a row-major BIT MASK; from here on the unit of work is a
+//     32-pixel mask word, not a pixel: "pieces" (maximal runs of set bits inside one word) are enumerated with
+//     carry-ripple bit tricks, each piece owns one union-find slot (16 slots per word, overlaid on the dead fp32
+//     strip), pieces are merged with the piece(s) they touch in the row above and across word borders with
+//     shared-memory atomicMin union-find, strips are stitched through DSMEM;
+//   * slot ids increase in raster order of the piece's first pixel, union always keeps the smaller id, so a
+//     component's root is its first pixel in raster order; roots are numbered with a block scan plus a DSMEM
+//     exchange of per-strip root counts, which reproduces scipy.ndimage.label's numbering bit-exactly;
+//   * labels leave the SM once (int4 per thread, coalesced; all-background quads take a fast path), boxes through
+//     per-piece global atomics.
 // Algorithmic HBM bytes per map: H*W*4 read + H*W*4 written (+ 20 B per box).
 #include <cooperative_groups.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -20,9 +28,9 @@ namespace cg = cooperative_groups;
 
 namespace agenda {
 
-constexpr uint32_t kBG = 0xFFFFFFFFu;
 constexpr uint32_t kRankFlag = 0x80000000u;
 constexpr int kMaxCluster = 16;
+constexpr int kSlotsPerWord = 16;  // at most 16 pieces (alternating bits) in a 32-pixel word
 
 struct CclStatic {
   unsigned long long mbar;
@@ -31,39 +39,64 @@ struct CclStatic {
   float x_min[kMaxCluster], x_max[kMaxCluster];
   int x_nan[kMaxCluster];
   int x_roots[kMaxCluster];
-  int warp_roots[32];
-  int warp_base[32];
+  int warp_tot[32];
+  float hstar;
+  int mode;  // 0: compare against hstar, 1: nothing is foreground, 2: everything is foreground
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-// ---- union-find on the CTA-local strip (labels are map-linear indices, strip covers [base, base+strip_px)) ----
-__device__ __forceinline__ uint32_t find_local(const uint32_t* L, uint32_t base, uint32_t x) {
-  uint32_t p = L[x - base];
-  while (p != x) { x = p; p = L[x - base]; }
-  return x;
+// order-preserving float <-> uint32 key
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ void unite_local(uint32_t* L, uint32_t base, uint32_t a, uint32_t b) {
-  bool done;
-  do {
-    a = find_local(L, base, a);
-    b = find_local(L, base, b);
-    if (a < b) { const uint32_t old = atomicMin(&L[b - base], a); done = (old == b); b = old; }
-    else if (b < a) { const uint32_t old = atomicMin(&L[a - base], b); done = (old == a); a = old; }
-    else done = true;
-  } while (!done);
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// ---- the same over the whole cluster (a label may live in another CTA's shared memory) ----
-struct ClusterLabels {
+// bits of the piece (maximal run of ones) of word m that starts at bit p (m has bit p set, bit p-1 clear or p == 0)
+__device__ __forceinline__ uint32_t piece_from(uint32_t m, int p) {
+  const uint32_t t = m + (1u << p);  // the carry ripples through the run
+  return (m ^ t) & m;
+}
+// start bit of the piece of m containing bit q
+__device__ __forceinline__ int piece_start(uint32_t m, int q) {
+  const uint32_t zeros_below = ~m & ((1u << q) - 1u);
+  return zeros_below ? 32 - __clz(zeros_below) : 0;
+}
+// index (0..15) of the piece of m containing bit q, pieces counted from bit 0
+__device__ __forceinline__ int piece_index(uint32_t m, int q) {
+  const uint32_t starts = m & ~(m << 1);
+  return __popc(starts & (0xFFFFFFFFu >> (31 - q))) - 1;
+}
+
+struct Forest {
   cg::cluster_group cluster;
-  uint32_t* L;         // this CTA's strip
-  uint32_t strip_px;   // R*W
-  __device__ __forceinline__ uint32_t* slot(uint32_t idx) const {
-    const uint32_t rk = idx / strip_px;
-    return cluster.map_shared_rank(L, rk) + (idx - rk * strip_px);
+  uint32_t* slots;       // this CTA's union-find slots
+  uint32_t strip_slots;  // slots per strip = R * words_per_row * 16
+  uint32_t base;         // first slot id of this strip
+
+  __device__ __forceinline__ uint32_t find_local(uint32_t x) const {
+    uint32_t p = slots[x - base];
+    while (p != x) { x = p; p = slots[x - base]; }
+    return x;
+  }
+  __device__ __forceinline__ void unite_local(uint32_t a, uint32_t b) const {
+    bool done;
+    do {
+      a = find_local(a);
+      b = find_local(b);
+      if (a < b) { const uint32_t old = atomicMin(&slots[b - base], a); done = (old == b); b = old; }
+      else if (b < a) { const uint32_t old = atomicMin(&slots[a - base], b); done = (old == a); a = old; }
+      else done = true;
+    } while (!done);
+  }
+  __device__ __forceinline__ uint32_t* slot(uint32_t id) const {
+    const uint32_t rk = id / strip_slots;
+    return cluster.map_shared_rank(slots, rk) + (id - rk * strip_slots);
   }
   __device__ __forceinline__ uint32_t find(uint32_t x) const {
     uint32_t p = *reinterpret_cast<volatile uint32_t*>(slot(x));
@@ -82,26 +115,51 @@ struct ClusterLabels {
   }
 };
 
-__global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels,
-                                int32_t* __restrict__ counts, int32_t* __restrict__ boxes, int max_boxes, int H,
-                                int W, int R, int use_bulk) {
+// Merge every piece of word `m` (slots first_slot + k) with the pieces of `up` (the word above, slots up_first + k)
+// it overlaps.  kLocal: both rows live in this CTA.
+template <bool kLocal>
+__device__ __forceinline__ void merge_with_row_above(const Forest& F, uint32_t m, uint32_t up, uint32_t first_slot,
+                                                     uint32_t up_first) {
+  uint32_t starts = m & ~(m << 1);
+  int k = 0;
+  while (starts) {
+    const int p = __ffs(starts) - 1;
+    starts &= starts - 1;
+    uint32_t ov = piece_from(m, p) & up;
+    while (ov) {
+      const int q = __ffs(ov) - 1;
+      const int pu = piece_start(up, q);
+      ov &= ~piece_from(up, pu);
+      const uint32_t a = first_slot + k, b = up_first + piece_index(up, q);
+      if (kLocal) F.unite_local(a, b); else F.unite(a, b);
+    }
+    ++k;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
+                int32_t* __restrict__ boxes, int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ CclStatic sh;
-  uint32_t* L = reinterpret_cast<uint32_t*>(dyn_smem);
-  float* Lf = reinterpret_cast<float*>(dyn_smem);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = static_cast<int>(cluster.num_blocks());
   const int rank = static_cast<int>(cluster.block_rank());
   const long long map = blockIdx.x / cs;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5, nthreads = blockDim.x;
 
   const int r0 = rank * R;
   const int rows = min(R, H - r0);
-  const int strip_px = R * W;
   const int n_px = rows * W;
-  const uint32_t base = static_cast<uint32_t>(r0) * W;  // map-linear index of this strip's first pixel
-  const float* src = heat + map * H * W + base;
+  const int wpr = (W + 31) >> 5;           // mask words per row
+  const int n_words = R * wpr;             // per strip (rows beyond `rows` stay zero)
+  const int strip_slots = n_words * kSlotsPerWord;
+
+  float* Lf = reinterpret_cast<float*>(dyn_smem);                      // fp32 strip, dead after thresholding
+  uint32_t* slots = reinterpret_cast<uint32_t*>(dyn_smem);             // union-find slots, overlaid on the strip
+  uint32_t* bits = reinterpret_cast<uint32_t*>(dyn_smem + strip_bytes);  // [R][wpr] foreground mask
+  const float* src = heat + map * H * W + static_cast<long long>(r0) * W;
 
   // ---- 1. strip -> shared memory (bulk async copy through the TMA engine when 16-B aligned) ----
   if (use_bulk) {
@@ -124,7 +182,6 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
             : "memory");
       }
     }
-    // all threads wait for phase 0
     uint32_t ok = 0;
     while (!ok) {
       asm volatile(
@@ -136,7 +193,7 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
           : "memory");
     }
   } else {
-    for (int i = tid; i < n_px; i += blockDim.x) Lf[i] = __ldg(src + i);
+    for (int i = tid; i < n_px; i += nthreads) Lf[i] = __ldg(src + i);
     __syncthreads();
   }
 
@@ -145,14 +202,14 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
     float lo = INFINITY, hi = -INFINITY;
     int nan = 0;
     if ((n_px & 3) == 0) {
-      for (int i = tid; i < (n_px >> 2); i += blockDim.x) {
+      for (int i = tid; i < (n_px >> 2); i += nthreads) {
         const float4 v = reinterpret_cast<const float4*>(Lf)[i];
         lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
         hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
         nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
       }
     } else {
-      for (int i = tid; i < n_px; i += blockDim.x) {
+      for (int i = tid; i < n_px; i += nthreads) {
         const float v = Lf[i];
         lo = fminf(lo, v); hi = fmaxf(hi, v); nan |= (v != v);
       }
@@ -175,129 +232,160 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
     }
   }
   cluster.sync();
-  float mn = INFINITY, mx = -INFINITY;
-  int any_nan = 0;
-  for (int j = 0; j < cs; ++j) {
-    mn = fminf(mn, sh.x_min[j]); mx = fmaxf(mx, sh.x_max[j]); any_nan |= sh.x_nan[j];
-  }
-  const float denom = np_denominator(mn, mx);
 
-  const int segs = (W + 31) >> 5;
-  const int n_seg = rows * segs;
-
-  // ---- 3. threshold, seed every pixel with the index of the first pixel of its (32-px-segment) run ----
-  for (int s = wid; s < n_seg; s += nwarps) {
-    const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-    const bool valid = x < W;
-    const int i = y * W + x;
-    bool fg = false;
-    if (valid) fg = !any_nan && (np_normalize(Lf[i], mn, denom) > thr);
-    const uint32_t m = __ballot_sync(0xffffffffu, fg);
-    if (valid) {
-      uint32_t lab = kBG;
-      if (fg) {
-        const uint32_t zeros_below = ~m & ((1u << lane) - 1u);
-        const int start = zeros_below ? (32 - __clz(zeros_below)) : 0;
-        lab = base + static_cast<uint32_t>(i - (lane - start));
+  // ---- 3. warp 0: smallest float h* with ((h*-min)/denom) > thr  (32-ary search over ordered bit patterns) ----
+  if (wid == 0) {
+    float mn = INFINITY, mx = -INFINITY;
+    int any_nan = 0;
+    for (int j = 0; j < cs; ++j) { mn = fminf(mn, sh.x_min[j]); mx = fmaxf(mx, sh.x_max[j]); any_nan |= sh.x_nan[j]; }
+    const float denom = np_denominator(mn, mx);
+    int mode = 0;
+    float hstar = 0.f;
+    if (any_nan || !(np_normalize(mx, mn, denom) > thr)) mode = 1;       // NaN map (numpy: all False) or max fails
+    else if (np_normalize(mn, mn, denom) > thr) mode = 2;                // even the minimum passes
+    else {
+      // invariant: pass(lo) false, pass(hi) true; keys are monotone in the float order
+      uint32_t lo = f2key(mn), hi = f2key(mx);
+      while (hi - lo > 1u) {
+        const uint32_t span = hi - lo;                       // >= 2
+        const uint32_t step = span / 33u + 1u;
+        uint32_t cand = lo + step * static_cast<uint32_t>(lane + 1);
+        const bool valid = (cand - lo) < span;               // lo < cand < hi (no wrap: step*(33) <= span + 33)
+        if (!valid) cand = hi;
+        const bool pass = np_normalize(key2f(cand), mn, denom) > thr;
+        const uint32_t pm = __ballot_sync(0xffffffffu, pass);  // monotone: 0..0 1..1 from some lane on
+        if (pm == 0) {                                         // all 32 probes fail: the cut is above the last one
+          lo = __shfl_sync(0xffffffffu, cand, 31);
+        } else {
+          const int first = __ffs(pm) - 1;
+          const uint32_t new_hi = __shfl_sync(0xffffffffu, cand, first);
+          const uint32_t new_lo = __shfl_sync(0xffffffffu, cand, first > 0 ? first - 1 : 0);
+          hi = new_hi;
+          if (first > 0) lo = new_lo;
+        }
       }
-      L[i] = lab;
+      hstar = key2f(hi);
     }
+    if (lane == 0) { sh.hstar = hstar; sh.mode = mode; }
+  }
+  __syncthreads();
+  const float hstar = sh.hstar;
+  const int mode = sh.mode;
+
+  // ---- 4. threshold four pixels per thread -> bit mask words ----
+  if ((W & 31) == 0) {
+    const int n_quads = n_px >> 2;
+    for (int i = tid; i < ((n_quads + 31) & ~31); i += nthreads) {
+      uint32_t nib = 0;
+      if (i < n_quads) {
+        const float4 v = reinterpret_cast<const float4*>(Lf)[i];
+        nib = (v.x >= hstar ? 1u : 0u) | (v.y >= hstar ? 2u : 0u) | (v.z >= hstar ? 4u : 0u) | (v.w >= hstar ? 8u : 0u);
+        if (mode) nib = (mode == 2) ? 0xFu : 0u;
+      }
+      // 8 consecutive lanes hold one 32-pixel word
+      const uint32_t word = __reduce_or_sync(0xFFu << (lane & 24), nib << ((lane & 7) * 4));
+      if ((lane & 7) == 0 && i < n_quads) bits[i >> 3] = word;
+    }
+    for (int i = (n_px >> 5) + tid; i < n_words; i += nthreads) bits[i] = 0;  // rows past the end of the map
+  } else {
+    // generic width: one warp per (row, word)
+    for (int s = wid; s < n_words; s += nwarps) {
+      const int y = s / wpr, x = ((s - y * wpr) << 5) + lane;
+      bool fg = false;
+      if (y < rows && x < W) fg = mode ? (mode == 2) : (Lf[y * W + x] >= hstar);
+      const uint32_t word = __ballot_sync(0xffffffffu, fg);
+      if (lane == 0) bits[s] = word;
+    }
+  }
+  __syncthreads();  // the fp32 strip is dead from here on: its memory becomes the union-find slots
+
+  Forest F{cluster, slots, static_cast<uint32_t>(strip_slots), static_cast<uint32_t>(rank) * strip_slots};
+
+  // ---- 5. one slot per piece, initialised to itself ----
+  for (int w = tid; w < n_words; w += nthreads) {
+    const uint32_t m = bits[w];
+    const int np = __popc(m & ~(m << 1));
+    for (int k = 0; k < np; ++k) slots[w * kSlotsPerWord + k] = F.base + w * kSlotsPerWord + k;
   }
   __syncthreads();
 
-  // ---- 4. merge inside the strip: across 32-px segment boundaries and with the row above ----
-  for (int s = wid; s < n_seg; s += nwarps) {
-    const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-    const bool valid = x < W;
-    const int i = y * W + x;
-    const bool fg = valid && (L[i] != kBG);
-    const bool up = fg && y > 0 && (L[i - W] != kBG);
-    const uint32_t m = __ballot_sync(0xffffffffu, fg);
-    const uint32_t mu = __ballot_sync(0xffffffffu, valid && y > 0 && (L[i - W] != kBG));
-    if (fg) {
-      bool left, upleft;
-      if (lane) { left = (m >> (lane - 1)) & 1u; upleft = (mu >> (lane - 1)) & 1u; }
-      else {
-        left = x > 0 && (L[i - 1] != kBG);
-        upleft = x > 0 && y > 0 && (L[i - W - 1] != kBG);
-        if (left) unite_local(L, base, base + i, base + i - 1);
-      }
-      if (up && !(left && upleft)) unite_local(L, base, base + i, base + i - W);
+  // ---- 6. merge inside the strip: across word borders and with the row above ----
+  for (int w = tid; w < n_words; w += nthreads) {
+    const uint32_t m = bits[w];
+    if (m == 0) continue;
+    const int y = w / wpr, wx = w - y * wpr;
+    const uint32_t first = F.base + w * kSlotsPerWord;
+    if (wx > 0 && (m & 1u)) {
+      const uint32_t left = bits[w - 1];
+      if (left >> 31) F.unite_local(first, first - kSlotsPerWord + __popc(left & ~(left << 1)) - 1);
+    }
+    if (y > 0) {
+      const uint32_t up = bits[w - wpr];
+      if (up & m) merge_with_row_above<true>(F, m, up, first, first - wpr * kSlotsPerWord);
     }
   }
-  cluster.sync();  // every strip holds labels (not floats) and is internally merged
+  cluster.sync();  // every strip is internally merged
 
-  ClusterLabels CL{cluster, L, static_cast<uint32_t>(strip_px)};
-
-  // ---- 5. stitch with the strip above through distributed shared memory ----
+  // ---- 7. stitch with the strip above through distributed shared memory ----
   if (rank > 0) {
-    const uint32_t* prev = cluster.map_shared_rank(L, rank - 1) + (R - 1) * W;  // last row of the strip above
-    for (int s = wid; s < segs; s += nwarps) {
-      const int x = (s << 5) + lane;
-      const bool valid = x < W;
-      const bool fg = valid && (L[x] != kBG);
-      const bool upv = valid && (prev[x] != kBG);
-      const uint32_t m = __ballot_sync(0xffffffffu, fg);
-      const uint32_t mu = __ballot_sync(0xffffffffu, upv);
-      if (fg && upv) {
-        bool left, upleft;
-        if (lane) { left = (m >> (lane - 1)) & 1u; upleft = (mu >> (lane - 1)) & 1u; }
-        else { left = x > 0 && (L[x - 1] != kBG); upleft = x > 0 && (prev[x - 1] != kBG); }
-        if (!(left && upleft)) CL.unite(base + x, base + x - W);
-      }
+    const uint32_t* up_bits = cluster.map_shared_rank(bits, rank - 1) + (R - 1) * wpr;
+    for (int wx = tid; wx < wpr; wx += nthreads) {
+      const uint32_t m = bits[wx];
+      const uint32_t up = up_bits[wx];
+      if (m & up)
+        merge_with_row_above<false>(F, m, up, F.base + wx * kSlotsPerWord,
+                                    F.base - wpr * kSlotsPerWord + wx * kSlotsPerWord);
     }
   }
-  cluster.sync();  // forest is final
+  cluster.sync();  // the forest is final
 
-  // ---- 6. flatten run heads to their root, count roots in raster order (contiguous segment chunk per warp) ----
-  const int chunk = (n_seg + nwarps - 1) / nwarps;
-  const int s_begin = min(wid * chunk, n_seg), s_end = min(s_begin + chunk, n_seg);
+  // ---- 8. flatten pieces to their root; count roots in raster order (thread t owns a contiguous word range) ----
+  const int wpt = (n_words + nthreads - 1) / nthreads;
+  const int w_begin = min(tid * wpt, n_words), w_end = min(w_begin + wpt, n_words);
   int my_roots = 0;
-  for (int s = s_begin; s < s_end; ++s) {
-    const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-    const bool valid = x < W;
-    const int i = y * W + x;
-    const uint32_t g = base + i;
-    const bool fg = valid && (L[i] != kBG);
-    const uint32_t m = __ballot_sync(0xffffffffu, fg);
-    const bool head = fg && (lane == 0 || !((m >> (lane - 1)) & 1u));
-    bool is_root = false;
-    if (head) {
-      const uint32_t root = CL.find(g);
-      is_root = (root == g);
-      if (!is_root) L[i] = root;
+  for (int w = w_begin; w < w_end; ++w) {
+    const uint32_t m = bits[w];
+    const int np = __popc(m & ~(m << 1));
+    for (int k = 0; k < np; ++k) {
+      const uint32_t id = F.base + w * kSlotsPerWord + k;
+      const uint32_t root = F.find(id);
+      if (root == id) ++my_roots; else slots[w * kSlotsPerWord + k] = root;
     }
-    my_roots += __popc(__ballot_sync(0xffffffffu, is_root));
   }
-  if (lane == 0) sh.warp_roots[wid] = my_roots;
+  // exclusive scan of my_roots over the block (raster order == thread order)
+  int incl = my_roots;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh.warp_tot[wid] = incl;
   __syncthreads();
   if (wid == 0) {
-    const int v = lane < nwarps ? sh.warp_roots[lane] : 0;
-    int incl = v;
+    const int v = lane < nwarps ? sh.warp_tot[lane] : 0;
+    int winc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
     }
-    sh.warp_base[lane] = incl - v;
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    sh.warp_tot[lane] = winc - v;  // exclusive prefix per warp
+    const int total = __shfl_sync(0xffffffffu, winc, 31);
     if (lane < cs) *cluster.map_shared_rank(&sh.x_roots[rank], lane) = total;
   }
   cluster.sync();  // root counts exchanged; nobody walks the forest any more
   int rank_base = 0, K = 0;
   for (int j = 0; j < cs; ++j) { if (j < rank) rank_base += sh.x_roots[j]; K += sh.x_roots[j]; }
 
-  // ---- 7. number the roots 1..K in raster order; CTA 0 publishes K and initialises the box accumulators ----
+  // ---- 9. number the roots 1..K in raster order; CTA 0 publishes K and initialises the box accumulators ----
   {
-    int running = rank_base + sh.warp_base[wid];
-    for (int s = s_begin; s < s_end; ++s) {
-      const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-      const bool valid = x < W;
-      const int i = y * W + x;
-      const bool is_root = valid && (L[i] == base + static_cast<uint32_t>(i));
-      const uint32_t rm = __ballot_sync(0xffffffffu, is_root);
-      if (is_root) L[i] = kRankFlag | static_cast<uint32_t>(running + __popc(rm & ((1u << lane) - 1u)) + 1);
-      running += __popc(rm);
+    int next = rank_base + sh.warp_tot[wid] + (incl - my_roots) + 1;
+    for (int w = w_begin; w < w_end; ++w) {
+      const uint32_t m = bits[w];
+      const int np = __popc(m & ~(m << 1));
+      for (int k = 0; k < np; ++k)
+        if (slots[w * kSlotsPerWord + k] == F.base + w * kSlotsPerWord + k)
+          slots[w * kSlotsPerWord + k] = kRankFlag | static_cast<uint32_t>(next++);
     }
   }
   const int n_box = min(K, max_boxes);
@@ -305,7 +393,7 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
   if (rank == 0) {
     if (tid == 0 && counts) counts[map] = K;
     if (mybox)
-      for (int k = tid; k < n_box; k += blockDim.x) {
+      for (int k = tid; k < n_box; k += nthreads) {
         mybox[k * 5 + 0] = 0x7fffffff; mybox[k * 5 + 1] = 0x7fffffff;
         mybox[k * 5 + 2] = -1; mybox[k * 5 + 3] = -1; mybox[k * 5 + 4] = 0;
       }
@@ -313,51 +401,66 @@ __global__ void ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32
   }
   cluster.sync();
 
-  // ---- 8a. run heads fetch their component number (possibly from another CTA) and feed the boxes ----
-  for (int s = wid; s < n_seg; s += nwarps) {
-    const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-    const bool valid = x < W;
-    const int i = y * W + x;
-    const uint32_t v = valid ? L[i] : kBG;
-    const bool fg = v != kBG;
-    const uint32_t m = __ballot_sync(0xffffffffu, fg);
-    const bool head = fg && (lane == 0 || !((m >> (lane - 1)) & 1u));
-    if (head) {
+  // ---- 10. every piece fetches its component number (possibly from another CTA) and feeds the boxes ----
+  for (int w = tid; w < n_words; w += nthreads) {
+    const uint32_t m = bits[w];
+    if (m == 0) continue;
+    const int y = w / wpr, wx = w - y * wpr;
+    uint32_t starts = m & ~(m << 1);
+    int k = 0;
+    while (starts) {
+      const int p = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint32_t v = slots[w * kSlotsPerWord + k];
       uint32_t id;
       if (v & kRankFlag) id = v & ~kRankFlag;
-      else { id = *CL.slot(v) & ~kRankFlag; L[i] = kRankFlag | id; }
+      else { id = *F.slot(v) & ~kRankFlag; slots[w * kSlotsPerWord + k] = kRankFlag | id; }
       if (mybox && static_cast<int>(id) <= n_box) {
-        const uint32_t run_end = ~(m >> lane);  // first zero at/after this lane; a full segment from lane 0 has none
-        const int len = run_end ? __ffs(run_end) - 1 : 32;
+        const int len = __popc(piece_from(m, p));
+        const int x0 = (wx << 5) + p;
         int32_t* b = mybox + (id - 1) * 5;
-        atomicMin(b + 0, x); atomicMin(b + 1, r0 + y);
-        atomicMax(b + 2, x + len - 1); atomicMax(b + 3, r0 + y);
+        atomicMin(b + 0, x0); atomicMin(b + 1, r0 + y);
+        atomicMax(b + 2, x0 + len - 1); atomicMax(b + 3, r0 + y);
         atomicAdd(b + 4, len);
       }
+      ++k;
     }
   }
   __syncthreads();
 
-  // ---- 8b. every pixel reads its run head's number; labels leave the SM once, coalesced ----
+  // ---- 11. labels leave the SM once: four pixels per thread, coalesced; all-background quads are free ----
   if (labels) {
-    int32_t* out = labels + map * H * W + base;
-    for (int s = wid; s < n_seg; s += nwarps) {
-      const int y = s / segs, x = ((s - y * segs) << 5) + lane;
-      if (x < W) {
-        const int i = y * W + x;
-        const uint32_t v = L[i];
-        uint32_t id = 0;
-        if (v != kBG) id = (v & kRankFlag) ? (v & ~kRankFlag) : (L[v - base] & ~kRankFlag);
-        out[i] = static_cast<int32_t>(id);
+    int32_t* out = labels + map * H * W + static_cast<long long>(r0) * W;
+    if ((W & 31) == 0) {
+      for (int i = tid; i < (n_px >> 2); i += nthreads) {
+        const int w = i >> 3, q0 = (i & 7) << 2;
+        const uint32_t m = bits[w];
+        int4 o = make_int4(0, 0, 0, 0);
+        if ((m >> q0) & 0xFu) {
+          const uint32_t* ws = slots + w * kSlotsPerWord;
+          if ((m >> q0) & 1u) o.x = static_cast<int>(ws[piece_index(m, q0)] & ~kRankFlag);
+          if ((m >> q0) & 2u) o.y = static_cast<int>(ws[piece_index(m, q0 + 1)] & ~kRankFlag);
+          if ((m >> q0) & 4u) o.z = static_cast<int>(ws[piece_index(m, q0 + 2)] & ~kRankFlag);
+          if ((m >> q0) & 8u) o.w = static_cast<int>(ws[piece_index(m, q0 + 3)] & ~kRankFlag);
+        }
+        reinterpret_cast<int4*>(out)[i] = o;
+      }
+    } else {
+      for (int s = wid; s < rows * wpr; s += nwarps) {
+        const int y = s / wpr, x = ((s - y * wpr) << 5) + lane;
+        if (x < W) {
+          const uint32_t m = bits[s];
+          out[y * W + x] = ((m >> lane) & 1u) ? static_cast<int>(slots[s * kSlotsPerWord + piece_index(m, lane)] & ~kRankFlag) : 0;
+        }
       }
     }
   }
   __threadfence();
   cluster.sync();  // all box atomics are done; no CTA's shared memory is read after this point
 
-  // ---- 9. (xmin, ymin, xmax, ymax, area) -> (x, y, w, h, area) ----
+  // ---- 12. (xmin, ymin, xmax, ymax, area) -> (x, y, w, h, area) ----
   if (rank == 0 && mybox) {
-    for (int k = tid; k < n_box; k += blockDim.x) {
+    for (int k = tid; k < n_box; k += nthreads) {
       const int x0 = __ldcg(mybox + k * 5 + 0), y0 = __ldcg(mybox + k * 5 + 1);
       const int x1 = __ldcg(mybox + k * 5 + 2), y1 = __ldcg(mybox + k * 5 + 3);
       mybox[k * 5 + 2] = x1 - x0 + 1;
@@ -375,18 +478,25 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   if (!heat) return fail(AGENDA_ERR_NULL_POINTER, "ccl_bbox: heat is null");
   if (n < 0 || H <= 0 || W <= 0 || max_boxes < 0) return fail(AGENDA_ERR_BAD_SHAPE, "ccl_bbox: bad shape");
   if (boxes == nullptr) max_boxes = 0;
-  if (static_cast<long long>(H) * W >= (1ll << 31)) return fail(AGENDA_ERR_UNSUPPORTED, "ccl_bbox: map too large");
+  if (static_cast<long long>(H) * W >= (1ll << 26)) return fail(AGENDA_ERR_UNSUPPORTED, "ccl_bbox: map too large");
   if (n == 0) return AGENDA_OK;
   const size_t budget = 200 * 1024;
   const size_t map_bytes = static_cast<size_t>(H) * W * 4;
+  const int wpr = (W + 31) / 32;
+  // per strip of R rows: fp32 strip R*W*4 (re-used for the union-find slots: R*wpr*64 B) + bit mask R*wpr*4
+  auto strip_smem = [&](int R) {
+    const size_t strip = std::max(static_cast<size_t>(R) * W * 4, static_cast<size_t>(R) * wpr * kSlotsPerWord * 4);
+    return ((strip + 127) & ~static_cast<size_t>(127)) + static_cast<size_t>(R) * wpr * 4;
+  };
   int cs = 1;
-  while (cs < kMaxCluster && (static_cast<size_t>((H + cs - 1) / cs) * W * 4 > budget)) cs <<= 1;
-  int R = (H + cs - 1) / cs;
-  if (static_cast<size_t>(R) * W * 4 > budget)
+  while (cs < kMaxCluster && strip_smem((H + cs - 1) / cs) > budget) cs <<= 1;
+  const int R = (H + cs - 1) / cs;
+  if (strip_smem(R) > budget)
     return fail(AGENDA_ERR_UNSUPPORTED, "ccl_bbox: %dx%d map (%zu B) does not fit a 16-CTA cluster's shared memory", H,
                 W, map_bytes);
   cs = (H + R - 1) / R;  // drop empty trailing strips
-  const size_t smem = (static_cast<size_t>(R) * W * 4 + 127) & ~static_cast<size_t>(127);
+  const size_t smem = strip_smem(R);
+  const int strip_bytes = static_cast<int>(smem - static_cast<size_t>(R) * wpr * 4);  // offset of the bit mask
   const int strip_px = R * W;
   const int threads = strip_px >= 16384 ? 1024 : (strip_px >= 4096 ? 512 : 256);
   const int use_bulk = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
@@ -405,6 +515,7 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AGENDA_CUDA(cudaLaunchKernelEx(&cfg, ccl_bbox_kernel, heat, thr, labels, counts, boxes, max_boxes, H, W, R, use_bulk));
+  AGENDA_CUDA(cudaLaunchKernelEx(&cfg, ccl_bbox_kernel, heat, thr, labels, counts, boxes, max_boxes, H, W, R, use_bulk,
+                                 strip_bytes));
   return AGENDA_OK;
 }

@@ -97,12 +97,14 @@ def test_trace_shim_end_to_end(cuda_ok):
     assert torch.equal(one, heat.heat_maps[1])
     assert all(m.processor is None for m in list(stack.attn1) + list(stack.attn2))  # restored
     # daam mode: 3 of the 4 cross-attention layers (mid excluded)
+    from agenda_b200 import UNetCrossAttentionHooker
+    default = UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=[4])
+    stack.set_attn_processor(default)  # in daam mode every non-hooked module keeps the processor it had
     with trace(Pipe(), tokens=[4], latent_hw=16, mode="daam") as trc:
-        for m in stack.attn1:
-            m.set_processor(trc.hooker)  # self-attention keeps "its own" processor in daam mode; give it one here
         with torch.no_grad():
             stack(hs, ctx)
-        assert trc.hooker.num_maps == 3
+        assert trc.hooker.num_maps == 3 and default.num_maps == 1
+    assert all(m.processor is default for m in list(stack.attn1) + list(stack.attn2))
 
 
 def test_postprocess_host_api(cuda_ok):

@@ -104,6 +104,8 @@ def test_ccl_oracle_spec():
 
 
 def test_synthetic_heatmaps_deterministic():
+    from agenda_b200.synthetic import synthetic_heatmaps
     a = O.synthetic_heatmaps(2, 64, seed=0)
     b = O.synthetic_heatmaps(2, 64, seed=0)
     assert a.dtype == np.float32 and np.array_equal(a, b)
+    assert np.array_equal(a, synthetic_heatmaps(2, 64, seed=0))  # product-side workload generator == oracle's
