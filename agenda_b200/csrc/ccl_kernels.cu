@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -79,9 +80,15 @@ struct Forest {
   uint32_t strip_slots;  // slots per strip = R * words_per_row * 16
   uint32_t base;         // first slot id of this strip
 
+  // find with path halving: re-pointing a node at its grandparent only ever moves it closer to the root, so it is
+  // safe against concurrent atomicMin unions (every stored value stays an ancestor)
   __device__ __forceinline__ uint32_t find_local(uint32_t x) const {
     uint32_t p = slots[x - base];
-    while (p != x) { x = p; p = slots[x - base]; }
+    while (p != x) {
+      const uint32_t g = slots[p - base];
+      if (g != p) slots[x - base] = g;
+      x = p; p = g;
+    }
     return x;
   }
   __device__ __forceinline__ void unite_local(uint32_t a, uint32_t b) const {
@@ -480,7 +487,10 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   if (boxes == nullptr) max_boxes = 0;
   if (static_cast<long long>(H) * W >= (1ll << 26)) return fail(AGENDA_ERR_UNSUPPORTED, "ccl_bbox: map too large");
   if (n == 0) return AGENDA_OK;
-  const size_t budget = 200 * 1024;
+  // Shared-memory budget per CTA.  100 KB lets two CTAs (of different clusters) share an SM, so one cluster's
+  // barrier waits are covered by another's work; AGENDA_CCL_SMEM_KB overrides it for experiments.
+  size_t budget = 100 * 1024;
+  if (const char* e = getenv("AGENDA_CCL_SMEM_KB")) { const long kb = atol(e); if (kb >= 8 && kb <= 220) budget = static_cast<size_t>(kb) * 1024; }
   const size_t map_bytes = static_cast<size_t>(H) * W * 4;
   const int wpr = (W + 31) / 32;
   // per strip of R rows: fp32 strip R*W*4 (re-used for the union-find slots: R*wpr*64 B) + bit mask R*wpr*4
@@ -491,14 +501,16 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   int cs = 1;
   while (cs < kMaxCluster && strip_smem((H + cs - 1) / cs) > budget) cs <<= 1;
   const int R = (H + cs - 1) / cs;
-  if (strip_smem(R) > budget)
+  if (strip_smem(R) > 200 * 1024)
     return fail(AGENDA_ERR_UNSUPPORTED, "ccl_bbox: %dx%d map (%zu B) does not fit a 16-CTA cluster's shared memory", H,
                 W, map_bytes);
   cs = (H + R - 1) / R;  // drop empty trailing strips
   const size_t smem = strip_smem(R);
   const int strip_bytes = static_cast<int>(smem - static_cast<size_t>(R) * wpr * 4);  // offset of the bit mask
   const int strip_px = R * W;
-  const int threads = strip_px >= 16384 ? 1024 : (strip_px >= 4096 ? 512 : 256);
+  // measured on 512x512 maps (16 strips of 32 rows): 256 threads 2.86 ms / 512: 3.36 / 1024: 6.0 per 2048 maps
+  int threads = strip_px >= 65536 ? 1024 : (strip_px >= 32768 ? 512 : 256);
+  if (const char* e = getenv("AGENDA_CCL_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 1024 && t % 32 == 0) threads = t; }
   const int use_bulk = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
 
   AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
