@@ -18,39 +18,59 @@
 namespace agenda {
 namespace sm100 {
 
-constexpr int kV2Threads = 320;
-constexpr bool kDynamicIssue = false;
 constexpr float kV2RescaleThreshold = 8.0f;
 
-template <int D>
+// Optional event trace (tools/ubench/trace_attn.cu builds with -DAGENDA_V2_TRACE): CTA (0,0) records clock64() at
+// the pipeline events of the first kTraceTiles key tiles.  Compiled out of the product library.
+#ifdef AGENDA_V2_TRACE
+constexpr int kTraceTiles = 24, kTraceEvents = 8, kTraceActors = 8;
+__device__ long long g_v2_trace[kTraceActors * kTraceTiles * kTraceEvents];
+#define V2_TRACE(actor, j, ev)                                                                             \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & ((actor) >= 6 ? 31 : 127)) == 0 &&           \
+        (j) < kTraceTiles)                                                                                 \
+      g_v2_trace[((actor) * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64();                         \
+  } while (0)
+#else
+#define V2_TRACE(actor, j, ev) do { } while (0)
+#endif
+constexpr int kV2MaxTiles = 3;
+
+// NT query tiles of 128 rows per CTA (one softmax warpgroup each), keys in tiles of BN.
+//   NT = 2, BN = 128: two warpgroups ping-pong (2 softmax warps per SM sub-partition)
+//   NT = 3, BN = 64 : three warpgroups (3 softmax warps per sub-partition) — more warps to cover tcgen05.ld /
+//                     mbarrier / MUFU latencies at small head dims, at the price of twice as many (half-size) tiles
+template <int D, int NT_, int BN_>
 struct V2Cfg {
+  static constexpr int kNT = NT_;
+  static constexpr int kThreads = NT_ * 128 + 64;
   static constexpr int kDP = (D + 15) / 16 * 16;
   static constexpr int kChunks = (D + 63) / 64;
-  static constexpr int kBlockN = (D <= 80) ? 128 : 64;
-  // d = 80 with 128-key tiles has no TMEM room for separate P columns (2*128 + 2*64 + 2*80 > 512): there P
-  // overwrites the S buffer it came from and QK(t, j+1) is issued after PV(t, j) (in-order MMA pipe).
-  static constexpr bool kAliasP = (3 * kBlockN + 2 * kDP > 512);
-  static constexpr int kStages = (kChunks * kBlockN * 128 * 2 * 3 + 2 * kChunks * 128 * 128 <= 200 * 1024) ? 3 : 2;
+  static constexpr int kBlockN = BN_;
+  // without TMEM room for separate P columns (e.g. d = 80: 2*128 + 2*64 + 2*80 > 512) P overwrites the S buffer
+  // it came from and QK(t, j+1) is issued after PV(t, j) (in-order MMA pipe).
+  static constexpr bool kAliasP = (NT_ * kBlockN * 3 / 2 + NT_ * kDP > 512);
   static constexpr int kQTileBytes = kChunks * 128 * 128;
   static constexpr int kKVBytes = kChunks * kBlockN * 128;
-  static constexpr int kColS = 0;                                   // + t * kBlockN
-  static constexpr int kColP = kAliasP ? 0 : 2 * kBlockN;            // + t * (kAliasP ? kBlockN : kBlockN / 2)
+  static constexpr int kStages = (kKVBytes * 2 * 3 + NT_ * kQTileBytes <= 200 * 1024) ? 3 : 2;
+  static constexpr int kColS = 0;                                       // + t * kBlockN
+  static constexpr int kColP = kAliasP ? 0 : NT_ * kBlockN;              // + t * kPStride
   static constexpr int kPStride = kAliasP ? kBlockN : kBlockN / 2;
-  static constexpr int kColO = kAliasP ? 2 * kBlockN : 3 * kBlockN;  // + t * kDP
-  static_assert(kColO + 2 * kDP <= 512, "TMEM overflow");
+  static constexpr int kColO = kAliasP ? NT_ * kBlockN : NT_ * kBlockN * 3 / 2;  // + t * kDP
+  static_assert(kColO + NT_ * kDP <= 512, "TMEM overflow");
+  static_assert(NT_ <= kV2MaxTiles, "too many query tiles");
 };
 
 struct V2Barriers {
   uint64_t q_full;
   uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
-  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
+  uint64_t s_full[kV2MaxTiles], s_free[kV2MaxTiles], p_full[kV2MaxTiles], pv_done[kV2MaxTiles];
   uint32_t tmem_base;
 };
 
-template <int D>
+template <class C>
 constexpr size_t v2_smem_bytes() {
-  using C = V2Cfg<D>;
-  return 1024 + 2 * C::kQTileBytes + 2 * C::kStages * C::kKVBytes + sizeof(V2Barriers) + 64;
+  return 1024 + C::kNT * C::kQTileBytes + 2 * C::kStages * C::kKVBytes + sizeof(V2Barriers) + 64;
 }
 
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -111,167 +131,184 @@ struct Ex2Emu {
 };
 
 // kEmu: share of exponential pairs evaluated by Ex2Emu: 0 none, 2 -> 50 %, 3 -> 37.5 %, 4 -> 25 %, 8 -> 12.5 %
-template <int D, int kEmu>
-__global__ void __launch_bounds__(kV2Threads, 1)
+template <int D, int kEmu, int NT, int BN_>
+__global__ void __launch_bounds__(NT * 128 + 64, 1)
 attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
                           float scale_log2) {
-  using C = V2Cfg<D>;
+  using C = V2Cfg<D, NT, BN_>;
   constexpr int BN = C::kBlockN;
   constexpr int ST = C::kStages;
+  constexpr int kTmaWarp = 4 * NT, kMmaWarp = 4 * NT + 1;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;                               // 2 query tiles
-  unsigned char* sK = sQ + 2 * C::kQTileBytes;            // ST stages
+  unsigned char* sQ = smem;                               // NT query tiles
+  unsigned char* sK = sQ + NT * C::kQTileBytes;           // ST stages
   unsigned char* sV = sK + ST * C::kKVBytes;              // ST stages
   V2Barriers* bars = reinterpret_cast<V2Barriers*>(sV + ST * C::kKVBytes);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * 256;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * (128 * NT);
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int n_tiles = (N + BN - 1) / BN;
+  const int nt = min(NT, (N - q0 + 127) / 128);  // query tiles of this CTA that hold at least one row
 
-  if (tid == 8 * 32) {
+  if (tid == kTmaWarp * 32) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     mbar_init(&bars->q_full, 1);
     for (int s = 0; s < 3; ++s) {
       mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
       mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NT; ++t) {
       mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128);
       mbar_init(&bars->p_full[t], 128); mbar_init(&bars->pv_done[t], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == kMmaWarp) tmem_alloc(&bars->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  if (warp == 8) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      mbar_expect_tx(&bars->q_full, 2 * C::kQTileBytes);
-      for (int t = 0; t < 2; ++t)
+  if (warp == kTmaWarp) {
+    // ============================== TMA producer (warp converged, one elected lane issues) ==============================
+    if (elect_one()) {
+      mbar_expect_tx(&bars->q_full, nt * C::kQTileBytes);
+      for (int t = 0; t < nt; ++t)
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(&map_q, &bars->q_full, sQ + t * C::kQTileBytes + c * 128 * 128, c * 64, h, q0 + t * 128, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % ST;
-        const uint32_t ph = (j / ST) & 1;
-        mbar_wait(&bars->k_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&bars->k_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->k_full[s], C::kKVBytes);
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(&map_k, &bars->k_full[s], sK + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
-        mbar_wait(&bars->v_empty[s], ph ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&bars->v_empty[s], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->v_full[s], C::kKVBytes);
         for (int c = 0; c < C::kChunks; ++c)
           tma_load_4d(&map_v, &bars->v_full[s], sV + s * C::kKVBytes + c * BN * 128, c * 64, h, j * BN, b);
       }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc(128, BN, 0);
-      constexpr uint32_t idesc_pv = make_idesc(128, C::kDP, 1);
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      auto issue_qk = [&](int t, int j) {
-        const int s = j % ST;
+    // The whole warp stays converged (every lane polls the mbarriers); only the tcgen05.mma / tcgen05.commit
+    // instructions sit under elect.sync.  With `if (lane == 0)` around the loop the compiler cannot prove the
+    // operands warp-uniform and wraps every UTCHMMA in an R2UR + ELECT + BRA.U.ANY loop (~14 SASS instructions and
+    // ~50 cycles per MMA): 22 MMAs per tile pair made the issuer itself the critical path behind s_full / pv_done.
+    constexpr uint32_t idesc_qk = make_idesc(128, BN, 0);
+    constexpr uint32_t idesc_pv = make_idesc(128, C::kDP, 1);
+    const uint64_t q_desc = make_sdesc(smem_u32(sQ), 16, 1024);
+    const uint64_t k_desc = make_sdesc(smem_u32(sK), 16, 1024);
+    const uint64_t v_desc = make_sdesc(smem_u32(sV), BN * 128, 1024);
+    // byte offsets are added to the 14-bit (addr >> 4) field; shared memory is < 256 KB so it never carries out
+    auto issue_qk = [&](int t, int s) {  // S(t) = Q(t) K(stage s)^T
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < C::kDP / 16; ++kk) {
-          const uint64_t adesc = make_sdesc(q_addr + t * C::kQTileBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_sdesc(k_addr + s * C::kKVBytes + (kk >> 2) * BN * 128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t adesc = q_desc + static_cast<uint64_t>((t * C::kQTileBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
+          const uint64_t bdesc = k_desc + static_cast<uint64_t>((s * C::kKVBytes + (kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
           umma_ss(tmem + C::kColS + t * BN, adesc, bdesc, idesc_qk, kk != 0);
         }
         umma_commit(&bars->s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j) {
-        const int s = j % ST;
-        tc_fence_after();  // caller has observed p_full(t, j) and v_full(stage)
+      }
+      __syncwarp();
+    };
+    int trace_j = 0;
+    (void)trace_j;
+    auto issue_pv = [&](int t, int s, bool first) {  // O(t) (+)= P(t) V(stage s)
+      tc_fence_after();  // caller has observed p_full(t, j) and v_full(stage)
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk) {
-          const uint64_t bdesc = make_sdesc(v_addr + s * C::kKVBytes + kk * 2048, BN * 128, 1024);
-          umma_ts(tmem + C::kColO + t * C::kDP, tmem + C::kColP + t * C::kPStride + kk * 8, bdesc, idesc_pv, (j | kk) != 0);
+          const uint64_t bdesc = v_desc + static_cast<uint64_t>((s * C::kKVBytes + kk * 2048) >> 4);
+          umma_ts(tmem + C::kColO + t * C::kDP, tmem + C::kColP + t * C::kPStride + kk * 8, bdesc, idesc_pv,
+                  !(first && kk == 0));
         }
         umma_commit(&bars->pv_done[t]);
-      };
-      mbar_wait(&bars->q_full, 0);
-      mbar_wait(&bars->k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      umma_commit(&bars->k_empty[0]);
-      if (C::kAliasP) {
-        // P(t, j) lives in S(t): fixed order PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)
-        for (int j = 0; j < n_tiles; ++j) {
-          const int s = j % ST, s1 = (j + 1) % ST;
-          const bool more = (j + 1 < n_tiles);
-          if (more) mbar_wait(&bars->k_full[s1], ((j + 1) / ST) & 1);
-          mbar_wait(&bars->v_full[s], (j / ST) & 1);
-          for (int t = 0; t < 2; ++t) {
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    mbar_wait(&bars->q_full, 0);
+    mbar_wait(&bars->k_full[0], 0);
+    tc_fence_after();
+    for (int t = 0; t < nt; ++t) issue_qk(t, 0);
+    commit(&bars->k_empty[0]);
+    // s = stage of tile j, s1 = stage of tile j+1; ph / ph1 their ring phases
+    int s = 0, s1 = (ST > 1) ? 1 : 0;
+    uint32_t ph = 0, ph1 = (ST > 1) ? 0u : 1u;
+    if (C::kAliasP) {
+      // P(t, j) lives in S(t): fixed order PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)
+      for (int j = 0; j < n_tiles; ++j) {
+        const bool more = (j + 1 < n_tiles);
+        if (more) mbar_wait(&bars->k_full[s1], ph1);
+        mbar_wait(&bars->v_full[s], ph);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (t < nt) {
             mbar_wait(&bars->p_full[t], j & 1);
-            issue_pv(t, j);
-            if (more) {
-              issue_qk(t, j + 1);
-              if (t == 1) umma_commit(&bars->k_empty[s1]);
-            }
+            issue_pv(t, s, j == 0);
+            if (more) issue_qk(t, s1);
           }
-          umma_commit(&bars->v_empty[s]);
         }
-      } else if (!kDynamicIssue) {
-        // Fixed order QK_A(j+1) PV_A(j) QK_B(j+1) PV_B(j): measured faster than event-driven issue (0.69 vs 0.78 ms
-        // at N=4096, d=40) — the fixed alternation keeps the two softmax warpgroups half a tile out of phase, so
-        // one is in its MUFU-heavy stretch while the other loads / reduces.
-        for (int j = 0; j < n_tiles; ++j) {
-          const int s = j % ST, s1 = (j + 1) % ST;
-          const bool more = (j + 1 < n_tiles);
-          if (more) mbar_wait(&bars->k_full[s1], ((j + 1) / ST) & 1);
-          for (int t = 0; t < 2; ++t) {
-            if (more) {
+        if (more) commit(&bars->k_empty[s1]);
+        commit(&bars->v_empty[s]);
+        s = s1; ph = ph1;
+        if (++s1 == ST) { s1 = 0; ph1 ^= 1u; }
+      }
+    } else {
+      // Fixed order QK_A(j+1) QK_B(j+1) .. | PV_A(j) PV_B(j) ..: every QK(t, j+1) only waits for its own warpgroup to
+      // have pulled S(t, j) into registers (early in the tile), so no warpgroup's next score tile queues behind
+      // another warpgroup's exponentials; the PVs follow in the order the warpgroups finish.
+      for (int j = 0; j < n_tiles; ++j) {
+        const bool more = (j + 1 < n_tiles);
+        if (more) {
+          mbar_wait(&bars->k_full[s1], ph1);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            if (t < nt) {
               mbar_wait(&bars->s_free[t], j & 1);  // S(t, j) is in the softmax warpgroup's registers
               tc_fence_after();
-              issue_qk(t, j + 1);
-              if (t == 1) umma_commit(&bars->k_empty[s1]);
+              V2_TRACE(7, j + 1, 3 + t);
+              issue_qk(t, s1);
+              V2_TRACE(6, j + 1, t);
             }
-            if (t == 0) mbar_wait(&bars->v_full[s], (j / ST) & 1);
-            mbar_wait(&bars->p_full[t], j & 1);
-            issue_pv(t, j);
           }
-          umma_commit(&bars->v_empty[s]);
+          commit(&bars->k_empty[s1]);
         }
-      } else {
-        // Event-driven issue: whichever warpgroup has released its S buffer (-> next QK) or published its P
-        // (-> PV) is served first.
-        int next_qk[2] = {1, 1}, next_pv[2] = {0, 0};
-        while (next_pv[0] < n_tiles || next_pv[1] < n_tiles) {
-          bool progressed = false;
+        mbar_wait(&bars->v_full[s], ph);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int jq = next_qk[t];
-            if (jq < n_tiles && mbar_test(&bars->s_free[t], (jq - 1) & 1) &&
-                mbar_test(&bars->k_full[jq % ST], (jq / ST) & 1)) {
-              tc_fence_after();
-              issue_qk(t, jq);
-              next_qk[t] = jq + 1;
-              if (next_qk[t ^ 1] > jq) umma_commit(&bars->k_empty[jq % ST]);  // both tiles have consumed K(jq)
-              progressed = true;
-            }
-            const int jp = next_pv[t];
-            if (jp < n_tiles && mbar_test(&bars->p_full[t], jp & 1) && mbar_test(&bars->v_full[jp % ST], (jp / ST) & 1)) {
-              issue_pv(t, jp);
-              next_pv[t] = jp + 1;
-              if (next_pv[t ^ 1] > jp) umma_commit(&bars->v_empty[jp % ST]);  // both tiles have consumed V(jp)
-              progressed = true;
-            }
+        for (int t = 0; t < NT; ++t) {
+          if (t < nt) {
+            mbar_wait(&bars->p_full[t], j & 1);
+            V2_TRACE(7, j, t);
+            issue_pv(t, s, j == 0);
+            V2_TRACE(6, j, 3 + t);
           }
-          if (!progressed) __nanosleep(20);
         }
+        commit(&bars->v_empty[s]);
+        s = s1; ph = ph1;
+        if (++s1 == ST) { s1 = 0; ph1 ^= 1u; }
       }
     }
   } else {
     // ============================== softmax warpgroups (thread == query row) ==============================
     const int t = warp >> 2;  // which query tile / warpgroup
+    if (t < nt) {
     const int row = tid & 127;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t s_taddr = tmem + lane_base + C::kColS + t * BN;
@@ -282,8 +319,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
     for (int j = 0; j < n_tiles; ++j) {
+      V2_TRACE(t, j, 0);
       mbar_wait(&bars->s_full[t], j & 1);
       tc_fence_after();
+      V2_TRACE(t, j, 1);
       float sv[BN];
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
@@ -310,14 +349,17 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       mx1 = fmax3(mx1, sv[BN - 2], sv[BN - 1]);
       const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
       const bool need = m_new > m_used + kV2RescaleThreshold;
-      if (j > 0) {
-        // PV(t, j-1) must have drained P(t) (single buffer) and left O(t) quiescent before we touch either
-        mbar_wait(&bars->pv_done[t], (j - 1) & 1);
-        tc_fence_after();
-      }
+      V2_TRACE(t, j, 2);
+      // PV(t, j-1) must have drained P(t) (single buffer) before P(t, j) is stored, and left O(t) quiescent before a
+      // rescale touches it.  The rescale is rare, so the wait normally happens right before the first P store, after
+      // the first 32 columns have been exponentiated (the PV MMA group needs ~500 cycles from p_full to pv_done).
+      bool pv_waited = (j == 0);
       if (j == 0) {
         m_used = m_new;
       } else if (__any_sync(0xffffffffu, need)) {
+        mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+        pv_waited = true;
         const float m_next = need ? m_new : m_used;
         const float f = ex2(m_used - m_next);
         l_run *= f;
@@ -334,6 +376,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
         tmem_wait_st();
       }
+      V2_TRACE(t, j, 3);
       const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
       uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = sum2a;
 #pragma unroll
@@ -363,15 +406,21 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           u[i] = pack_bf16(a0, a1);
           u[i + 1] = pack_bf16(b0, b1);
         }
+        if (c == 0 && !pv_waited) {
+          mbar_wait(&bars->pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
         tmem_st16(p_taddr + c * 16, u);  // P as packed bf16 pairs
       }
       float s0, s1, s2, s3;
       unpack_f32x2(sum2a, s0, s1);
       unpack_f32x2(sum2b, s2, s3);
       l_run += (s0 + s1) + (s2 + s3);
+      V2_TRACE(t, j, 4);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars->p_full[t]);
+      V2_TRACE(t, j, 5);
     }
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(&bars->pv_done[t], (n_tiles - 1) & 1);
@@ -395,9 +444,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       }
     }
     tc_fence_before();
+    }  // t < nt
   }
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -405,46 +455,62 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 
 }  // namespace sm100
 
-template <int D, int kEmu>
+template <int D, int kEmu, int NT, int BN>
 static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
                      cudaStream_t stream) {
-  using C = sm100::V2Cfg<D>;
+  using C = sm100::V2Cfg<D, NT, BN>;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
-  constexpr size_t smem = sm100::v2_smem_bytes<D>();
-  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu>;
+  constexpr size_t smem = sm100::v2_smem_bytes<C>();
+  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid((N + 255) / 256, B * H);
-  kern<<<grid, sm100::kV2Threads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
-                                                  scale * 1.4426950408889634f);
+  dim3 grid((N + 128 * NT - 1) / (128 * NT), B * H);
+  kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
+                                            scale * 1.4426950408889634f);
   AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");
   return AGENDA_OK;
 }
 
-// emu: 0 = every exponential on the MUFU; 2/3/4/8 = 50/37.5/25/12.5 % of them on the FMA pipe
+// emu: 0 = every exponential on the MUFU; 2/3/4/8 = 50/37.5/25/12.5 % of them on the FMA pipe.
+// tiles: 2 = two 128-query tiles per CTA with 128-key tiles (64 for d = 160); 3 = three query tiles with 64-key
+// tiles (d = 40 / 64 only).
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, void* stream) {
+                       int emu, int tiles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define AGENDA_V2(DD)                                                                   \
-  case DD:                                                                              \
+#define AGENDA_V2_EMU(DD, NT, BN)                                                       \
     switch (emu) {                                                                      \
-      case 0: return launch_v2<DD, 0>(q, k, v, out, B, H, N, scale, st);                \
-      case 2: return launch_v2<DD, 2>(q, k, v, out, B, H, N, scale, st);                \
-      case 3: return launch_v2<DD, 3>(q, k, v, out, B, H, N, scale, st);                \
-      case 8: return launch_v2<DD, 8>(q, k, v, out, B, H, N, scale, st);                \
-      default: return launch_v2<DD, 4>(q, k, v, out, B, H, N, scale, st);               \
+      case 0: return launch_v2<DD, 0, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
+      case 2: return launch_v2<DD, 2, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
+      case 3: return launch_v2<DD, 3, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
+      case 8: return launch_v2<DD, 8, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
+      default: return launch_v2<DD, 4, NT, BN>(q, k, v, out, B, H, N, scale, st);       \
     }
+  if (tiles == 3) {
+    switch (d) {
+      case 40: AGENDA_V2_EMU(40, 3, 64)
+      case 64: AGENDA_V2_EMU(64, 3, 64)
+      default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 3-tile variant needs head dim 40 or 64, got %d", d);
+    }
+  }
   switch (d) {
-    AGENDA_V2(40)
-    AGENDA_V2(64)
-    AGENDA_V2(80)
-    AGENDA_V2(160)
+    case 40: AGENDA_V2_EMU(40, 2, 128)
+    case 64: AGENDA_V2_EMU(64, 2, 128)
+    case 80: AGENDA_V2_EMU(80, 2, 128)
+    case 160: AGENDA_V2_EMU(160, 2, 64)
     default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: head dim %d not in {40,64,80,160}", d);
   }
-#undef AGENDA_V2
+#undef AGENDA_V2_EMU
 }
+
+#ifdef AGENDA_V2_TRACE
+extern "C" int agenda_v2_trace_read(long long* host, int n) {
+  const int total = sm100::kTraceActors * sm100::kTraceTiles * sm100::kTraceEvents;
+  if (n < total) return -total;
+  return cudaMemcpyFromSymbol(host, sm100::g_v2_trace, sizeof(long long) * total) == cudaSuccess ? total : -1;
+}
+#endif
 
 }  // namespace agenda

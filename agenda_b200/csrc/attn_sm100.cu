@@ -335,7 +335,7 @@ int attn_common_checks(const char* who, const void* q, const void* k, const void
                        int H, int N, int M, int d);
 
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, void* stream);
+                       int emu, int tiles, void* stream);
 
 // variant: 0 = two query tiles per CTA, ping-pong softmax warpgroups (v2; falls back to variant 1 when N <= 128),
 //          1 = one query tile per CTA, P through TMEM (TS-form PV MMA), 2 = same with P through shared memory (SS)
@@ -346,8 +346,11 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_self_fwd: q/k/v/out must be 16-byte aligned");
   // variants 10/12/13/14/18: v2 with 0 / 50 / 37.5 / 25 / 12.5 % of the exponentials emulated on the FMA pipe
-  if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, stream);
-  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, d == 80 ? 4 : 0, stream);
+  // variants 20/22/23/24/28: the same emulation shares with three query tiles per CTA and 64-key tiles (d = 40 / 64)
+  if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream);
+  if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream);
+  // defaults measured on B200 (tools/bench_attn.py): 25 % emulated exponentials except at d = 64
+  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, d == 64 ? 0 : 4, 2, stream);
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
     return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \

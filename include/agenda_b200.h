@@ -55,7 +55,9 @@ int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out,
 
 /* Test hook: agenda_attn_self_fwd (bf16) with an explicit kernel variant: 0 = default (two 128-query tiles per
  * CTA, ping-pong softmax warpgroups, P through TMEM), 1 = one query tile per CTA with P through TMEM (TS-form
- * tcgen05.mma), 2 = one query tile per CTA with P through a 128B-swizzled shared-memory tile (SS-form). */
+ * tcgen05.mma), 2 = one query tile per CTA with P through a 128B-swizzled shared-memory tile (SS-form);
+ * 10+e = variant 0 with a share of the exponentials on the FMA pipe (e in {0,2,3,4,8} -> 0/50/37.5/25/12.5 %);
+ * 20+e = the same with three query tiles per CTA and 64-key tiles (d = 40 or 64 only). */
 int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                                  int d, float scale, int variant, void* stream);
 

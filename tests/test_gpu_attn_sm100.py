@@ -49,7 +49,22 @@ def test_sm100_self_attention(lib, B, N, H, d, variant):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18])
+@pytest.mark.parametrize("variant", [20, 23, 24])
+@pytest.mark.parametrize("B,N,H,d", [s for s in SHAPES if s[3] in (40, 64)] + [(1, 384, 2, 40), (1, 385, 1, 64)])
+def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
+    """Three query tiles per CTA / 64-key tiles (d = 40, 64), including CTAs whose last tiles are partly or fully
+    past the end of the sequence."""
+    g = torch.Generator().manual_seed(N * 11 + d + H)
+    q = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    k = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    v = (torch.randn(B, N, H * d, generator=g) * 0.25).bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, variant)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
     B, N, H, d = 1, 1024, 2, 40
