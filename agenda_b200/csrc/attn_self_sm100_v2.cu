@@ -13,6 +13,9 @@
 // warpgroup has pulled S(t, j) into registers (s_free), i.e. the next score tile is computed WHILE the current one
 // is being exponentiated, and PV(t, j) runs under softmax(t, j+1): the softmax warpgroups never wait on the MMA.
 // MMA order: QK_A(0) QK_B(0) | QK_A(1) PV_A(0) QK_B(1) PV_B(0) | QK_A(2) PV_A(1) ...
+#include <cstdlib>
+#include <type_traits>
+
 #include "sm100_common.cuh"
 
 namespace agenda {
@@ -27,7 +30,7 @@ constexpr int kTraceTiles = 24, kTraceEvents = 8, kTraceActors = 8;
 __device__ long long g_v2_trace[kTraceActors * kTraceTiles * kTraceEvents];
 #define V2_TRACE(actor, j, ev)                                                                             \
   do {                                                                                                     \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & ((actor) >= 6 ? 31 : 127)) == 0 &&           \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (actor) < kTraceActors &&        \
         (j) < kTraceTiles)                                                                                 \
       g_v2_trace[((actor) * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64();                         \
   } while (0)
@@ -40,10 +43,14 @@ constexpr int kV2MaxTiles = 3;
 //   NT = 2, BN = 128: two warpgroups ping-pong (2 softmax warps per SM sub-partition)
 //   NT = 3, BN = 64 : three warpgroups (3 softmax warps per sub-partition) — more warps to cover tcgen05.ld /
 //                     mbarrier / MUFU latencies at small head dims, at the price of twice as many (half-size) tiles
-template <int D, int NT_, int BN_>
+//   KS = 2 (with NT = 2, BN = 128): TWO warpgroups per query tile, each thread owns half a row (BN/2 columns);
+//                     4 softmax warps per sub-partition while the MMAs keep their efficient 128-key shape.  The two
+//                     halves of a row agree on the running max through shared memory + a 256-thread named barrier.
+template <int D, int NT_, int BN_, int KS_ = 1>
 struct V2Cfg {
   static constexpr int kNT = NT_;
-  static constexpr int kThreads = NT_ * 128 + 64;
+  static constexpr int kKS = KS_;
+  static constexpr int kThreads = NT_ * KS_ * 128 + 64;
   static constexpr int kDP = (D + 15) / 16 * 16;
   static constexpr int kChunks = (D + 63) / 64;
   static constexpr int kBlockN = BN_;
@@ -62,6 +69,7 @@ struct V2Cfg {
 };
 
 struct V2Barriers {
+  float xmax[2][2][2][128];  // [tile parity][query tile][column half][row]: row-max exchange (KS = 2 only)
   uint64_t q_full;
   uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
   uint64_t s_full[kV2MaxTiles], s_free[kV2MaxTiles], p_full[kV2MaxTiles], pv_done[kV2MaxTiles];
@@ -131,15 +139,16 @@ struct Ex2Emu {
 };
 
 // kEmu: share of exponential pairs evaluated by Ex2Emu: 0 none, 2 -> 50 %, 3 -> 37.5 %, 4 -> 25 %, 8 -> 12.5 %
-template <int D, int kEmu, int NT, int BN_>
-__global__ void __launch_bounds__(NT * 128 + 64, 1)
+template <int D, int kEmu, int NT, int BN_, int KS>
+__global__ void __launch_bounds__(NT * KS * 128 + 64, 1)
 attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
-                          float scale_log2) {
-  using C = V2Cfg<D, NT, BN_>;
+                          float scale_log2, int issue_order) {
+  using C = V2Cfg<D, NT, BN_, KS>;
   constexpr int BN = C::kBlockN;
   constexpr int ST = C::kStages;
-  constexpr int kTmaWarp = 4 * NT, kMmaWarp = 4 * NT + 1;
+  constexpr int kTmaWarp = 4 * NT * KS, kMmaWarp = 4 * NT * KS + 1;
+  static_assert(KS == 1 || (KS == 2 && NT <= 2 && !C::kAliasP), "column split needs separate P columns");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sQ = smem;                               // NT query tiles
@@ -161,8 +170,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
     }
     for (int t = 0; t < NT; ++t) {
-      mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128);
-      mbar_init(&bars->p_full[t], 128); mbar_init(&bars->pv_done[t], 1);
+      mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128 * KS);
+      mbar_init(&bars->p_full[t], 128 * KS); mbar_init(&bars->pv_done[t], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -271,34 +280,52 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         if (++s1 == ST) { s1 = 0; ph1 ^= 1u; }
       }
     } else {
-      // Fixed order QK_A(j+1) QK_B(j+1) .. | PV_A(j) PV_B(j) ..: every QK(t, j+1) only waits for its own warpgroup to
-      // have pulled S(t, j) into registers (early in the tile), so no warpgroup's next score tile queues behind
-      // another warpgroup's exponentials; the PVs follow in the order the warpgroups finish.
+      // issue_order 0: QK_A(j+1) PV_A(j) QK_B(j+1) PV_B(j) — keeps the warpgroups out of phase (one is in its exponential
+      //   stretch while the other loads / reduces), but QK_B(j+1) queues behind warpgroup A's exponentials.
+      // issue_order 1: QK_A(j+1) QK_B(j+1) | PV_A(j) PV_B(j) — no score tile waits on another warpgroup; the warpgroups
+      //   drift into phase and share the MUFU.
       for (int j = 0; j < n_tiles; ++j) {
         const bool more = (j + 1 < n_tiles);
-        if (more) {
-          mbar_wait(&bars->k_full[s1], ph1);
+        if (more) mbar_wait(&bars->k_full[s1], ph1);
+        if (issue_order == 1) {
+          if (more) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              if (t < nt) {
+                mbar_wait(&bars->s_free[t], j & 1);  // S(t, j) is in the softmax warpgroup's registers
+                tc_fence_after();
+                issue_qk(t, s1);
+              }
+            }
+            commit(&bars->k_empty[s1]);
+          }
+          mbar_wait(&bars->v_full[s], ph);
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
             if (t < nt) {
-              mbar_wait(&bars->s_free[t], j & 1);  // S(t, j) is in the softmax warpgroup's registers
-              tc_fence_after();
-              V2_TRACE(7, j + 1, 3 + t);
-              issue_qk(t, s1);
-              V2_TRACE(6, j + 1, t);
+              mbar_wait(&bars->p_full[t], j & 1);
+              issue_pv(t, s, j == 0);
             }
           }
-          commit(&bars->k_empty[s1]);
-        }
-        mbar_wait(&bars->v_full[s], ph);
+        } else {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          if (t < nt) {
-            mbar_wait(&bars->p_full[t], j & 1);
-            V2_TRACE(7, j, t);
-            issue_pv(t, s, j == 0);
-            V2_TRACE(6, j, 3 + t);
+          for (int t = 0; t < NT; ++t) {
+            if (t < nt) {
+              if (more) {
+                mbar_wait(&bars->s_free[t], j & 1);
+                tc_fence_after();
+                V2_TRACE(7, j + 1, 3 + t);
+                issue_qk(t, s1);
+                V2_TRACE(6, j + 1, t);
+              }
+              if (t == 0) mbar_wait(&bars->v_full[s], ph);
+              mbar_wait(&bars->p_full[t], j & 1);
+              V2_TRACE(7, j, t);
+              issue_pv(t, s, j == 0);
+              V2_TRACE(6, j, 3 + t);
+            }
           }
+          if (more) commit(&bars->k_empty[s1]);
         }
         commit(&bars->v_empty[s]);
         s = s1; ph = ph1;
@@ -307,56 +334,76 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     }
   } else {
     // ============================== softmax warpgroups (thread == query row) ==============================
-    const int t = warp >> 2;  // which query tile / warpgroup
+    const int wg = warp >> 2;
+    const int t = wg / KS;      // query tile
+    const int half = wg % KS;   // which CW-column slice of the tile's rows this warpgroup owns
     if (t < nt) {
+    constexpr int CW = BN / KS;  // score columns per thread and key tile
     const int row = tid & 127;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t s_taddr = tmem + lane_base + C::kColS + t * BN;
-    const uint32_t p_taddr = tmem + lane_base + C::kColP + t * C::kPStride;
+    const uint32_t s_taddr = tmem + lane_base + C::kColS + t * BN + half * CW;
+    const uint32_t p_taddr = tmem + lane_base + C::kColP + t * C::kPStride + half * (C::kAliasP ? CW : CW / 2);
     const Ex2Emu ex2_emu;
     const uint32_t o_taddr = tmem + lane_base + C::kColO + t * C::kDP;
+    // O column chunks (16 fp32 columns each) this thread rescales / writes out
+    constexpr int kOChunks = C::kDP / 16;
+    const int oc_begin = (KS == 1) ? 0 : (half == 0 ? 0 : (kOChunks + 1) / 2);
+    const int oc_end = (KS == 1) ? kOChunks : (half == 0 ? (kOChunks + 1) / 2 : kOChunks);
     float m_used = -INFINITY;
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
-    for (int j = 0; j < n_tiles; ++j) {
-      V2_TRACE(t, j, 0);
+    // One key tile.  kMasked is only instantiated for a ragged last tile: with a run-time test the compiler
+    // if-converts the masking into an ISETP + FSEL per score on EVERY tile (2 of ~7 instructions per element).
+    auto softmax_tile = [&](const int j, auto masked_c) {
+      constexpr bool kMasked = decltype(masked_c)::value;
+      V2_TRACE((warp < 6 ? warp : 99), j, 0);
       mbar_wait(&bars->s_full[t], j & 1);
       tc_fence_after();
-      V2_TRACE(t, j, 1);
-      float sv[BN];
+      V2_TRACE((warp < 6 ? warp : 99), j, 1);
+      float sv[CW];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
+      for (int c = 0; c < CW / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
       tmem_wait_ld();
       if (!C::kAliasP) {
         tc_fence_before();
         mbar_arrive(&bars->s_free[t]);  // the tensor core may overwrite S(t) with QK(t, j+1) now
       }
-      const int kv_left = N - j * BN;
-      if (kv_left < BN) {
+      if (kMasked) {
+        const int kv_left = N - j * BN - half * CW;
 #pragma unroll
-        for (int i = 0; i < BN; ++i)
+        for (int i = 0; i < CW; ++i)
           if (i >= kv_left) sv[i] = -INFINITY;
       }
-      float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
-      float mx2 = fmax3(sv[6], sv[7], sv[8]), mx3 = fmax3(sv[9], sv[10], sv[11]);
+      float mx;
+      {
+        float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
+        float mx2 = fmax3(sv[6], sv[7], sv[8]), mx3 = fmax3(sv[9], sv[10], sv[11]);
 #pragma unroll
-      for (int i = 12; i + 8 <= BN; i += 8) {
-        mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
-        mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]); mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
+        for (int i = 12; i + 8 <= CW; i += 8) {
+          mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+          mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]); mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
+        }
+        // CW = 128: elements 12..123 covered above, 124..127 here; CW = 64: 12..59 above, 60..63 here
+        mx0 = fmax3(mx0, sv[CW - 4], sv[CW - 3]);
+        mx1 = fmax3(mx1, sv[CW - 2], sv[CW - 1]);
+        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
-      // BN = 128: elements 12..123 covered above, 124..127 here; BN = 64: 12..59 above, 60..63 here
-      mx0 = fmax3(mx0, sv[BN - 4], sv[BN - 3]);
-      mx1 = fmax3(mx1, sv[BN - 2], sv[BN - 1]);
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      if (KS == 2) {
+        // both halves of a row must use the same running max: swap partial maxima through shared memory
+        bars->xmax[j & 1][t][half][row] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+        mx = fmaxf(mx, bars->xmax[j & 1][t][half ^ 1][row]);
+      }
+      const float m_new = mx * scale_log2;
       const bool need = m_new > m_used + kV2RescaleThreshold;
-      V2_TRACE(t, j, 2);
+      V2_TRACE((warp < 6 ? warp : 99), j, 2);
       // PV(t, j-1) must have drained P(t) (single buffer) before P(t, j) is stored, and left O(t) quiescent before a
       // rescale touches it.  The rescale is rare, so the wait normally happens right before the first P store, after
       // the first 32 columns have been exponentiated (the PV MMA group needs ~500 cycles from p_full to pv_done).
       bool pv_waited = (j == 0);
       if (j == 0) {
         m_used = m_new;
-      } else if (__any_sync(0xffffffffu, need)) {
+      } else if (__any_sync(0xffffffffu, need)) {  // (identical in both halves: same rows, same m_new, same m_used)
         mbar_wait(&bars->pv_done[t], (j - 1) & 1);
         tc_fence_after();
         pv_waited = true;
@@ -365,22 +412,24 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         l_run *= f;
         m_used = m_next;
 #pragma unroll
-        for (int c = 0; c < C::kDP / 16; ++c) {
-          float o[16];
-          tmem_ld16(o_taddr + c * 16, o);
-          tmem_wait_ld();
-          uint32_t u[16];
+        for (int c = 0; c < kOChunks; ++c) {
+          if (c >= oc_begin && c < oc_end) {
+            float o[16];
+            tmem_ld16(o_taddr + c * 16, o);
+            tmem_wait_ld();
+            uint32_t u[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(o[i] * f);
-          tmem_st16(o_taddr + c * 16, u);
+            for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(o[i] * f);
+            tmem_st16(o_taddr + c * 16, u);
+          }
         }
         tmem_wait_st();
       }
-      V2_TRACE(t, j, 3);
+      V2_TRACE((warp < 6 ? warp : 99), j, 3);
       const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
       uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = sum2a;
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < CW / 32; ++c) {
         uint32_t u[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
@@ -416,31 +465,41 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       unpack_f32x2(sum2a, s0, s1);
       unpack_f32x2(sum2b, s2, s3);
       l_run += (s0 + s1) + (s2 + s3);
-      V2_TRACE(t, j, 4);
+      V2_TRACE((warp < 6 ? warp : 99), j, 4);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars->p_full[t]);
-      V2_TRACE(t, j, 5);
-    }
+      V2_TRACE((warp < 6 ? warp : 99), j, 5);
+    };
+    const int n_full = N / BN;  // key tiles without padding
+    for (int j = 0; j < n_full; ++j) softmax_tile(j, std::false_type{});
+    if (n_full < n_tiles) softmax_tile(n_full, std::true_type{});
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(&bars->pv_done[t], (n_tiles - 1) & 1);
     tc_fence_after();
+    if (KS == 2) {  // row sum = sum of the two halves' partial sums (both were scaled by the same running max)
+      bars->xmax[0][t][half][row] = l_run;
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      l_run += bars->xmax[0][t][half ^ 1][row];
+    }
     const float inv_l = 1.0f / l_run;
     const int n = q0 + t * 128 + row;
     __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + h * D;
 #pragma unroll
-    for (int c = 0; c < C::kDP / 16; ++c) {
-      float o[16];
-      tmem_ld16(o_taddr + c * 16, o);
-      tmem_wait_ld();
-      if (n < N) {
-        uint4 lo, hi;
-        lo.x = pack_bf16(o[0] * inv_l, o[1] * inv_l); lo.y = pack_bf16(o[2] * inv_l, o[3] * inv_l);
-        lo.z = pack_bf16(o[4] * inv_l, o[5] * inv_l); lo.w = pack_bf16(o[6] * inv_l, o[7] * inv_l);
-        hi.x = pack_bf16(o[8] * inv_l, o[9] * inv_l); hi.y = pack_bf16(o[10] * inv_l, o[11] * inv_l);
-        hi.z = pack_bf16(o[12] * inv_l, o[13] * inv_l); hi.w = pack_bf16(o[14] * inv_l, o[15] * inv_l);
-        if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
-        if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+    for (int c = 0; c < kOChunks; ++c) {
+      if (c >= oc_begin && c < oc_end) {
+        float o[16];
+        tmem_ld16(o_taddr + c * 16, o);
+        tmem_wait_ld();
+        if (n < N) {
+          uint4 lo, hi;
+          lo.x = pack_bf16(o[0] * inv_l, o[1] * inv_l); lo.y = pack_bf16(o[2] * inv_l, o[3] * inv_l);
+          lo.z = pack_bf16(o[4] * inv_l, o[5] * inv_l); lo.w = pack_bf16(o[6] * inv_l, o[7] * inv_l);
+          hi.x = pack_bf16(o[8] * inv_l, o[9] * inv_l); hi.y = pack_bf16(o[10] * inv_l, o[11] * inv_l);
+          hi.z = pack_bf16(o[12] * inv_l, o[13] * inv_l); hi.w = pack_bf16(o[14] * inv_l, o[15] * inv_l);
+          if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+          if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+        }
       }
     }
     tc_fence_before();
@@ -455,51 +514,60 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 
 }  // namespace sm100
 
-template <int D, int kEmu, int NT, int BN>
+template <int D, int kEmu, int NT, int BN, int KS = 1>
 static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
                      cudaStream_t stream) {
-  using C = sm100::V2Cfg<D, NT, BN>;
+  using C = sm100::V2Cfg<D, NT, BN, KS>;
   CUtensorMap mq, mk, mv;
   int rc;
   if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::v2_smem_bytes<C>();
-  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN>;
+  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((N + 128 * NT - 1) / (128 * NT), B * H);
+  int issue_order = 0;
+  if (const char* e = getenv("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only
   kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
-                                            scale * 1.4426950408889634f);
+                                            scale * 1.4426950408889634f, issue_order);
   AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");
   return AGENDA_OK;
 }
 
 // emu: 0 = every exponential on the MUFU; 2/3/4/8 = 50/37.5/25/12.5 % of them on the FMA pipe.
 // tiles: 2 = two 128-query tiles per CTA with 128-key tiles (64 for d = 160); 3 = three query tiles with 64-key
-// tiles (d = 40 / 64 only).
+// tiles (d = 40 / 64 only); 4 = two query tiles, each served by two warpgroups owning half a row (d = 40 / 64).
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
                        int emu, int tiles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define AGENDA_V2_EMU(DD, NT, BN)                                                       \
+#define AGENDA_V2_EMU(DD, NT, BN, KS)                                                   \
     switch (emu) {                                                                      \
-      case 0: return launch_v2<DD, 0, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
-      case 2: return launch_v2<DD, 2, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
-      case 3: return launch_v2<DD, 3, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
-      case 8: return launch_v2<DD, 8, NT, BN>(q, k, v, out, B, H, N, scale, st);        \
-      default: return launch_v2<DD, 4, NT, BN>(q, k, v, out, B, H, N, scale, st);       \
+      case 0: return launch_v2<DD, 0, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
+      case 2: return launch_v2<DD, 2, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
+      case 3: return launch_v2<DD, 3, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
+      case 8: return launch_v2<DD, 8, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
+      default: return launch_v2<DD, 4, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);   \
     }
   if (tiles == 3) {
     switch (d) {
-      case 40: AGENDA_V2_EMU(40, 3, 64)
-      case 64: AGENDA_V2_EMU(64, 3, 64)
+      case 40: AGENDA_V2_EMU(40, 3, 64, 1)
+      case 64: AGENDA_V2_EMU(64, 3, 64, 1)
       default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 3-tile variant needs head dim 40 or 64, got %d", d);
     }
   }
+  if (tiles == 4) {  // two query tiles, two warpgroups (half rows) per tile
+    switch (d) {
+      case 40: AGENDA_V2_EMU(40, 2, 128, 2)
+      case 64: AGENDA_V2_EMU(64, 2, 128, 2)
+      default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: split-row variant needs head dim 40 or 64, got %d", d);
+    }
+  }
   switch (d) {
-    case 40: AGENDA_V2_EMU(40, 2, 128)
-    case 64: AGENDA_V2_EMU(64, 2, 128)
-    case 80: AGENDA_V2_EMU(80, 2, 128)
-    case 160: AGENDA_V2_EMU(160, 2, 64)
+    case 40: AGENDA_V2_EMU(40, 2, 128, 1)
+    case 64: AGENDA_V2_EMU(64, 2, 128, 1)
+    case 80: AGENDA_V2_EMU(80, 2, 128, 1)
+    case 160: AGENDA_V2_EMU(160, 2, 64, 1)
     default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: head dim %d not in {40,64,80,160}", d);
   }
 #undef AGENDA_V2_EMU

@@ -347,10 +347,12 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_self_fwd: q/k/v/out must be 16-byte aligned");
   // variants 10/12/13/14/18: v2 with 0 / 50 / 37.5 / 25 / 12.5 % of the exponentials emulated on the FMA pipe
   // variants 20/22/23/24/28: the same emulation shares with three query tiles per CTA and 64-key tiles (d = 40 / 64)
+  // variants 30/32/33/34/38: two query tiles, two softmax warpgroups per tile (half a row per thread; d = 40 / 64)
+  if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream);
   if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream);
   if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream);
-  // defaults measured on B200 (tools/bench_attn.py): 25 % emulated exponentials except at d = 64
-  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, d == 64 ? 0 : 4, 2, stream);
+  // default measured on B200 (tools/bench_attn.py): two query tiles, full-row threads, 25 % emulated exponentials
+  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2, stream);
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
     return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \

@@ -49,11 +49,11 @@ def test_sm100_self_attention(lib, B, N, H, d, variant):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("variant", [20, 23, 24])
+@pytest.mark.parametrize("variant", [20, 23, 24, 30, 32, 34])
 @pytest.mark.parametrize("B,N,H,d", [s for s in SHAPES if s[3] in (40, 64)] + [(1, 384, 2, 40), (1, 385, 1, 64)])
 def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
-    """Three query tiles per CTA / 64-key tiles (d = 40, 64), including CTAs whose last tiles are partly or fully
-    past the end of the sequence."""
+    """Three query tiles per CTA / 64-key tiles (20+) and two warpgroups per query tile with half a row per thread
+    (30+) at d = 40, 64, including CTAs whose last tiles are partly or fully past the end of the sequence."""
     g = torch.Generator().manual_seed(N * 11 + d + H)
     q = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
     k = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
@@ -64,7 +64,7 @@ def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
     B, N, H, d = 1, 1024, 2, 40
@@ -76,6 +76,23 @@ def test_sm100_peaked_softmax_and_rescale(lib, variant):
     q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
     ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
     out = _run(lib, q, k, v, H, variant)
+    assert (out - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("variant", [0, 10, 14, 20, 30])
+def test_sm100_score_jump_beyond_lazy_max_guard(lib, variant):
+    """Scores of a late key tile tower (by far more than 2^64) over everything before it: the lazy running-max path must
+    re-run that tile against its own max instead of overflowing."""
+    B, N, H, d = 1, 512, 1, 40
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, N, H * d, generator=g)
+    k = torch.randn(B, N, H * d, generator=g)
+    k[:, 300:310] *= 60.0   # a few keys in the third 128-key tile with logits of several hundred
+    v = torch.randn(B, N, H * d, generator=g) * 0.25
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, variant)
+    assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < TOL
 
 

@@ -18,6 +18,20 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, long long* cyc, int ite
       if (MODE == 1) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(x[i]));
       if (MODE == 2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(x[i]));
       if (MODE == 3) asm volatile("ex2.approx.ftz.bf16 %0, %0;" : "+h"(*reinterpret_cast<unsigned short*>(&x[i])));
+      if (MODE == 4) asm volatile("cvt.rn.bf16x2.f32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[(i + 1) & 7]));
+      if (MODE == 5) {  // the softmax inner loop's mix: two ex2 + one pack per element pair
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x[i]));
+        if (i & 1) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x[i]) : "r"(x[i]), "r"(x[i - 1]));
+      }
+      if (MODE == 6) {  // ex2 + packed fma + packed add (no conversion)
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x[i]));
+        if (i & 1) {
+          unsigned long long a, b;
+          asm volatile("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(x[i - 1]), "r"(x[i]));
+          asm volatile("fma.rn.f32x2 %0, %1, %1, %1;" : "=l"(b) : "l"(a));
+          asm volatile("mov.b64 {%0, %1}, %2;" : "=r"(x[i - 1]), "=r"(x[i]) : "l"(b));
+        }
+      }
     }
   }
   const long long t1 = clock64();
@@ -32,9 +46,9 @@ int main() {
   uint32_t* out; long long* cyc;
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 8);
   const int iters = 2000;
-  const char* names[] = {"ex2.f32", "ex2.bf16x2", "ex2.f16x2", "ex2.bf16 (scalar)"};
-  for (int threads : {128, 256, 512, 1024}) {
-    for (int mode = 0; mode < 4; ++mode) {
+  const char* names[] = {"ex2.f32", "ex2.bf16x2", "ex2.f16x2", "ex2.bf16 (scalar)", "cvt.bf16x2.f32", "2 ex2 + 1 cvt pack", "2 ex2 + 1 ffma2"};
+  for (int threads : {128, 512}) {
+    for (int mode = 0; mode < 7; ++mode) {
       auto run = [&](auto kern) {
         kern<<<148, threads>>>(out, cyc, iters);
         kern<<<148, threads>>>(out, cyc, iters);
@@ -47,6 +61,7 @@ int main() {
                ops * per / c, ops / c);
       };
       if (mode == 0) run(k<0>); if (mode == 1) run(k<1>); if (mode == 2) run(k<2>); if (mode == 3) run(k<3>);
+      if (mode == 4) run(k<4>); if (mode == 5) run(k<5>); if (mode == 6) run(k<6>);
     }
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));

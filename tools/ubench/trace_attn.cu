@@ -43,9 +43,9 @@ int main(int argc, char** argv) {
   const long long t0 = at(0, 0, 0);
   printf("softmax events per tile: wait_s | s_ready | max_done | pv_ok | exp_done | p_arrived   (cycles since WG0 start)\n");
   for (int j = 0; j < 16; ++j) {
-    for (int a = 0; a < 3; ++a) {
+    for (int a = 0; a < 6; ++a) {
       if (at(a, j, 0) == 0) continue;
-      printf("j=%2d WG%d:", j, a);
+      printf("j=%2d warp%d:", j, a);
       for (int e = 0; e < 6; ++e) printf(" %7lld", at(a, j, e) - t0);
       printf("   | waitS %5lld ld+max %5lld waitPV %5lld exp %5lld st %5lld\n", at(a, j, 1) - at(a, j, 0), at(a, j, 2) - at(a, j, 1),
              at(a, j, 3) - at(a, j, 2), at(a, j, 4) - at(a, j, 3), at(a, j, 5) - at(a, j, 4));
@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
     printf("\n        issue cost: QK");
     for (int t = 0; t < 3; ++t) if (at(6, j, t)) printf(" t%d %5lld", t, at(6, j, t) - at(7, j, 3 + t));
     printf("  PV");
-    for (int t = 0; t < 3; ++t) if (at(6, j, 3 + t)) printf(" t%d %5lld (p_full->issue start %5lld)", t, at(6, j, 3 + t) - at(7, j, t), at(7, j, t) - at(t, j, 5));
+    for (int t = 0; t < 3; ++t) if (at(6, j, 3 + t)) printf(" t%d %5lld (start@%7lld)", t, at(6, j, 3 + t) - at(7, j, t), at(7, j, t) - t0);
     printf("\n");
   }
   return 0;
