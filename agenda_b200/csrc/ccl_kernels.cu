@@ -32,6 +32,8 @@ namespace agenda {
 constexpr uint32_t kRankFlag = 0x80000000u;
 constexpr int kMaxCluster = 16;
 constexpr int kSlotsPerWord = 16;  // at most 16 pieces (alternating bits) in a 32-pixel word
+constexpr int32_t kCtaOverflowFlag = -1;  // counts[map] value with which the one-CTA kernel hands a map to the cluster kernel
+constexpr int kSmemBoxes = 256;           // boxes accumulated in shared memory by the one-CTA kernel
 
 struct CclStatic {
   unsigned long long mbar;
@@ -146,7 +148,8 @@ __device__ __forceinline__ void merge_with_row_above(const Forest& F, uint32_t m
 
 __global__ void __launch_bounds__(1024, 1)
 ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
-                int32_t* __restrict__ boxes, int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes) {
+                int32_t* __restrict__ boxes, int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes,
+                int only_flagged) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ CclStatic sh;
 
@@ -154,6 +157,9 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
   const int cs = static_cast<int>(cluster.num_blocks());
   const int rank = static_cast<int>(cluster.block_rank());
   const long long map = blockIdx.x / cs;
+  // second-chance launch behind ccl_bbox_cta_kernel: only maps it flagged (piece table overflow) are processed;
+  // the flag is read by every CTA of the cluster before any of them can overwrite it (cluster.sync below)
+  if (only_flagged && __ldcg(counts + map) != kCtaOverflowFlag) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5, nthreads = blockDim.x;
 
   const int r0 = rank * R;
@@ -476,6 +482,323 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// One CTA per map (maps whose bit mask fits one CTA's shared memory, W % 32 == 0).
+//
+// The cluster kernel above keeps the fp32 map resident in distributed shared memory, which caps the number of maps in
+// flight at ~21 per GPU and makes every phase a cluster barrier (46 % of its warp samples, profiles/r01_ccl_*).  Here
+// only the BIT MASK (1 bit per pixel) and a compact piece table live in shared memory:
+//   pass 1  streams the map once for min / max / NaN (float4, 4 loads in flight per thread);
+//   pass 2  re-reads it in REVERSE order — the tail of pass 1 is still in L2 — and thresholds straight into mask words;
+//   pieces (runs of set bits inside a word) get compact ids by a block scan (raster order is preserved, so the
+//   smallest id of a component is still its first pixel and scipy's numbering falls out of a second scan);
+//   union-find, root numbering, boxes (shared-memory accumulators) and the label write need __syncthreads only.
+// Extra HBM traffic: the part of pass 2 that misses L2.  Several CTAs per SM, no cluster, no DSMEM.
+// A map with more pieces than `cap` is flagged in counts[] and redone by the cluster kernel (second launch).
+// L2 eviction-priority hints: pass 1 asks L2 to keep the map (evict_last), pass 2 releases it (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
+                    int32_t* __restrict__ boxes, int max_boxes, int H, int W, int cap, int hints) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ float red_min[32], red_max[32];
+  __shared__ int red_nan[32], warp_tot[32];
+  __shared__ float sh_hstar;
+  __shared__ int sh_mode, sh_total;
+  __shared__ int sbox[kSmemBoxes * 5];
+
+  constexpr int kWarps = kThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long map = blockIdx.x;
+  const int n_px = H * W;
+  const int wpr = W >> 5;
+  const int n_words = H * wpr;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint32_t* slots = bits + n_words;
+  unsigned short* base = reinterpret_cast<unsigned short*>(slots + cap);  // first piece id of every word
+  const float4* src4 = reinterpret_cast<const float4*>(heat + map * n_px);
+  const int n4 = n_px >> 2;
+
+  // ---- pass 1: min / max / NaN ----
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  auto ld1 = [&](int i) { return hints ? ldg_hint(src4 + i, pol_keep) : __ldg(src4 + i); };
+  auto ld2 = [&](int i) { return hints ? ldg_hint(src4 + i, pol_drop) : __ldg(src4 + i); };
+  {
+    float lo = INFINITY, hi = -INFINITY;
+    int nan = 0;
+    int i = tid;
+    for (; i + 3 * kThreads < n4; i += 4 * kThreads) {
+      const float4 a = ld1(i), b = ld1(i + kThreads), c = ld1(i + 2 * kThreads), d = ld1(i + 3 * kThreads);
+      lo = fminf(fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w))), fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
+      lo = fminf(fminf(fminf(lo, c.x), fminf(c.y, fminf(c.z, c.w))), fminf(fminf(d.x, d.y), fminf(d.z, d.w)));
+      hi = fmaxf(fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w))), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+      hi = fmaxf(fmaxf(fmaxf(hi, c.x), fmaxf(c.y, fmaxf(c.z, c.w))), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)));
+      nan |= (a.x != a.x) | (a.y != a.y) | (a.z != a.z) | (a.w != a.w) | (b.x != b.x) | (b.y != b.y) | (b.z != b.z) |
+             (b.w != b.w) | (c.x != c.x) | (c.y != c.y) | (c.z != c.z) | (c.w != c.w) | (d.x != d.x) | (d.y != d.y) |
+             (d.z != d.z) | (d.w != d.w);
+    }
+    for (; i < n4; i += kThreads) {
+      const float4 a = ld1(i);
+      lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
+      hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+      nan |= (a.x != a.x) | (a.y != a.y) | (a.z != a.z) | (a.w != a.w);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) { red_min[wid] = lo; red_max[wid] = hi; red_nan[wid] = nan; }
+  }
+  __syncthreads();
+
+  // ---- warp 0: smallest float h* with ((h*-min)/denom) > thr (32-ary search over ordered bit patterns) ----
+  if (wid == 0) {
+    float mn = lane < kWarps ? red_min[lane] : INFINITY;
+    float mx = lane < kWarps ? red_max[lane] : -INFINITY;
+    int any_nan = lane < kWarps ? red_nan[lane] : 0;
+    mn = warp_min(mn); mx = warp_max(mx);
+    any_nan = __any_sync(0xffffffffu, any_nan);
+    const float denom = np_denominator(mn, mx);
+    int mode = 0;
+    float hstar = 0.f;
+    if (any_nan || !(np_normalize(mx, mn, denom) > thr)) mode = 1;       // NaN map (numpy: all False) or max fails
+    else if (np_normalize(mn, mn, denom) > thr) mode = 2;                // even the minimum passes
+    else {
+      uint32_t lo = f2key(mn), hi = f2key(mx);                            // pass(lo) false, pass(hi) true
+      while (hi - lo > 1u) {
+        const uint32_t span = hi - lo;
+        const uint32_t step = span / 33u + 1u;
+        uint32_t cand = lo + step * static_cast<uint32_t>(lane + 1);
+        const bool valid = (cand - lo) < span;
+        if (!valid) cand = hi;
+        const bool pass = np_normalize(key2f(cand), mn, denom) > thr;
+        const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+        if (pm == 0) {
+          lo = __shfl_sync(0xffffffffu, cand, 31);
+        } else {
+          const int first = __ffs(pm) - 1;
+          const uint32_t new_hi = __shfl_sync(0xffffffffu, cand, first);
+          const uint32_t new_lo = __shfl_sync(0xffffffffu, cand, first > 0 ? first - 1 : 0);
+          hi = new_hi;
+          if (first > 0) lo = new_lo;
+        }
+      }
+      hstar = key2f(hi);
+    }
+    if (lane == 0) { sh_hstar = hstar; sh_mode = mode; }
+  }
+  for (int k = tid; k < kSmemBoxes * 5; k += kThreads) {
+    const int f = k % 5;
+    sbox[k] = (f < 2) ? 0x7fffffff : (f < 4 ? -1 : 0);
+  }
+  __syncthreads();
+  const float hstar = sh_hstar;
+  const int mode = sh_mode;
+
+  // ---- pass 2 (reverse order: the end of the map is the most recently used part of L2): threshold -> mask words ----
+  if (mode == 0) {
+    const int iters = (n4 + kThreads - 1) / kThreads;
+    for (int it = iters - 1; it >= 0; --it) {
+      const int i = it * kThreads + tid;
+      uint32_t nib = 0;
+      if (i < n4) {
+        const float4 v = ld2(i);
+        nib = (v.x >= hstar ? 1u : 0u) | (v.y >= hstar ? 2u : 0u) | (v.z >= hstar ? 4u : 0u) | (v.w >= hstar ? 8u : 0u);
+      }
+      const uint32_t word = __reduce_or_sync(0xFFu << (lane & 24), nib << ((lane & 7) * 4));  // 8 lanes = one word
+      if ((lane & 7) == 0 && i < n4) bits[i >> 3] = word;
+    }
+  } else {
+    const uint32_t fill = (mode == 2) ? 0xFFFFFFFFu : 0u;
+    for (int w = tid; w < n_words; w += kThreads) bits[w] = fill;
+  }
+  __syncthreads();
+
+  // ---- compact piece ids: thread t owns a contiguous word range; exclusive block scan of the piece counts ----
+  const int wpt = (n_words + kThreads - 1) / kThreads;
+  const int w_begin = min(tid * wpt, n_words), w_end = min(w_begin + wpt, n_words);
+  auto block_exclusive_scan = [&](int mine, int& total) -> int {  // returns the exclusive prefix of `mine`
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __syncthreads();  // warp_tot / sh_total from a previous scan have been consumed
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const int v = lane < kWarps ? warp_tot[lane] : 0;
+      int winc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      warp_tot[lane] = winc - v;
+      if (lane == 31) sh_total = winc;
+    }
+    __syncthreads();
+    total = sh_total;
+    return warp_tot[wid] + incl - mine;
+  };
+  int my_pieces = 0;
+  for (int w = w_begin; w < w_end; ++w) {
+    const uint32_t m = bits[w];
+    my_pieces += __popc(m & ~(m << 1));
+  }
+  int P;
+  int next_id = block_exclusive_scan(my_pieces, P);
+  if (P > cap) {  // piece table overflow: hand the map to the cluster kernel
+    if (tid == 0) counts[map] = kCtaOverflowFlag;
+    return;
+  }
+  for (int w = w_begin; w < w_end; ++w) {
+    const uint32_t m = bits[w];
+    const int np = __popc(m & ~(m << 1));
+    base[w] = static_cast<unsigned short>(next_id);
+    for (int k = 0; k < np; ++k) slots[next_id + k] = next_id + k;
+    next_id += np;
+  }
+  __syncthreads();
+
+  // ---- union-find: merge across word borders and with the row above ----
+  Forest F{cg::this_cluster(), slots, 0u, 0u};
+  for (int w = tid; w < n_words; w += kThreads) {
+    const uint32_t m = bits[w];
+    if (m == 0) continue;
+    const int y = w / wpr, wx = w - y * wpr;
+    const uint32_t first = base[w];
+    if (wx > 0 && (m & 1u)) {
+      const uint32_t left = bits[w - 1];
+      if (left >> 31) F.unite_local(first, base[w - 1] + __popc(left & ~(left << 1)) - 1);
+    }
+    if (y > 0) {
+      const uint32_t up = bits[w - wpr];
+      if (up & m) merge_with_row_above<true>(F, m, up, first, base[w - wpr]);
+    }
+  }
+  __syncthreads();
+
+  // ---- flatten; count and number the roots in raster order ----
+  int my_roots = 0;
+  for (int w = w_begin; w < w_end; ++w) {
+    const uint32_t m = bits[w];
+    const int np = __popc(m & ~(m << 1));
+    const uint32_t id0 = base[w];
+    for (int k = 0; k < np; ++k) {
+      const uint32_t id = id0 + k;
+      uint32_t x = id, p = slots[x];
+      while (p != x) { x = p; p = slots[x]; }
+      if (x == id) ++my_roots; else slots[id] = x;  // non-roots point straight at their root (roots never change now)
+    }
+  }
+  int K;
+  int next_label = block_exclusive_scan(my_roots, K) + 1;
+  // (the scan's barriers order every flatten write before the numbering below; a non-root's target is a root, and roots
+  //  are only rewritten by their owner after this point, flagged, so readers in the next phase can tell them apart)
+  for (int w = w_begin; w < w_end; ++w) {
+    const uint32_t m = bits[w];
+    const int np = __popc(m & ~(m << 1));
+    const uint32_t id0 = base[w];
+    for (int k = 0; k < np; ++k)
+      if (slots[id0 + k] == id0 + k) slots[id0 + k] = kRankFlag | static_cast<uint32_t>(next_label++);
+  }
+  __syncthreads();
+
+  // ---- every piece resolves its label and feeds the boxes ----
+  const int n_box = min(K, max_boxes);
+  int32_t* mybox = boxes ? boxes + map * static_cast<long long>(max_boxes) * 5 : nullptr;
+  if (tid == 0) counts[map] = K;
+  if (mybox)
+    for (int k = kSmemBoxes + tid; k < n_box; k += kThreads) {  // boxes beyond the shared-memory window: global atomics
+      mybox[k * 5 + 0] = 0x7fffffff; mybox[k * 5 + 1] = 0x7fffffff;
+      mybox[k * 5 + 2] = -1; mybox[k * 5 + 3] = -1; mybox[k * 5 + 4] = 0;
+    }
+  if (n_box > kSmemBoxes) { __threadfence_block(); __syncthreads(); }
+  for (int w = tid; w < n_words; w += kThreads) {
+    const uint32_t m = bits[w];
+    if (m == 0) continue;
+    const int y = w / wpr, wx = w - y * wpr;
+    const uint32_t id0 = base[w];
+    uint32_t starts = m & ~(m << 1);
+    int k = 0;
+    while (starts) {
+      const int p = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint32_t v = slots[id0 + k];
+      uint32_t label;
+      if (v & kRankFlag) label = v & ~kRankFlag;
+      else { label = slots[v] & ~kRankFlag; slots[id0 + k] = kRankFlag | label; }
+      if (mybox && static_cast<int>(label) <= n_box) {
+        const int len = __popc(piece_from(m, p));
+        const int x0 = (wx << 5) + p;
+        if (label <= kSmemBoxes) {
+          int* b = sbox + (label - 1) * 5;
+          atomicMin(b + 0, x0); atomicMin(b + 1, y); atomicMax(b + 2, x0 + len - 1); atomicMax(b + 3, y); atomicAdd(b + 4, len);
+        } else {
+          int32_t* b = mybox + (label - 1) * 5;
+          atomicMin(b + 0, x0); atomicMin(b + 1, y); atomicMax(b + 2, x0 + len - 1); atomicMax(b + 3, y); atomicAdd(b + 4, len);
+        }
+      }
+      ++k;
+    }
+  }
+  __syncthreads();
+
+  // ---- labels leave the SM once: four pixels per thread, coalesced; all-background quads are free ----
+  if (labels) {
+    int4* out4 = reinterpret_cast<int4*>(labels + map * n_px);
+    for (int i = tid; i < n4; i += kThreads) {
+      const int w = i >> 3, q0 = (i & 7) << 2;
+      const uint32_t m = bits[w];
+      int4 o = make_int4(0, 0, 0, 0);
+      if ((m >> q0) & 0xFu) {
+        const uint32_t* ws = slots + base[w];
+        if ((m >> q0) & 1u) o.x = static_cast<int>(ws[piece_index(m, q0)] & ~kRankFlag);
+        if ((m >> q0) & 2u) o.y = static_cast<int>(ws[piece_index(m, q0 + 1)] & ~kRankFlag);
+        if ((m >> q0) & 4u) o.z = static_cast<int>(ws[piece_index(m, q0 + 2)] & ~kRankFlag);
+        if ((m >> q0) & 8u) o.w = static_cast<int>(ws[piece_index(m, q0 + 3)] & ~kRankFlag);
+      }
+      __stcs(out4 + i, o);  // streaming store: labels are never re-read, keep L2 for the heat maps
+    }
+  }
+  // ---- boxes: (xmin, ymin, xmax, ymax, area) -> (x, y, w, h, area) ----
+  if (mybox) {
+    for (int k = tid; k < min(n_box, kSmemBoxes); k += kThreads) {
+      const int x0 = sbox[k * 5 + 0], y0 = sbox[k * 5 + 1], x1 = sbox[k * 5 + 2], y1 = sbox[k * 5 + 3];
+      mybox[k * 5 + 0] = x0; mybox[k * 5 + 1] = y0; mybox[k * 5 + 2] = x1 - x0 + 1; mybox[k * 5 + 3] = y1 - y0 + 1;
+      mybox[k * 5 + 4] = sbox[k * 5 + 4];
+    }
+    if (n_box > kSmemBoxes) {
+      __threadfence();  // (global atomics of this CTA are complete: __syncthreads above)
+      for (int k = kSmemBoxes + tid; k < n_box; k += kThreads) {
+        const int x0 = __ldcg(mybox + k * 5 + 0), y0 = __ldcg(mybox + k * 5 + 1);
+        const int x1 = __ldcg(mybox + k * 5 + 2), y1 = __ldcg(mybox + k * 5 + 3);
+        mybox[k * 5 + 2] = x1 - x0 + 1;
+        mybox[k * 5 + 3] = y1 - y0 + 1;
+      }
+    }
+  }
+}
+
 }  // namespace agenda
 
 using namespace agenda;
@@ -513,6 +836,46 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   if (const char* e = getenv("AGENDA_CCL_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 1024 && t % 32 == 0) threads = t; }
   const int use_bulk = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
 
+  // ---- one CTA per map when the bit mask fits (see ccl_bbox_cta_kernel); the cluster kernel then only redoes flagged maps ----
+  int only_flagged = 0;
+  {
+    const long long n_px = static_cast<long long>(H) * W;
+    const long long n_words = n_px / 32;
+    bool use_cta = counts != nullptr && (W & 31) == 0 && n_words <= 12288 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
+    if (const char* e = getenv("AGENDA_CCL_CTA")) use_cta = use_cta && atoi(e) != 0;
+    if (use_cta) {
+      const size_t fixed = static_cast<size_t>(n_words) * 6;  // mask words (4 B) + first piece id per word (2 B)
+      size_t target = std::max<size_t>(72 * 1024, fixed + 16 * 1024);  // 72 KB: three CTAs per SM
+      if (const char* e = getenv("AGENDA_CCL_CTA_SMEM_KB")) { const long kb = atol(e); if (kb >= 4 && kb <= 200) target = static_cast<size_t>(kb) * 1024; }
+      long long cap = std::min<long long>({16 * n_words, 65535ll, static_cast<long long>((target - std::min(target, fixed)) / 4)});
+      cap &= ~1ll;  // keeps the u16 table 4-byte aligned behind the slots
+      if (cap >= 64 || cap >= 16 * n_words - 1) {
+        const size_t smem_cta = static_cast<size_t>(n_words) * 4 + static_cast<size_t>(cap) * 4 + static_cast<size_t>(n_words) * 2 + 16;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define AGENDA_CCL_CTA(T)                                                                                              \
+  do {                                                                                                                 \
+    AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                     static_cast<int>(smem_cta)));                                                     \
+    ccl_bbox_cta_kernel<T><<<n, T, smem_cta, st>>>(heat, thr, labels, counts, boxes, max_boxes, H, W,                  \
+                                                   static_cast<int>(cap), hints);                                      \
+  } while (0)
+        int hints = 1;  // measured: +1-2 % (pass 2 still misses L2: ~300 MB of maps are in flight, L2 is 126 MB)
+        if (const char* e = getenv("AGENDA_CCL_HINTS")) hints = atoi(e);
+        int cta_threads = n_px >= 65536 ? 1024 : (n_px >= 16384 ? 256 : 128);
+        if (const char* e = getenv("AGENDA_CCL_CTA_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) cta_threads = t; }
+        if (cta_threads == 1024) AGENDA_CCL_CTA(1024);
+        else if (cta_threads == 512) AGENDA_CCL_CTA(512);
+        else if (cta_threads == 256) AGENDA_CCL_CTA(256);
+        else AGENDA_CCL_CTA(128);
+#undef AGENDA_CCL_CTA
+        AGENDA_LAUNCH_CHECK("ccl_bbox_cta_kernel");
+        if (cap >= 16 * n_words) return AGENDA_OK;  // the piece table cannot overflow: no second launch
+        only_flagged = 1;
+      }
+    }
+  }
+
   AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   if (cs > 8) AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -528,6 +891,6 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AGENDA_CUDA(cudaLaunchKernelEx(&cfg, ccl_bbox_kernel, heat, thr, labels, counts, boxes, max_boxes, H, W, R, use_bulk,
-                                 strip_bytes));
+                                 strip_bytes, only_flagged));
   return AGENDA_OK;
 }
