@@ -24,12 +24,15 @@ namespace sm100 {
 constexpr int kXBlockM = 128;
 constexpr int kXThreads = 192;
 constexpr int kXMPad = 80;      // 77 prompt tokens padded to a multiple of 16
-constexpr int kXSlot = 96;      // TMEM columns reserved per S/P buffer
+constexpr int kXSlot = 80;      // TMEM columns per S/P buffer (S: 80 fp32 columns; P: 48 packed columns over it)
+constexpr int kXFewTokens = 8;  // heat maps for at most this many tokens take the register-light path
 constexpr int kHeatLd = 81;     // padded accumulator row in shared memory (bank-conflict free)
 
 template <int D>
 struct XCfg {
   static constexpr int kDP = (D + 15) / 16 * 16;
+  // TMEM columns actually needed, rounded to the power of two tcgen05.alloc wants: 256 at d = 40, so two CTAs fit an SM
+  static constexpr int kTmemCols = (2 * kXSlot + 2 * kDP <= 256) ? 256 : 512;
   static constexpr int kChunks = (D + 63) / 64;
   static constexpr int kStages = (D <= 80) ? 3 : 2;
   static constexpr int kQBytes = kChunks * kXBlockM * 128;
@@ -51,8 +54,12 @@ constexpr size_t x_smem_bytes() {
   return 1024 + XCfg<D>::kStages * XCfg<D>::kStageBytes + sizeof(XBarriers) + 64;
 }
 
-template <int D>
-__global__ void __launch_bounds__(kXThreads, 1)
+// kFew: heat maps are wanted for <= kXFewTokens key tokens (what every caller of the reference reads,
+// data_generation.py:74-77): only those columns are accumulated (the raw scores are fetched again from TMEM with
+// one-column loads and pushed through the same fp32 ops, so the values are bit-identical to the all-token path).
+// That frees ~70 registers per thread, and with 256 TMEM columns two CTAs share an SM at d = 40.
+template <int D, bool kFew>
+__global__ void __launch_bounds__(kXThreads, (kFew && XCfg<D>::kTmemCols == 256) ? 2 : 1)
 attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out,
                         float* __restrict__ maps, const TokenList tl, int H, int N, int M, int b_first,
@@ -62,7 +69,7 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   XBarriers* bars = reinterpret_cast<XBarriers*>(smem + C::kStages * C::kStageBytes);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kXBlockM;
   const int b = blockIdx.y;
   const bool want_heat = (maps != nullptr) && (b >= b_first);
@@ -76,22 +83,22 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 5) tmem_alloc(&bars->tmem_base, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
   if (warp == 4) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      for (int h = 0; h < H; ++h) {
-        const int st = h % C::kStages;
-        const uint32_t ph = (h / C::kStages) & 1;
-        unsigned char* sQ = smem + st * C::kStageBytes;
-        unsigned char* sK = sQ + C::kQBytes;
-        unsigned char* sV = sK + C::kKVBytes;
-        mbar_wait(&bars->in_empty[st], ph ^ 1);
+    // ============================== TMA producer (warp converged, one elected lane issues) ==============================
+    int st = 0;
+    uint32_t ph = 0;
+    for (int h = 0; h < H; ++h) {
+      unsigned char* sQ = smem + st * C::kStageBytes;
+      unsigned char* sK = sQ + C::kQBytes;
+      unsigned char* sV = sK + C::kKVBytes;
+      mbar_wait(&bars->in_empty[st], ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->in_full[st], C::kStageBytes);
         for (int c = 0; c < C::kChunks; ++c) {
           tma_load_4d(&map_q, &bars->in_full[st], sQ + c * kXBlockM * 128, c * 64, h, q0, b);
@@ -99,52 +106,63 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           tma_load_4d(&map_v, &bars->in_full[st], sV + c * kXMPad * 128, c * 64, h, 0, b);
         }
       }
+      __syncwarp();
+      if (++st == C::kStages) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 5) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc(kXBlockM, kXMPad, 0);
-      constexpr uint32_t idesc_pv = make_idesc(kXBlockM, C::kDP, 1);
-      auto issue_pv = [&](int h) {
-        const int sb = h & 1, st = h % C::kStages;
-        const uint32_t ph = (h >> 1) & 1;
-        mbar_wait(&bars->p_full[sb], ph);
-        mbar_wait(&bars->o_free[sb], ph ^ 1);  // O[sb] drained by the epilogue of head h-2
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + st * C::kStageBytes + C::kQBytes + C::kKVBytes);
+    // ============================== MMA issuer (warp converged; tcgen05.mma / commit under elect.sync) ==============================
+    constexpr uint32_t idesc_qk = make_idesc(kXBlockM, kXMPad, 0);
+    constexpr uint32_t idesc_pv = make_idesc(kXBlockM, C::kDP, 1);
+    const uint64_t q_desc0 = make_sdesc(smem_u32(smem), 16, 1024);
+    const uint64_t k_desc0 = make_sdesc(smem_u32(smem + C::kQBytes), 16, 1024);
+    const uint64_t v_desc0 = make_sdesc(smem_u32(smem + C::kQBytes + C::kKVBytes), kXMPad * 128, 1024);
+    auto issue_pv = [&](int h, int st) {
+      const int sb = h & 1;
+      const uint32_t ph = (h >> 1) & 1;
+      mbar_wait(&bars->p_full[sb], ph);
+      mbar_wait(&bars->o_free[sb], ph ^ 1);  // O[sb] drained by the epilogue of head h-2
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < kXMPad / 16; ++kk) {
-          const uint64_t bdesc = make_sdesc(v_addr + kk * 2048, kXMPad * 128, 1024);
+          const uint64_t bdesc = v_desc0 + static_cast<uint64_t>((st * C::kStageBytes + kk * 2048) >> 4);
           umma_ts(tmem + C::kColO + sb * C::kDP, tmem + sb * kXSlot + kk * 8, bdesc, idesc_pv, kk != 0);
         }
         umma_commit(&bars->in_empty[st]);
         umma_commit(&bars->pv_done[sb]);
-      };
-      for (int h = 0; h < H; ++h) {
-        const int sb = h & 1, st = h % C::kStages;
-        mbar_wait(&bars->in_full[st], (h / C::kStages) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(smem + st * C::kStageBytes);
-        const uint32_t k_addr = q_addr + C::kQBytes;
+      }
+      __syncwarp();
+    };
+    int st = 0, st_prev = 0;
+    uint32_t ph = 0;
+    for (int h = 0; h < H; ++h) {
+      const int sb = h & 1;
+      mbar_wait(&bars->in_full[st], ph);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < C::kDP / 16; ++kk) {
-          const uint64_t adesc = make_sdesc(q_addr + (kk >> 2) * kXBlockM * 128 + (kk & 3) * 32, 16, 1024);
-          const uint64_t bdesc = make_sdesc(k_addr + (kk >> 2) * kXMPad * 128 + (kk & 3) * 32, 16, 1024);
+          const uint64_t adesc = q_desc0 + static_cast<uint64_t>((st * C::kStageBytes + (kk >> 2) * kXBlockM * 128 + (kk & 3) * 32) >> 4);
+          const uint64_t bdesc = k_desc0 + static_cast<uint64_t>((st * C::kStageBytes + (kk >> 2) * kXMPad * 128 + (kk & 3) * 32) >> 4);
           umma_ss(tmem + sb * kXSlot, adesc, bdesc, idesc_qk, kk != 0);
         }
         umma_commit(&bars->s_full[sb]);
-        if (h > 0) issue_pv(h - 1);
       }
-      issue_pv(H - 1);
+      __syncwarp();
+      if (h > 0) issue_pv(h - 1, st_prev);
+      st_prev = st;
+      if (++st == C::kStages) { st = 0; ph ^= 1u; }
     }
+    issue_pv(H - 1, st_prev);
   } else {
     // ============================== softmax warpgroup (thread == query row) ==============================
     const int row = tid;
     const int n = q0 + row;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    float acc[kXMPad];
+    constexpr int kAcc = kFew ? kXFewTokens : kXMPad;
+    float acc[kAcc];
 #pragma unroll
-    for (int i = 0; i < kXMPad; ++i) acc[i] = 0.f;
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
 
     auto drain_o = [&](int g) {  // O of head g: TMEM -> bf16 -> global
       const int ob = g & 1;
@@ -172,15 +190,27 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       const int sb = h & 1;
       mbar_wait(&bars->s_full[sb], (h >> 1) & 1);
       tc_fence_after();
-      float sv[kXSlot];
+      float sv[96];
+      float sel[kFew ? kXFewTokens : 1];
       const uint32_t s_taddr = tmem + lane_base + sb * kXSlot;
       tmem_ld32(s_taddr, sv);
       tmem_ld32(s_taddr + 32, sv + 32);
       tmem_ld16(s_taddr + 64, sv + 64);
-      tmem_wait_ld();
+      if (kFew && want_heat) {
 #pragma unroll
-      for (int i = 0; i < kXMPad; ++i)
-        if (i >= M) sv[i] = -INFINITY;
+        for (int t = 0; t < kXFewTokens; ++t)
+          if (t < tl.n) sel[t] = tmem_ld1(s_taddr + tl.idx[t]);
+      }
+      tmem_wait_ld();
+      if (M >= 64) {  // the usual case (77 prompt tokens): only the last 16 columns can be padding
+#pragma unroll
+        for (int i = 64; i < kXMPad; ++i)
+          if (i >= M) sv[i] = -INFINITY;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kXMPad; ++i)
+          if (i >= M) sv[i] = -INFINITY;
+      }
       float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
       for (int i = 4; i < kXMPad; i += 4) {
@@ -198,13 +228,19 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
       for (int i = 0; i < kXMPad; ++i) sv[i] *= inv_l;  // normalised probabilities: PV needs no later division
       if (want_heat) {
+        if (kFew) {
 #pragma unroll
-        for (int i = 0; i < kXMPad; ++i) acc[i] += sv[i];
+          for (int t = 0; t < kXFewTokens; ++t)
+            if (t < tl.n) acc[t] += ex2(fmaf(sel[t], scale_log2, -m)) * inv_l;  // same ops as sv[idx[t]] above
+        } else {
+#pragma unroll
+          for (int i = 0; i < kXMPad; ++i) acc[i] += sv[i];
+        }
       }
 #pragma unroll
-      for (int i = kXMPad; i < kXSlot; ++i) sv[i] = 0.f;
+      for (int i = kXMPad; i < 96; ++i) sv[i] = 0.f;
 #pragma unroll
-      for (int c = 0; c < kXSlot / 32; ++c) {
+      for (int c = 0; c < 3; ++c) {
         uint32_t u[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) u[i] = pack_bf16(sv[c * 32 + 2 * i], sv[c * 32 + 2 * i + 1]);
@@ -219,17 +255,30 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 
     // ---- heat epilogue: mean over heads, selected token columns, coalesced per token plane ----
     if (want_heat) {
-      // all MMAs and TMA loads of this CTA have completed (pv_done of the last head was observed)
-      float* srow = reinterpret_cast<float*>(smem) + row * kHeatLd;
-#pragma unroll
-      for (int i = 0; i < kXMPad; ++i) srow[i] = acc[i];
       const float inv_h = 1.0f / static_cast<float>(H);
       float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n;
-      if (n < N) {
-        for (int t = 0; t < tl.n; ++t) {
-          const float val = srow[tl.idx[t]] * inv_h;
-          float* ptr = dst + static_cast<long long>(t) * N;
-          *ptr = accumulate ? (*ptr + val) : val;
+      if (kFew) {
+        if (n < N) {
+#pragma unroll
+          for (int t = 0; t < kXFewTokens; ++t) {
+            if (t < tl.n) {
+              const float val = acc[t] * inv_h;
+              float* ptr = dst + static_cast<long long>(t) * N;
+              *ptr = accumulate ? (*ptr + val) : val;
+            }
+          }
+        }
+      } else {
+        // all MMAs and TMA loads of this CTA have completed (pv_done of the last head was observed)
+        float* srow = reinterpret_cast<float*>(smem) + row * kHeatLd;
+#pragma unroll
+        for (int i = 0; i < kXMPad; ++i) srow[i] = acc[i];
+        if (n < N) {
+          for (int t = 0; t < tl.n; ++t) {
+            const float val = srow[tl.idx[t]] * inv_h;
+            float* ptr = dst + static_cast<long long>(t) * N;
+            *ptr = accumulate ? (*ptr + val) : val;
+          }
         }
       }
     }
@@ -238,14 +287,14 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, C::kTmemCols);
   }
 }
 
 }  // namespace sm100
 
-template <int D>
-static int launch_cross(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, float scale,
+template <int D, bool kFew>
+static int launch_cross_t(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, float scale,
                         const TokenList& tl, int b_first, float* maps, int accumulate, cudaStream_t stream) {
   using C = sm100::XCfg<D>;
   CUtensorMap mq, mk, mv;
@@ -254,13 +303,21 @@ static int launch_cross(const void* q, const void* k, const void* v, void* out, 
   if ((rc = make_head_map(&mk, k, B, H, M, D, sm100::kXMPad)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mv, v, B, H, M, D, sm100::kXMPad)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::x_smem_bytes<D>();
-  auto kern = sm100::attn_cross_sm100_kernel<D>;
+  auto kern = sm100::attn_cross_sm100_kernel<D, kFew>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((N + sm100::kXBlockM - 1) / sm100::kXBlockM, B);
   kern<<<grid, sm100::kXThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), maps, tl, H, N, M,
                                                  b_first, accumulate, scale * 1.4426950408889634f);
   AGENDA_LAUNCH_CHECK("attn_cross_sm100_kernel");
   return AGENDA_OK;
+}
+
+template <int D>
+static int launch_cross(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, float scale,
+                        const TokenList& tl, int b_first, float* maps, int accumulate, cudaStream_t stream) {
+  const bool few = (maps == nullptr) || tl.n <= sm100::kXFewTokens;
+  return few ? launch_cross_t<D, true>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, stream)
+             : launch_cross_t<D, false>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, stream);
 }
 
 // bf16 tensor-core path; returns AGENDA_ERR_UNSUPPORTED for shapes it does not cover.

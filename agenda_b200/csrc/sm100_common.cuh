@@ -131,6 +131,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
       : "r"(taddr)
       : "memory");
 }
+// one 32-bit column: thread t of the warp gets TMEM lane (base_lane + t), column `col` of taddr
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t u;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(u) : "r"(taddr) : "memory");
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* u) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
