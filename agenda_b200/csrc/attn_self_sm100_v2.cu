@@ -50,7 +50,7 @@ template <int D, int NT_, int BN_, int KS_ = 1>
 struct V2Cfg {
   static constexpr int kNT = NT_;
   static constexpr int kKS = KS_;
-  static constexpr int kThreads = NT_ * KS_ * 128 + 64;
+  static constexpr int kThreads = NT_ * KS_ * 128 + 32 + 32 * NT_;  // softmax warpgroups, TMA warp, one MMA warp per query tile
   static constexpr int kDP = (D + 15) / 16 * 16;
   static constexpr int kChunks = (D + 63) / 64;
   static constexpr int kBlockN = BN_;
@@ -64,6 +64,10 @@ struct V2Cfg {
   static constexpr int kColP = kAliasP ? 0 : NT_ * kBlockN;              // + t * kPStride
   static constexpr int kPStride = kAliasP ? kBlockN : kBlockN / 2;
   static constexpr int kColO = kAliasP ? NT_ * kBlockN : NT_ * kBlockN * 3 / 2;  // + t * kDP
+  // A head dim that is not a multiple of 16 leaves zero-padded V columns inside the PV MMA's N extent: column D of
+  // every V tile is set to 1.0, so O[:, D] accumulates the softmax denominator sum_j P (in fp32, from the same
+  // bf16-rounded P the numerator uses) and the softmax warps drop one packed add per pair of scores.
+  static constexpr bool kSumInMma = (kDP > D);
   static_assert(kColO + NT_ * kDP <= 512, "TMEM overflow");
   static_assert(NT_ <= kV2MaxTiles, "too many query tiles");
 };
@@ -140,7 +144,7 @@ struct Ex2Emu {
 
 // kEmu: share of exponential pairs evaluated by Ex2Emu: 0 none, 2 -> 50 %, 3 -> 37.5 %, 4 -> 25 %, 8 -> 12.5 %
 template <int D, int kEmu, int NT, int BN_, int KS>
-__global__ void __launch_bounds__(NT * KS * 128 + 64, 1)
+__global__ void __launch_bounds__(NT * KS * 128 + 32 + 32 * NT, 1)
 attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
                           float scale_log2, int issue_order) {
@@ -165,9 +169,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (tid == kTmaWarp * 32) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     mbar_init(&bars->q_full, 1);
+    const int releasers = ((issue_order & 3) == 2) ? nt : 1;  // MMA warps that must have consumed a K / V stage
     for (int s = 0; s < 3; ++s) {
-      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
-      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], releasers);
+      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], releasers);
     }
     for (int t = 0; t < NT; ++t) {
       mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128 * KS);
@@ -209,8 +214,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       __syncwarp();
       if (++s == ST) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == kMmaWarp) {
-    // ============================== MMA issuer ==============================
+  } else if (warp >= kMmaWarp) {
+    // ============================== MMA issuer(s) ==============================
     // The whole warp stays converged (every lane polls the mbarriers); only the tcgen05.mma / tcgen05.commit
     // instructions sit under elect.sync.  With `if (lane == 0)` around the loop the compiler cannot prove the
     // operands warp-uniform and wraps every UTCHMMA in an R2UR + ELECT + BRA.U.ANY loop (~14 SASS instructions and
@@ -252,20 +257,65 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       if (elect_one()) umma_commit(bar);
       __syncwarp();
     };
+    // kSumInMma: V(stage s)[key r][column D] = 1.0 (bf16), in the 128B-swizzled layout TMA wrote (16-byte piece
+    // (D*2/16) ^ (r & 7) of row r); generic-proxy stores, made visible to the tensor core by fence.proxy.async
+    auto set_ones_column = [&](int s) {
+      if (C::kSumInMma) {
+        constexpr int kPiece = (D % 64) * 2 / 16, kInPiece = (D % 64) * 2 % 16;
+        unsigned char* vs = sV + s * C::kKVBytes + (D / 64) * BN * 128;
+        for (int r = (tid & 31); r < BN; r += 32)
+          *reinterpret_cast<unsigned short*>(vs + r * 128 + ((kPiece ^ (r & 7)) << 4) + kInPiece) = 0x3F80;
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+    };
+    // s = stage of tile j, s1 = stage of tile j+1; ph / ph1 their ring phases
+    int s = 0, s1 = (ST > 1) ? 1 : 0;
+    uint32_t ph = 0, ph1 = (ST > 1) ? 0u : 1u;
+    if ((issue_order & 3) == 2) {
+      // One MMA warp per query tile: each issues QK(t, .) / PV(t, .) for its own tile only, so no tile's MMAs queue
+      // behind a barrier of another softmax warpgroup (head-of-line blocking of the single in-order issuer).  The
+      // tensor pipe serialises the instructions of the warps; a K / V stage is released once every tile's warp has
+      // committed behind its last MMA that reads it (k_empty / v_empty count = number of active tiles).
+      const int t = warp - kMmaWarp;
+      if (t < nt) {
+        mbar_wait(&bars->q_full, 0);
+        mbar_wait(&bars->k_full[0], 0);
+        tc_fence_after();
+        issue_qk(t, 0);
+        commit(&bars->k_empty[0]);
+        for (int j = 0; j < n_tiles; ++j) {
+          const bool more = (j + 1 < n_tiles);
+          if (more) mbar_wait(&bars->k_full[s1], ph1);
+          if (!C::kAliasP && more) {
+            mbar_wait(&bars->s_free[t], j & 1);  // S(t, j) is in the softmax warpgroup's registers
+            tc_fence_after();
+            issue_qk(t, s1);
+          }
+          mbar_wait(&bars->v_full[s], ph);
+          set_ones_column(s);  // (idempotent: every tile's warp writes the same ones before its own PV)
+          mbar_wait(&bars->p_full[t], j & 1);
+          issue_pv(t, s, j == 0);
+          if (C::kAliasP && more) issue_qk(t, s1);  // P(t, j) lived in S(t): QK(t, j+1) may only follow PV(t, j)
+          if (more) commit(&bars->k_empty[s1]);
+          commit(&bars->v_empty[s]);
+          s = s1; ph = ph1;
+          if (++s1 == ST) { s1 = 0; ph1 ^= 1u; }
+        }
+      }
+    } else if (warp == kMmaWarp) {
     mbar_wait(&bars->q_full, 0);
     mbar_wait(&bars->k_full[0], 0);
     tc_fence_after();
     for (int t = 0; t < nt; ++t) issue_qk(t, 0);
     commit(&bars->k_empty[0]);
-    // s = stage of tile j, s1 = stage of tile j+1; ph / ph1 their ring phases
-    int s = 0, s1 = (ST > 1) ? 1 : 0;
-    uint32_t ph = 0, ph1 = (ST > 1) ? 0u : 1u;
     if (C::kAliasP) {
       // P(t, j) lives in S(t): fixed order PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)
       for (int j = 0; j < n_tiles; ++j) {
         const bool more = (j + 1 < n_tiles);
         if (more) mbar_wait(&bars->k_full[s1], ph1);
         mbar_wait(&bars->v_full[s], ph);
+        set_ones_column(s);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
           if (t < nt) {
@@ -287,7 +337,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       for (int j = 0; j < n_tiles; ++j) {
         const bool more = (j + 1 < n_tiles);
         if (more) mbar_wait(&bars->k_full[s1], ph1);
-        if (issue_order == 1) {
+        if ((issue_order & 3) == 1) {
           if (more) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -300,6 +350,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             commit(&bars->k_empty[s1]);
           }
           mbar_wait(&bars->v_full[s], ph);
+          set_ones_column(s);
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
             if (t < nt) {
@@ -318,7 +369,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                 issue_qk(t, s1);
                 V2_TRACE(6, j + 1, t);
               }
-              if (t == 0) mbar_wait(&bars->v_full[s], ph);
+              if (t == 0) {
+                mbar_wait(&bars->v_full[s], ph);
+                set_ones_column(s);
+              }
               mbar_wait(&bars->p_full[t], j & 1);
               V2_TRACE(7, j, t);
               issue_pv(t, s, j == 0);
@@ -332,7 +386,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         if (++s1 == ST) { s1 = 0; ph1 ^= 1u; }
       }
     }
-  } else {
+    }  // single issuer
+  } else if (warp < kTmaWarp) {
     // ============================== softmax warpgroups (thread == query row) ==============================
     const int wg = warp >> 2;
     const int t = wg / KS;      // query tile
@@ -352,6 +407,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     float m_used = -INFINITY;
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+    const bool pingpong = (NT == 2) && (nt == 2) && (issue_order >= 2) && (issue_order & 4);
+    if (pingpong && t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(3), "r"(2 * KS * 128) : "memory");  // tile 0 goes first
     // One key tile.  kMasked is only instantiated for a ragged last tile: with a run-time test the compiler
     // if-converts the masking into an ISETP + FSEL per score on EVERY tile (2 of ~7 instructions per element).
     auto softmax_tile = [&](const int j, auto masked_c) {
@@ -425,6 +482,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
         tmem_wait_st();
       }
+      // Exponential passes of the two query tiles alternate (FlashAttention-3 style named-barrier ping-pong): with the
+      // tiles free-running, all softmax warps of an SM sub-partition drift into the same phase, the MUFU idles while
+      // they all load / reduce and is then fought over.  Tile t enters its pass when tile t^1 has left its own.
+      if (pingpong) asm volatile("bar.sync %0, %1;" ::"r"(3 + t), "r"(2 * KS * 128) : "memory");
       V2_TRACE((warp < 6 ? warp : 99), j, 3);
       const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
       uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = sum2a;
@@ -450,17 +511,23 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             unpack_f32x2(xb, b0, b1);
             b0 = ex2(b0); b1 = ex2(b1);
           }
-          sum2a = fadd2(sum2a, pack_f32x2(a0, a1));
-          sum2b = fadd2(sum2b, pack_f32x2(b0, b1));
+          if (!C::kSumInMma) {
+            sum2a = fadd2(sum2a, pack_f32x2(a0, a1));
+            sum2b = fadd2(sum2b, pack_f32x2(b0, b1));
+          }
           u[i] = pack_bf16(a0, a1);
           u[i + 1] = pack_bf16(b0, b1);
         }
         if (c == 0 && !pv_waited) {
+          V2_TRACE((warp < 6 ? warp : 99), j, 6);
           mbar_wait(&bars->pv_done[t], (j - 1) & 1);
           tc_fence_after();
+          V2_TRACE((warp < 6 ? warp : 99), j, 7);
         }
         tmem_st16(p_taddr + c * 16, u);  // P as packed bf16 pairs
       }
+      if (pingpong && !(t == 1 && j + 1 == n_tiles))  // (tile 1's last pass has nobody left to release)
+        asm volatile("bar.arrive %0, %1;" ::"r"(3 + (t ^ 1)), "r"(2 * KS * 128) : "memory");
       float s0, s1, s2, s3;
       unpack_f32x2(sum2a, s0, s1);
       unpack_f32x2(sum2b, s2, s3);
@@ -477,7 +544,12 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(&bars->pv_done[t], (n_tiles - 1) & 1);
     tc_fence_after();
-    if (KS == 2) {  // row sum = sum of the two halves' partial sums (both were scaled by the same running max)
+    if (C::kSumInMma) {  // the denominator is column D of O
+      float tmp[16];
+      tmem_ld16(o_taddr + (D / 16) * 16, tmp);
+      tmem_wait_ld();
+      l_run = tmp[D % 16];
+    } else if (KS == 2) {  // row sum = sum of the two halves' partial sums (both were scaled by the same running max)
       bars->xmax[0][t][half][row] = l_run;
       asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
       l_run += bars->xmax[0][t][half ^ 1][row];
@@ -527,8 +599,9 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
   auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((N + 128 * NT - 1) / (128 * NT), B * H);
-  int issue_order = 0;
-  if (const char* e = getenv("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only
+  // measured on B200 (tools/bench_attn.py): one MMA warp per query tile (2) wins except where P aliases S (d = 80)
+  int issue_order = C::kAliasP ? 0 : 2;
+  if (const char* e = getenv("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only (+4: exp-pass ping-pong)
   kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
                                             scale * 1.4426950408889634f, issue_order);
   AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");

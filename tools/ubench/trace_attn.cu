@@ -49,6 +49,7 @@ int main(int argc, char** argv) {
       for (int e = 0; e < 6; ++e) printf(" %7lld", at(a, j, e) - t0);
       printf("   | waitS %5lld ld+max %5lld waitPV %5lld exp %5lld st %5lld\n", at(a, j, 1) - at(a, j, 0), at(a, j, 2) - at(a, j, 1),
              at(a, j, 3) - at(a, j, 2), at(a, j, 4) - at(a, j, 3), at(a, j, 5) - at(a, j, 4));
+      if (at(a, j, 6)) printf("            first 32 cols %5lld, wait pv_done %5lld, rest %5lld\n", at(a, j, 6) - at(a, j, 3), at(a, j, 7) - at(a, j, 6), at(a, j, 4) - at(a, j, 7));
     }
     printf("        MMA: QK issued");
     for (int t = 0; t < 3; ++t) if (at(6, j, t)) printf(" t%d@%7lld", t, at(6, j, t) - t0);
