@@ -294,11 +294,11 @@ def run_ours(args):
     ms_all, flops_all, _ = summarize(sink["agenda_attn_self_fwd"], lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
-    roofline = {"kernel": "attn_self_sm100_v2_kernel<40,4,2,128,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",
+    roofline = {"kernel": "attn_self_sm100_v2_kernel<40,3,2,128,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture
-                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (125.9 MB + 25.2 MB)
-                "traffic": 151.0e6 if n_img == 8 else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (125.9 MB + 28.5 MB)
+                "traffic": 154.4e6 if n_img == 8 else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "avg_launch_ms": ms_k / max(n_k, 1), "launches_timed": n_k,
                 "share_of_step": (ms_k / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
                 "how": "CUDA events around each launch in an eager replay of 5 denoising steps; useful FLOPs "
@@ -328,7 +328,7 @@ def run_ours(args):
                                            "ms_per_denoise_step": ms_all / 5.0},
              "ccl_bbox_512": {"bound": "hbm", "achieved": ccl_gbs, "peak": hbm_gbs, "unit": "GB/s",
                               "frac": ccl_gbs / hbm_gbs, "maps": n_maps, "ms": ccl_ms,
-                              "traffic": 2.95e6,
+                              "traffic": 2.79e6,
                               "note": "BASELINE configs[4] generator (Gaussian blobs + noise floor), 64 distinct maps "
                                       "tiled, labels + boxes written; algorithmic bytes = H*W*(4 read + 4 written) per map; "
                                       "traffic = ncu dram bytes per map (the two-pass one-CTA kernel re-reads the map)"}}
