@@ -30,10 +30,14 @@ _SIGNATURES = {
                                  c_void_p],
     "agenda_attn_cross_fwd_heat": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                    c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int, c_void_p],
+    "agenda_attn_cross_fwd_heat_heads": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                         c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int,
+                                         c_void_p],
     "agenda_attn_cross_fwd_heat_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int,
                                        c_void_p],
     "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "agenda_heat_upsample_accum_heads": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_heat_finalize": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "agenda_heat_normalize_u8": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "agenda_resize_bicubic_u8": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

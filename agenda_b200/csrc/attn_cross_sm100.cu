@@ -230,8 +230,19 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       if (want_heat) {
         if (kFew) {
 #pragma unroll
-          for (int t = 0; t < kXFewTokens; ++t)
-            if (t < tl.n) acc[t] += ex2(fmaf(sel[t], scale_log2, -m)) * inv_l;  // same ops as sv[idx[t]] above
+          for (int t = 0; t < kXFewTokens; ++t) {
+            if (t < tl.n) {
+              const float pt = ex2(fmaf(sel[t], scale_log2, -m)) * inv_l;  // same ops as sv[idx[t]] above
+              if (tl.per_head) {  // DAAM-style: one plane per (batch, head, token), no head mean
+                if (n < N) {
+                  float* ptr = maps + ((static_cast<long long>(b - b_first) * H + h) * tl.n + t) * N + n;
+                  *ptr = accumulate ? (*ptr + pt) : pt;
+                }
+              } else {
+                acc[t] += pt;
+              }
+            }
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < kXMPad; ++i) acc[i] += sv[i];
@@ -254,7 +265,7 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     drain_o(H - 1);
 
     // ---- heat epilogue: mean over heads, selected token columns, coalesced per token plane ----
-    if (want_heat) {
+    if (want_heat && !(kFew && tl.per_head)) {
       const float inv_h = 1.0f / static_cast<float>(H);
       float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n;
       if (kFew) {
@@ -325,6 +336,9 @@ int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int
                      float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M > sm100::kXMPad) return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross (tensor-core path): M=%d > %d", M, sm100::kXMPad);
+  if (maps && tl.per_head && tl.n > sm100::kXFewTokens)
+    return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross (tensor-core path): per-head maps for %d > %d tokens", tl.n,
+                sm100::kXFewTokens);
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_cross_fwd_heat: q/k/v/out must be 16-byte aligned");

@@ -153,13 +153,20 @@ __global__ void __launch_bounds__(kWarps * 32) attn_f32_kernel(const T* __restri
 #pragma unroll
             for (int j = 0; j < kTK / 32; ++j)
               if ((tok >> 5) == j) pv = p[r][j];
-            sHeat[row * nT + t] += pv * inv_l;  // this warp owns the row: no race
+            if (tl.per_head) {  // DAAM-style: one plane per (batch, head, token), no head mean
+              if (n < N) {
+                float* ptr = maps + ((static_cast<long long>(b - b_first) * H + h) * nT + t) * N + n;
+                *ptr = accumulate ? (*ptr + pv * inv_l) : pv * inv_l;
+              }
+            } else {
+              sHeat[row * nT + t] += pv * inv_l;  // this warp owns the row: no race
+            }
           }
         }
       }
     }
   }
-  if (want_heat) {
+  if (want_heat && !tl.per_head) {
     __syncthreads();
     const float inv_h = 1.0f / static_cast<float>(H);  // .mean(dim=1) over heads, hook.py:55
     float* dst = maps + static_cast<long long>(b - b_first) * nT * N;
@@ -217,6 +224,7 @@ int build_token_list(const char* who, const int32_t* token_idx, int T, int M, To
     }
   }
   tl->n = T;
+  tl->per_head = 0;
   return AGENDA_OK;
 }
 
@@ -241,6 +249,7 @@ extern "C" int agenda_attn_self_fwd_f32(const void* q, const void* k, const void
   if (d > kMaxD) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_f32: d=%d > %d", d, kMaxD);
   TokenList tl;
   tl.n = 0;
+  tl.per_head = 0;
   return dtype == AGENDA_F32
              ? launch_attn_f32<float, false>(q, k, v, out, B, H, N, N, d, scale, tl, 0, nullptr, 0, stream)
              : launch_attn_f32<__nv_bfloat16, false>(q, k, v, out, B, H, N, N, d, scale, tl, 0, nullptr, 0, stream);

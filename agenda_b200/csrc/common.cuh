@@ -41,6 +41,7 @@ constexpr int kMaxTokens = 128;
 // heat-map token selection, passed to kernels by value
 struct TokenList {
   int n;
+  int per_head;  // 0: maps[b', t, n] = mean over heads (hook.py:55); 1: maps[b', head, t, n], no mean (DAAM keeps heads)
   int idx[kMaxTokens];
 };
 

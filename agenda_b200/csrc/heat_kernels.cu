@@ -28,9 +28,11 @@ __device__ __forceinline__ void cubic_src(int dst, float scale, int n_in, int id
 }
 
 // One thread -> 4 consecutive output pixels of one row (float4 read-modify-write of acc, coalesced).
+// G > 1 (DAAM-style aggregation): accumulator plane p = b'*T + t receives the G source planes (b'*G + g)*T + t, each
+// upsampled and clamped on its own, summed in the fixed order g = 0..G-1 (deterministic).
 __global__ void __launch_bounds__(256) heat_upsample_accum_kernel(const float* __restrict__ maps,
                                                                   float* __restrict__ acc, int n_planes,
-                                                                  int h, int w, int L) {
+                                                                  int h, int w, int L, int T, int G) {
   const int quads_per_row = L >> 2;
   const long long total = static_cast<long long>(n_planes) * L * quads_per_row;
   const float sy = static_cast<float>(h) / static_cast<float>(L);
@@ -41,9 +43,10 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_kernel(const float* _
     const long long r = i / quads_per_row;
     const int y = static_cast<int>(r % L);
     const long long plane = r / L;
-    const float* __restrict__ src = maps + plane * h * w;
     float4* dst = reinterpret_cast<float4*>(acc + (plane * L + y) * L) + qx;
     float4 a = *dst;
+    for (int g = 0; g < G; ++g) {
+    const float* __restrict__ src = maps + ((plane / T * G + g) * T + plane % T) * h * w;
     float v[4];
     if (h == L && w == L) {  // scale 1: torch returns the input bit-exactly
       const float4 s = *reinterpret_cast<const float4*>(src + static_cast<long long>(y) * w + qx * 4);
@@ -71,6 +74,7 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_kernel(const float* _
     a.y += fmaxf(v[1], 0.f);
     a.z += fmaxf(v[2], 0.f);
     a.w += fmaxf(v[3], 0.f);
+    }
     *dst = a;
   }
 }
@@ -95,8 +99,23 @@ __global__ void __launch_bounds__(256) heat_finalize_kernel(const float* __restr
 
 using namespace agenda;
 
+static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes, int h, int w, int L, int T, int G,
+                                    void* stream);
+
 extern "C" int agenda_heat_upsample_accum(const float* maps, float* acc, int n_planes, int h, int w, int L,
                                           void* stream) {
+  return heat_upsample_accum_impl(maps, acc, n_planes, h, w, L, 1, 1, stream);
+}
+
+extern "C" int agenda_heat_upsample_accum_heads(const float* maps, float* acc, int n_acc_planes, int T, int G, int h,
+                                                int w, int L, void* stream) {
+  if (T <= 0 || G <= 0 || (n_acc_planes % T) != 0)
+    return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum_heads: n_acc_planes=%d T=%d G=%d", n_acc_planes, T, G);
+  return heat_upsample_accum_impl(maps, acc, n_acc_planes, h, w, L, T, G, stream);
+}
+
+static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes, int h, int w, int L, int T, int G,
+                                    void* stream) {
   if (!maps || !acc) return fail(AGENDA_ERR_NULL_POINTER, "heat_upsample_accum: null pointer");
   if (n_planes < 0 || h <= 0 || w <= 0 || L <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: bad shape");
   if (L % 4 != 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: latent_hw must be a multiple of 4 (got %d)", L);
@@ -109,7 +128,7 @@ extern "C" int agenda_heat_upsample_accum(const float* maps, float* acc, int n_p
   const long long cap = static_cast<long long>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   heat_upsample_accum_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      maps, acc, n_planes, h, w, L);
+      maps, acc, n_planes, h, w, L, T, G);
   AGENDA_LAUNCH_CHECK("heat_upsample_accum_kernel");
   return AGENDA_OK;
 }

@@ -64,11 +64,13 @@ def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 
 def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, maps: Optional[torch.Tensor],
                     token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
-                    scale: Optional[float] = None, force_f32_kernel: bool = False) -> torch.Tensor:
+                    scale: Optional[float] = None, force_f32_kernel: bool = False,
+                    per_head: bool = False) -> torch.Tensor:
     """Cross-attention + heat epilogue (hook.py:108-114 and _unravel_attn hook.py:28-56).
 
     maps: fp32 [B-b_first, T, N] written (accumulate=False) or added to (accumulate=True), T = len(token_idx) or
-    M when token_idx is None; pass maps=None to skip the epilogue.  Returns out [B,N,H*d]."""
+    M when token_idx is None; pass maps=None to skip the epilogue.  per_head=True keeps the heads apart (DAAM):
+    maps is [B-b_first, H, T, N] and no head mean is taken.  Returns out [B,N,H*d]."""
     q = _dev(q, "q")
     k, v = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype)
     B, N, C = q.shape
@@ -79,8 +81,9 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     if maps is not None:
         maps = _dev(maps, "maps", torch.float32)
         T = M if token_idx is None else len(token_idx)
-        if tuple(maps.shape[:2]) != (B - b_first, T) or maps[0, 0].numel() != N:
-            raise ValueError(f"maps must be [{B - b_first},{T},{N}] (any trailing shape of {N} elements), "
+        lead = (B - b_first, heads, T) if per_head else (B - b_first, T)
+        if tuple(maps.shape[:len(lead)]) != lead or maps.numel() != N * int(torch.tensor(lead).prod()):
+            raise ValueError(f"maps must be {list(lead)} + [{N}] (any trailing shape of {N} elements), "
                              f"got {tuple(maps.shape)}")
         if not maps.is_contiguous():
             raise ValueError("maps must be contiguous (it is written in place)")
@@ -88,7 +91,13 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
         mp = maps.data_ptr()
     else:
         T, idx, mp = 0, None, None
-    _lib.call("agenda_attn_cross_fwd_heat_f32" if force_f32_kernel else "agenda_attn_cross_fwd_heat", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
+    if per_head:
+        if maps is None or force_f32_kernel:
+            raise ValueError("per_head=True needs maps and has no forced-fp32 variant")
+        entry = "agenda_attn_cross_fwd_heat_heads"
+    else:
+        entry = "agenda_attn_cross_fwd_heat_f32" if force_f32_kernel else "agenda_attn_cross_fwd_heat"
+    _lib.call(entry, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
               B, heads, N, M, d, scale, idx, T, int(b_first), mp, int(bool(accumulate)), _stream())
     return out
 
@@ -106,6 +115,19 @@ def heat_upsample_accum(maps: torch.Tensor, acc: torch.Tensor) -> None:
     if acc.shape[-2] != L or acc.numel() != n * L * L:
         raise ValueError(f"acc {tuple(acc.shape)} does not match maps {tuple(maps.shape)}")
     _lib.call("agenda_heat_upsample_accum", maps.data_ptr(), acc.data_ptr(), n, h, w, L, _stream())
+
+
+def heat_upsample_accum_heads(maps: torch.Tensor, acc: torch.Tensor) -> None:
+    """DAAM-style aggregation: maps fp32 [B', G, T, h, w] (G = heads) -> acc fp32 [B', T, L, L] +=
+    sum_g clamp(bicubic(maps[:, g]), min=0), every (batch, head, token) plane upsampled and clamped on its own."""
+    maps, acc = _dev(maps, "maps", torch.float32), _dev(acc, "acc", torch.float32)
+    if maps.dim() != 5 or acc.dim() != 4 or not acc.is_contiguous():
+        raise ValueError("maps must be [B',G,T,h,w] and acc a contiguous [B',T,L,L]")
+    Bp, G, T, h, w = maps.shape
+    L = acc.shape[-1]
+    if tuple(acc.shape) != (Bp, T, L, L):
+        raise ValueError(f"acc {tuple(acc.shape)} does not match maps {tuple(maps.shape)}")
+    _lib.call("agenda_heat_upsample_accum_heads", maps.data_ptr(), acc.data_ptr(), Bp * T, T, G, h, w, L, _stream())
 
 
 def heat_finalize(acc: torch.Tensor, count: int) -> torch.Tensor:

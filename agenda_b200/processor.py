@@ -21,6 +21,11 @@ Differences from the reference, by design:
     steps); aggregation never needs it.
   * forward only: `is_train=True` keeps both batch halves (hook.py:48-49) but no autograd graph is built
     (training is out of scope, SURVEY.md §8 f N3).
+  * `aggregate="daam"` switches the aggregation to the `daam` package's (what data_generation.py:57-77 actually
+    calls; un-vendored, parity unpinned — SURVEY.md §8 a5): per hooked layer one [B',H,T,h,w] buffer sums the per-head
+    probabilities over the denoising steps at native resolution (the attention epilogue adds into it), layers whose
+    map is latent_hw/8 wide are skipped, and `compute_global_heat_map()` upsamples + clamps every (layer, head) plane
+    on its own before averaging over all of them.
 """
 from __future__ import annotations
 
@@ -34,7 +39,11 @@ from . import ops
 
 class UNetCrossAttentionHooker:
     def __init__(self, is_train: bool = True, latent_hw: int = 64, tokens: Optional[Sequence[int]] = None,
-                 precision: str = "bf16", record_maps: bool = False):
+                 precision: str = "bf16", record_maps: bool = False, aggregate: str = "hook"):
+        if aggregate not in ("hook", "daam"):
+            raise ValueError("aggregate must be 'hook' or 'daam'")
+        self.aggregate = aggregate
+        self._layer_sums = {}   # aggregate="daam": id(attn) -> [B',H,T,h,w] fp32 sum over denoising steps
         self.cross_attn_maps: List[torch.Tensor] = []
         self.is_train = is_train
         self.latent_hw = latent_hw
@@ -49,6 +58,8 @@ class UNetCrossAttentionHooker:
         self.cross_attn_maps.clear()
         if self._acc is not None:
             self._acc.zero_()
+        for buf in self._layer_sums.values():
+            buf.zero_()
         self._count = 0
 
     @property
@@ -58,6 +69,17 @@ class UNetCrossAttentionHooker:
     # ---- hook.py:59-81 -------------------------------------------------------------------------------------
     def compute_global_heat_map(self) -> torch.Tensor:
         """[B', T, latent_hw, latent_hw] fp32 (T = 77 rows, or len(tokens))."""
+        if self.aggregate == "daam":
+            if self._count == 0 or not self._layer_sums:
+                raise RuntimeError('No heat maps found.')
+            first = next(iter(self._layer_sums.values()))
+            L = self.latent_hw
+            acc = torch.zeros((first.shape[0], first.shape[2], L, L), dtype=torch.float32, device=first.device)
+            pairs = 0
+            for buf in self._layer_sums.values():   # insertion order == network order: deterministic sum
+                ops.heat_upsample_accum_heads(buf, acc)
+                pairs += buf.shape[1]
+            return ops.heat_finalize(acc, pairs)    # mean over every (layer, head) map
         if self._count == 0 or self._acc is None:
             raise RuntimeError('No heat maps found.')
         return ops.heat_finalize(self._acc, self._count)
@@ -94,6 +116,20 @@ class UNetCrossAttentionHooker:
             n_tok = M if self.tokens is None else len(self.tokens)
             b_first = 0 if self.is_train else batch_size // 2  # hook.py:48-49: drop the unconditional half
             h = w = int(math.sqrt(sequence_length))
+            if self.aggregate == "daam":
+                if self.latent_hw // h == 8:  # daam drops the factor-8 maps
+                    hidden_states = ops.attn_cross_heat(query, key, value, heads, None, scale=scale)
+                else:
+                    buf = self._layer_sums.get(id(attn))
+                    shape = (batch_size - b_first, heads, n_tok, h, w)
+                    if buf is None or tuple(buf.shape) != shape or buf.device != query.device:
+                        buf = torch.zeros(shape, dtype=torch.float32, device=query.device)
+                        self._layer_sums[id(attn)] = buf
+                    hidden_states = ops.attn_cross_heat(query, key, value, heads, buf, self.tokens, b_first,
+                                                        accumulate=True, scale=scale, per_head=True)
+                    self._count += 1
+                hidden_states = attn.to_out[0](hidden_states)
+                return attn.to_out[1](hidden_states)
             acc = self._accumulate(batch_size - b_first, n_tok, query.device)
             if h == self.latent_hw and not self.record_maps:
                 # bicubic at scale 1 is the identity and probabilities are >= 0: accumulate from the epilogue

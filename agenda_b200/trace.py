@@ -13,8 +13,9 @@ which are restated from daam's published algorithm:
   * batch-1 generation, the unconditional CFG half is dropped;
   * the result is truncated to len(tokenize(prompt)) + 2 rows when a tokenizer is available.
 mode="hook" (default) aggregates with hook.py's semantics (mean over heads at native resolution, then bicubic+clamp
-per map, mean over maps — SURVEY.md §8 a4), which IS pinned by the golden vectors; mode="daam" keeps DAAM's layer
-selection (same aggregation kernel; DAAM's per-head upsampling order is not reproduced — see DESIGN.md).
+per map, mean over maps — SURVEY.md §8 a4), which IS pinned by the golden vectors; mode="daam" reproduces DAAM's own
+aggregation as restated in oracle/hook_oracle.py:daam_global_heat_map: DAAM's layer selection, per-(layer, head) sums
+over the denoising steps at native resolution, bicubic+clamp per (layer, head), mean over all of them.
 """
 from __future__ import annotations
 
@@ -86,7 +87,7 @@ class trace:
         self.prompt = prompt
         self.tokens = None if tokens is None else list(tokens)
         self.hooker = UNetCrossAttentionHooker(is_train=False, latent_hw=latent_hw, tokens=self.tokens,
-                                               precision=precision)
+                                               precision=precision, aggregate="daam" if mode == "daam" else "hook")
         self._saved = []
 
     def __enter__(self):

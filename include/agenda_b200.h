@@ -81,6 +81,16 @@ int agenda_attn_cross_fwd_heat(const void* q, const void* k, const void* v, void
                                const int32_t* token_idx, int T, int b_first,
                                float* maps, int accumulate, void* stream);
 
+/* DAAM-style capture (the `daam` package data_generation.py:57-77 is written against keeps one map per head and
+ * upsamples before it averages — SURVEY.md §8 a5): same attention, but
+ *     maps[b-b_first, head, t, n] (=|+=) softmax(scale*q k^T)[b, head, n, token_idx[t]]       (no head mean)
+ * maps is fp32 [B-b_first, H, T, N] and must not be NULL.  accumulate!=0 adds (DAAM sums over denoising steps at
+ * native resolution).  The tensor-core path covers T <= 8; more tokens take the fp32 CUDA-core kernel. */
+int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v, void* out, int dtype,
+                                     int B, int H, int N, int M, int d, float scale,
+                                     const int32_t* token_idx, int T, int b_first,
+                                     float* maps, int accumulate, void* stream);
+
 /* Test hook: same contract, forcing the exact fp32 CUDA-core kernel (bf16 inputs otherwise take the tcgen05
  * tensor-core kernel; fp32 inputs always take the fp32 kernel). */
 int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, void* out, int dtype,
@@ -94,6 +104,10 @@ int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, 
  * src=(dst+0.5)*h/L-0.5, border-replicated taps. */
 int agenda_heat_upsample_accum(const float* maps, float* acc, int n_planes, int h, int w, int L,
                                void* stream);
+/* DAAM-style aggregation: acc[b'*T + t] += sum over g < G of max(0, bicubic(maps[(b'*G + g)*T + t])), g ascending
+ * (deterministic).  maps fp32 [n_acc_planes/T, G, T, h, w] (G = heads), acc fp32 [n_acc_planes, L, L]. */
+int agenda_heat_upsample_accum_heads(const float* maps, float* acc, int n_acc_planes, int T, int G, int h, int w,
+                                     int L, void* stream);
 /* out[i] = acc[i] / count  (torch.mean over the (layer x step) list, hook.py:79).  count>=1. */
 int agenda_heat_finalize(const float* acc, float* out, int64_t n_elems, int count, void* stream);
 

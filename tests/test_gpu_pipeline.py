@@ -107,6 +107,48 @@ def test_trace_shim_end_to_end(cuda_ok):
     assert all(m.processor is default for m in list(stack.attn1) + list(stack.attn2))
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_trace_daam_mode_matches_daam_oracle(cuda_ok, precision):
+    """mode="daam": per-(layer, head) sums over the steps at native resolution, bicubic + clamp per (layer, head),
+    mean over all of them, mid block and factor-8 layers left out (oracle/hook_oracle.py:daam_global_heat_map)."""
+    from agenda_b200.sd_attention import AttentionStack, BlockSpec
+    from agenda_b200.trace import trace
+    blocks = [BlockSpec("down0", 16, 320, 8), BlockSpec("down1", 8, 640, 8), BlockSpec("down2", 2, 1280, 8),
+              BlockSpec("mid", 4, 1280, 8), BlockSpec("up3", 16, 320, 8)]
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    stack = AttentionStack(blocks, 768, seed=4).cuda().to(dt)
+
+    class Pipe:
+        unet = stack
+        tokenizer = None
+
+    toks = [3, 6, 9]
+    steps = 2
+    hs, ctx = stack.make_inputs(2, "cuda", dt, seed=5)
+    from agenda_b200 import UNetCrossAttentionHooker
+    stack.set_attn_processor(UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=toks, precision=precision))
+    with trace(Pipe(), tokens=toks, latent_hw=16, mode="daam", precision=precision) as trc:
+        with torch.no_grad():
+            for _ in range(steps):
+                stack(hs, ctx)
+        heat = trc.compute_global_heat_map().heat_maps.cpu().numpy()      # [T, 16, 16]
+    sums = []
+    for b, a2 in zip(blocks, stack.attn2):
+        if b.name == "mid" or 16 // b.hw == 8:
+            continue
+        x = hs[(b.hw, b.channels)].float().cpu()
+        q = O.head_to_batch_dim(x @ a2.to_q.weight.detach().float().cpu().T, b.heads)
+        k = O.head_to_batch_dim(ctx.float().cpu() @ a2.to_k.weight.detach().float().cpu().T, b.heads)
+        p = O.attention_probs(q, k, b.dim_head ** -0.5)                   # [B*H, N, 77]
+        cond = p[b.heads:]                                                # conditional half (batch index 1)
+        m = cond[:, :, toks].permute(0, 2, 1).reshape(b.heads, len(toks), b.hw, b.hw).numpy()
+        sums.append(m * np.float32(steps))
+    ref = O.daam_global_heat_map(sums, 16)
+    assert heat.shape == ref.shape == (3, 16, 16)
+    tol = 2e-3 * ref.max() + 1e-5 if precision == "bf16" else 1e-4 * ref.max() + 1e-6
+    assert np.abs(heat - ref).max() < tol
+
+
 def test_postprocess_host_api(cuda_ok):
     from agenda_b200 import postprocess
     rng = np.random.default_rng(0)
