@@ -151,6 +151,28 @@ def test_ccl_ragged_shapes(ops, H, W):
     _check_ccl(ops, heat, 0.5, max_boxes=128)
 
 
+def test_ccl_config5_full_size_sweep(ops):
+    """BASELINE configs[4] at full size: 10 000 synthetic 512x512 maps in ONE call (10 GB in, 10 GB of labels out).
+    50 distinct maps are checked against the oracle pixel by pixel; the other 9 950 are replicas, so every replica must
+    reproduce its original's labels / counts / boxes bit for bit (independence of the maps within a launch)."""
+    base = O.synthetic_heatmaps(50, 512, seed=11)
+    d_base = cuda(base)
+    heat = d_base.repeat(200, 1, 1)                                  # [10000, 512, 512], map i = base[i % 50]
+    labels, counts, boxes = ops.ccl_bbox(heat, 0.5, max_boxes=64)
+    torch.cuda.synchronize()
+    l0, c0, b0 = labels[:50].cpu().numpy(), counts[:50].cpu().numpy(), boxes[:50].cpu().numpy()
+    for i in range(50):
+        rl, rb = O.ccl_bbox(base[i], 0.5)
+        assert c0[i] == rb.shape[0] and np.array_equal(l0[i], rl)
+        assert np.array_equal(b0[i, :min(len(rb), 64)], rb[:64])
+    assert torch.equal(labels.view(200, 50, 512, 512), labels[:50].unsqueeze(0).expand(200, -1, -1, -1))
+    assert torch.equal(counts.view(200, 50), counts[:50].unsqueeze(0).expand(200, -1))
+    assert torch.equal(boxes.view(200, 50, 64, 5), boxes[:50].unsqueeze(0).expand(200, -1, -1, -1))
+    del labels
+    _, counts2, boxes2 = ops.ccl_bbox(heat, 0.5, max_boxes=64, want_labels=False)
+    assert torch.equal(counts2, counts) and torch.equal(boxes2, boxes)
+
+
 def test_ccl_threshold_values_and_no_labels(ops):
     heat = O.synthetic_heatmaps(3, 128, seed=9)
     for thr in (0.0, 0.25, 0.9, 1.0):
