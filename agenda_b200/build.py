@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagenda_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "-cudart", "static", "--expt-relaxed-constexpr"]
+              "-shared", "-cudart", "static", "--expt-relaxed-constexpr", "--threads", "0"]
 
 
 def sources():

@@ -629,6 +629,12 @@ int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, i
       default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 3-tile variant needs head dim 40 or 64, got %d", d);
     }
   }
+  if (tiles == 5) {  // two query tiles, 64-key tiles: P gets its own TMEM columns at d = 80 (no S/P aliasing)
+    switch (d) {
+      case 80: AGENDA_V2_EMU(80, 2, 64, 1)
+      default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 64-key variant is for head dim 80, got %d", d);
+    }
+  }
   if (tiles == 4) {  // two query tiles, two warpgroups (half rows) per tile
     switch (d) {
       case 40: AGENDA_V2_EMU(40, 2, 128, 2)

@@ -64,6 +64,20 @@ def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
+@pytest.mark.parametrize("variant", [40, 44])
+@pytest.mark.parametrize("B,N,H,d", [(2, 1024, 8, 80), (1, 200, 2, 80), (1, 64, 1, 80)])
+def test_sm100_self_attention_d80_64key_tiles(lib, B, N, H, d, variant):
+    """d = 80 with 64-key tiles: P has its own TMEM columns (the default d = 80 path aliases P onto S)."""
+    g = torch.Generator().manual_seed(N + variant)
+    q = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    k = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    v = (torch.randn(B, N, H * d, generator=g) * 0.25).bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, variant)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
