@@ -407,7 +407,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     float m_used = -INFINITY;
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
-    const bool pingpong = (NT == 2) && (nt == 2) && (issue_order >= 2) && (issue_order & 4);
+    const bool pingpong = (NT == 2) && (nt == 2) && ((issue_order & 3) >= 2) && (issue_order & 4);
     if (pingpong && t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(3), "r"(2 * KS * 128) : "memory");  // tile 0 goes first
     // One key tile.  kMasked is only instantiated for a ragged last tile: with a run-time test the compiler
     // if-converts the masking into an ISETP + FSEL per score on EVERY tile (2 of ~7 instructions per element).
