@@ -24,6 +24,8 @@ class AgendaError(RuntimeError):
 _SIGNATURES = {
     "agenda_attn_self_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
                              c_void_p],
+    "agenda_attn_self_fwd_strided": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     ctypes.c_longlong, c_float, c_void_p],
     "agenda_attn_self_fwd_variant": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                      c_void_p],
     "agenda_attn_self_fwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,

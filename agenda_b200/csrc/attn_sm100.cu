@@ -296,10 +296,15 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [B, N, H*d] bf16 viewed as (d, H, N, B); box (64, 1, rows, 1), 128-byte swizzle, zero fill out of bounds.
+// Row stride (elements) of the NEXT tensor maps built on this thread; 0 = packed rows of H*d.  Set only for the duration
+// of agenda_attn_self_fwd_strided (q/k/v as column slices of one fused-projection output) — thread-local call scratch,
+// not library state.
+static thread_local long long g_row_stride = 0;
+
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t C = static_cast<cuuint64_t>(H) * d;
+  const cuuint64_t C = g_row_stride ? static_cast<cuuint64_t>(g_row_stride) : static_cast<cuuint64_t>(H) * d;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N),
                         static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(d) * 2, C * 2, static_cast<cuuint64_t>(N) * C * 2};
@@ -381,6 +386,19 @@ extern "C" int agenda_attn_self_fwd(const void* q, const void* k, const void* v,
   if (rc != AGENDA_OK) return rc;
   if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: tensor-core path takes bf16 (dtype=1)");
   return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
+}
+
+extern "C" int agenda_attn_self_fwd_strided(const void* q, const void* k, const void* v, void* out, int dtype, int B,
+                                            int H, int N, int d, long long ld, float scale, void* stream) {
+  int rc = attn_common_checks("attn_self_fwd_strided", q, k, v, out, dtype, B, H, N, N, d);
+  if (rc != AGENDA_OK) return rc;
+  if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_strided: bf16 only (dtype=1)");
+  if (ld < static_cast<long long>(H) * d || (ld & 7))
+    return fail(AGENDA_ERR_BAD_SHAPE, "attn_self_fwd_strided: ld=%lld must be >= H*d=%d and a multiple of 8", ld, H * d);
+  g_row_stride = ld;
+  rc = attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
+  g_row_stride = 0;
+  return rc;
 }
 
 // Test hook: same contract, explicit kernel variant (see attn_self_sm100).

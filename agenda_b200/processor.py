@@ -30,6 +30,7 @@ Differences from the reference, by design:
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -44,6 +45,11 @@ class UNetCrossAttentionHooker:
             raise ValueError("aggregate must be 'hook' or 'daam'")
         self.aggregate = aggregate
         self._layer_sums = {}   # aggregate="daam": id(attn) -> [B',H,T,h,w] fp32 sum over denoising steps
+        # self-attention, bf16: to_q/to_k/to_v (hook.py:93,101-102) act on the same hidden_states, so they run as ONE
+        # GEMM with the concatenated weights (hidden_states read once instead of three times) and the attention kernel
+        # reads q/k/v as column slices of its output.  id(attn) -> (weight versions, fused [3C,C] weight)
+        self.fuse_qkv = os.environ.get("AGENDA_FUSE_QKV", "1") != "0"
+        self._qkv_weights = {}
         self.cross_attn_maps: List[torch.Tensor] = []
         self.is_train = is_train
         self.latent_hw = latent_hw
@@ -84,6 +90,24 @@ class UNetCrossAttentionHooker:
             raise RuntimeError('No heat maps found.')
         return ops.heat_finalize(self._acc, self._count)
 
+    def _fused_qkv_weight(self, attn):
+        """[3C, C] concatenation of to_q/to_k/to_v weights (bias-free Linear layers of equal shape), cached per module
+        and rebuilt when any of the three weights is modified in place or replaced."""
+        mods = (attn.to_q, attn.to_k, attn.to_v)
+        ws = [getattr(m, "weight", None) for m in mods]
+        if any(w is None or w.dtype != torch.bfloat16 or not w.is_cuda for w in ws):
+            return None
+        if any(getattr(m, "bias", None) is not None for m in mods) or not (ws[0].shape == ws[1].shape == ws[2].shape):
+            return None
+        if type(attn.to_q) is not torch.nn.Linear or ws[0].shape[0] % 8:
+            return None
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        hit = self._qkv_weights.get(id(attn))
+        if hit is None or hit[0] != key:
+            hit = (key, torch.cat([w.detach() for w in ws], 0).contiguous())
+            self._qkv_weights[id(attn)] = hit
+        return hit[1]
+
     def _accumulate(self, b_kept: int, n_tok: int, device) -> torch.Tensor:
         L = self.latent_hw
         if self._acc is None or self._acc.shape != (b_kept, n_tok, L, L) or self._acc.device != device:
@@ -98,6 +122,14 @@ class UNetCrossAttentionHooker:
         attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
         if attention_mask is not None:
             raise NotImplementedError("agenda_b200: attention masks are not supported (the SD UNet passes none)")
+        if (encoder_hidden_states is None and self.fuse_qkv and self.precision == "bf16"
+                and hidden_states.dtype == torch.bfloat16 and hidden_states.is_cuda):
+            w = self._fused_qkv_weight(attn)
+            if w is not None:
+                qkv = torch.nn.functional.linear(hidden_states, w)
+                hidden_states = ops.attn_self_fused_qkv(qkv, attn.heads, scale=float(attn.scale))
+                hidden_states = attn.to_out[0](hidden_states)
+                return attn.to_out[1](hidden_states)
         query = attn.to_q(hidden_states)
 
         is_cross_attn = encoder_hidden_states is not None

@@ -272,7 +272,7 @@ def run_ours(args):
     # around every launch of the kernel on the launching stream.
     pipe_eager = pipe
     pipe_eager.use_cuda_graph = False
-    _lib.event_sink = {"agenda_attn_self_fwd": [], "agenda_attn_cross_fwd_heat": []}
+    _lib.event_sink = {"agenda_attn_self_fwd": [], "agenda_attn_self_fwd_strided": [], "agenda_attn_cross_fwd_heat": []}
     pipe_eager.num_steps = 5
     pipe_eager.run_device(hs_dev, ctx_dev)
     torch.cuda.synchronize()
@@ -288,10 +288,11 @@ def run_ours(args):
             tot_ms += s.elapsed_time(e); tot_work += w; n += 1
         return tot_ms, tot_work, n
 
-    # args of agenda_attn_self_fwd: q,k,v,out,dtype,B,H,N,d,scale,stream
-    ms_k, flops, n_k = summarize(sink["agenda_attn_self_fwd"],
+    # args of agenda_attn_self_fwd[_strided]: q,k,v,out,dtype,B,H,N,d,[ld,]scale,stream
+    self_calls = sink["agenda_attn_self_fwd"] + sink["agenda_attn_self_fwd_strided"]
+    ms_k, flops, n_k = summarize(self_calls,
                                  lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8] if a[7] == 4096 else None)
-    ms_all, flops_all, _ = summarize(sink["agenda_attn_self_fwd"], lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
+    ms_all, flops_all, _ = summarize(self_calls, lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
     roofline = {"kernel": "attn_self_sm100_v2_kernel<40,3,2,128,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",

@@ -53,6 +53,13 @@ int agenda_device_ok(void);
 int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out, int dtype,
                          int B, int H, int N, int d, float scale, void* stream);
 
+/* Same, with q/k/v rows `ld` elements apart (batch stride N*ld): q, k, v may be column slices [.., 0:C], [.., C:2C],
+ * [.., 2C:3C] of ONE fused projection output [B,N,3C] (to_q/to_k/to_v of hook.py:93,101-102 act on the same
+ * hidden_states in self-attention, so one GEMM with the concatenated weights reads them once).  out stays packed
+ * [B,N,H*d].  ld >= H*d, ld % 8 == 0, pointers 16-byte aligned. */
+int agenda_attn_self_fwd_strided(const void* q, const void* k, const void* v, void* out, int dtype,
+                                 int B, int H, int N, int d, long long ld, float scale, void* stream);
+
 /* Test hook: agenda_attn_self_fwd (bf16) with an explicit kernel variant: 0 = default (two 128-query tiles per
  * CTA, ping-pong softmax warpgroups, P through TMEM), 1 = one query tile per CTA with P through TMEM (TS-form
  * tcgen05.mma), 2 = one query tile per CTA with P through a 128B-swizzled shared-memory tile (SS-form);
