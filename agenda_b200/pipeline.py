@@ -56,13 +56,15 @@ class HeatmapPipeline:
         """All tensors on the device.  Returns heat [n,T,L,L] fp32, planes u8 [n,3,S,S], stack u8 [n,S,S,3], inv u8
         [n,S,S], counts int32 [n], boxes int32 [n,max_boxes,5] (x,y,w,h,area on the object-token map)."""
         proc = self.proc
-        proc.clear()
+        proc.clear(keep_context_kv=True)  # the captured graph reads the cached prompt K/V buffers
+        proc.refresh_context_kv()         # the prompt embedding may have been overwritten in place since the last run
         key = (tuple((k, v.data_ptr()) for k, v in sorted(hs.items())), ctx.data_ptr())
         if self.use_cuda_graph:
             if self._graph is None or self._graph_key != key:
                 # warm the allocator/cuBLAS handles outside capture, then capture one denoising step's 32 calls
+                proc.clear()             # new input buffers: rebuild the prompt K/V cache outside the capture
                 self.stack(hs, ctx)
-                proc.clear()
+                proc.clear(keep_context_kv=True)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 from . import _lib
@@ -72,7 +74,7 @@ class HeatmapPipeline:
                 self._graph_launches = _lib.launches - l0  # C-ABI kernel nodes captured per denoising step
                 self._graph, self._graph_key = g, key
                 self._maps_per_step = proc.num_maps
-                proc.clear()
+                proc.clear(keep_context_kv=True)
             for _ in range(self.num_steps):
                 self._graph.replay()
             proc._count = self._maps_per_step * self.num_steps

@@ -50,6 +50,12 @@ class UNetCrossAttentionHooker:
         # reads q/k/v as column slices of its output.  id(attn) -> (weight versions, fused [3C,C] weight)
         self.fuse_qkv = os.environ.get("AGENDA_FUSE_QKV", "1") != "0"
         self._qkv_weights = {}
+        # cross-attention: to_k / to_v of the prompt embedding (hook.py:101-102) do not depend on the latent, yet the
+        # reference recomputes them in every block at every denoising step.  K and V are kept per module for as long as
+        # the SAME encoder_hidden_states tensor object (held here, so its storage cannot be recycled) is passed again
+        # unmodified (`_version`) and the two weights are unchanged.  id(attn) -> _ContextKV
+        self.cache_context_kv = os.environ.get("AGENDA_CACHE_CONTEXT_KV", "1") != "0"
+        self._ctx_kv = {}
         self.cross_attn_maps: List[torch.Tensor] = []
         self.is_train = is_train
         self.latent_hw = latent_hw
@@ -60,8 +66,12 @@ class UNetCrossAttentionHooker:
         self._count = 0
 
     # ---- hook.py:25-26 -------------------------------------------------------------------------------------
-    def clear(self):
+    def clear(self, keep_context_kv: bool = False):
+        """hook.py:25-26.  Also forgets the cached prompt K/V unless `keep_context_kv` (a caller that replays a
+        captured CUDA graph reading those buffers keeps them and calls refresh_context_kv())."""
         self.cross_attn_maps.clear()
+        if not keep_context_kv:
+            self._ctx_kv.clear()
         if self._acc is not None:
             self._acc.zero_()
         for buf in self._layer_sums.values():
@@ -108,6 +118,37 @@ class UNetCrossAttentionHooker:
             self._qkv_weights[id(attn)] = hit
         return hit[1]
 
+    @staticmethod
+    def _kv_state(attn, ehs):
+        wk, wv = attn.to_k.weight, attn.to_v.weight
+        return (ehs._version, tuple(ehs.shape), wk.data_ptr(), wk._version, wv.data_ptr(), wv._version)
+
+    def _context_kv(self, attn, ehs):
+        ent = self._ctx_kv.get(id(attn))
+        state = self._kv_state(attn, ehs)
+        if ent is not None and ent[0] is ehs and ent[1] == state:
+            return ent[2], ent[3]
+        key, value = attn.to_k(ehs), attn.to_v(ehs)
+        if torch.is_grad_enabled() and (key.requires_grad or value.requires_grad):
+            return key, value  # never cache tensors that carry an autograd graph
+        self._ctx_kv[id(attn)] = (ehs, state, key, value, attn)
+        return key, value
+
+    def refresh_context_kv(self) -> None:
+        """Recompute every cached K / V IN PLACE from the tensor it was built from.  For callers that replay a captured
+        CUDA graph of the processor calls after overwriting the prompt embedding in place (HeatmapPipeline): the graph
+        reads the cached buffers, so they must be brought up to date outside the graph before the replays."""
+        for mod_id, (ehs, state, key, value, attn) in list(self._ctx_kv.items()):
+            new_state = self._kv_state(attn, ehs)
+            if new_state == state:
+                continue
+            if new_state[1] != state[1]:   # shape changed: rebuilt on the next call
+                del self._ctx_kv[mod_id]
+                continue
+            key.copy_(attn.to_k(ehs))
+            value.copy_(attn.to_v(ehs))
+            self._ctx_kv[mod_id] = (ehs, new_state, key, value, attn)
+
     def _accumulate(self, b_kept: int, n_tok: int, device) -> torch.Tensor:
         L = self.latent_hw
         if self._acc is None or self._acc.shape != (b_kept, n_tok, L, L) or self._acc.device != device:
@@ -138,8 +179,11 @@ class UNetCrossAttentionHooker:
         elif attn.norm_cross is not None:
             encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
 
-        key = attn.to_k(encoder_hidden_states)
-        value = attn.to_v(encoder_hidden_states)
+        if is_cross_attn and self.cache_context_kv and attn.norm_cross is None:
+            key, value = self._context_kv(attn, encoder_hidden_states)
+        else:
+            key = attn.to_k(encoder_hidden_states)
+            value = attn.to_v(encoder_hidden_states)
         heads = attn.heads
         scale = float(attn.scale)
 

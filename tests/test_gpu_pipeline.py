@@ -74,6 +74,51 @@ def test_pipeline_host_api_equals_device_api(cuda_ok):
     assert pipe.h2d_bytes(hs_h, ctx_h) > 0 and pipe.d2h_bytes(host) > 0
 
 
+def test_pipeline_graph_replay_follows_in_place_input_updates(cuda_ok):
+    """The captured graph reads the cached prompt K/V: overwriting the prompt embedding (and hidden states) in place
+    between runs must be picked up (refresh_context_kv), exactly as an eager run on fresh tensors would."""
+    from agenda_b200.pipeline import HeatmapPipeline
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=[1, 2, 3], num_steps=2, latent_hw=16, use_cuda_graph=True)
+    eager = HeatmapPipeline(_small_blocks(), 768, tokens=[1, 2, 3], num_steps=2, latent_hw=16, use_cuda_graph=False)
+    hs, ctx = pipe.make_inputs(2, seed=1)
+    out1 = {k: v.clone() for k, v in pipe.run_device(hs, ctx).items()}
+    hs2, ctx2 = pipe.make_inputs(2, seed=7)
+    for k in hs:
+        hs[k].copy_(hs2[k])
+    ctx.copy_(ctx2)                                   # same buffers, new content -> graph is replayed, not recaptured
+    out2 = pipe.run_device(hs, ctx)
+    ref2 = eager.run_device(hs2, ctx2)
+    assert not torch.equal(out2["heat"], out1["heat"])
+    assert torch.equal(out2["heat"], ref2["heat"]) and torch.equal(out2["boxes"], ref2["boxes"])
+
+
+def test_processor_context_kv_cache_invalidation(cuda_ok):
+    """Cached to_k/to_v of the prompt embedding: reused for the same unmodified tensor, rebuilt after an in-place edit
+    of the embedding or of a weight, never shared between different tensors."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    torch.manual_seed(0)
+    attn = SDAttention(320, 768, 8, 40).cuda().bfloat16()
+    x = torch.randn(2, 256, 320, device="cuda").bfloat16()
+    ctx = torch.randn(2, 77, 768, device="cuda").bfloat16()
+    cached = UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=[3])
+    plain = UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=[3])
+    plain.cache_context_kv = False
+    with torch.no_grad():
+        for step in range(3):
+            assert torch.equal(cached(attn, x, ctx), plain(attn, x, ctx))
+        assert len(cached._ctx_kv) == 1
+        ctx.mul_(0.5)                                  # in-place edit of the embedding
+        assert torch.equal(cached(attn, x, ctx), plain(attn, x, ctx))
+        attn.to_v.weight.add_(0.01)                    # in-place edit of a weight
+        assert torch.equal(cached(attn, x, ctx), plain(attn, x, ctx))
+        other = torch.randn(2, 77, 768, device="cuda").bfloat16()
+        assert torch.equal(cached(attn, x, other), plain(attn, x, other))
+        assert torch.equal(cached.compute_global_heat_map(), plain.compute_global_heat_map())
+        cached.clear()
+        assert len(cached._ctx_kv) == 0
+
+
 def test_trace_shim_end_to_end(cuda_ok):
     """data_generation.py:57-77 call sequence against the shim."""
     from agenda_b200.sd_attention import AttentionStack
