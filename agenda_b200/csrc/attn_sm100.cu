@@ -358,9 +358,11 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream);
   if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream);
   if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream);
-  // default measured on B200 (tools/bench_attn.py): two query tiles, full-row threads, 37.5 % (d = 40) or 25 % of the
-  // exponentials on the FMA pipe
-  if (variant == 0 && N > 128) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, d == 40 ? 3 : 4, 2, stream);
+  // defaults measured on B200 (tools/bench_attn.py): d = 40: three query tiles with 64-key tiles, 37.5 % of the
+  // exponentials on the FMA pipe; otherwise two query tiles with 128-key tiles (64 at d = 160), 25 %
+  if (variant == 0 && N > 128)
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3, stream)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2, stream);
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
     return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \

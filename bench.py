@@ -295,7 +295,7 @@ def run_ours(args):
     ms_all, flops_all, _ = summarize(self_calls, lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
-    roofline = {"kernel": "attn_self_sm100_v2_kernel<40,3,2,128,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",
+    roofline = {"kernel": "attn_self_sm100_v2_kernel<40,3,3,64,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture
                 # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (125.9 MB + 28.5 MB)
