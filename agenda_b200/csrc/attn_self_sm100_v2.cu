@@ -427,6 +427,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       float sv[CW];
 #pragma unroll
       for (int c = 0; c < CW / 32; ++c) tmem_ld32(s_taddr + c * 32, sv + c * 32);
+      if (CW % 32) tmem_ld16(s_taddr + (CW / 32) * 32, sv + (CW / 32) * 32);  // CW = 80: 32 + 32 + 16 columns
       tmem_wait_ld();
       if (!C::kAliasP) {
         tc_fence_before();
@@ -447,7 +448,9 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
           mx2 = fmax3(mx2, sv[i + 4], sv[i + 5]); mx3 = fmax3(mx3, sv[i + 6], sv[i + 7]);
         }
-        // CW = 128: elements 12..123 covered above, 124..127 here; CW = 64: 12..59 above, 60..63 here
+        // the loop covers elements 12 .. 12 + 8*floor((CW-12)/8) - 1; the last (CW - 12) % 8 = 4 elements follow here
+        // (CW = 128: 124..127, CW = 80: 76..79, CW = 64: 60..63)
+        static_assert(CW % 16 == 0 && (CW - 12) % 8 == 4, "max reduction assumes CW % 16 == 0");
         mx0 = fmax3(mx0, sv[CW - 4], sv[CW - 3]);
         mx1 = fmax3(mx1, sv[CW - 2], sv[CW - 1]);
         mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
@@ -496,18 +499,19 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       V2_TRACE((warp < 6 ? warp : 99), j, 3);
       const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
       uint64_t sum2a = pack_f32x2(0.f, 0.f), sum2b = sum2a;
+      // kCols = 32 (or a 16-column tail when CW % 32 == 16) scores -> exponentials -> kCols/2 packed bf16 P columns
+      auto exp_chunk = [&](const int col0, auto ncols_c) {
+        constexpr int kCols = decltype(ncols_c)::value;
+        uint32_t u[kCols / 2];
 #pragma unroll
-      for (int c = 0; c < CW / 32; ++c) {
-        uint32_t u[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const int e = c * 32 + 2 * i;
+        for (int i = 0; i < kCols / 2; i += 2) {
+          const int e = col0 + 2 * i;
           float a0, a1, b0, b1;
           const uint64_t xa = ffma2(pack_f32x2(sv[e], sv[e + 1]), scale2, negm2);
           const uint64_t xb = ffma2(pack_f32x2(sv[e + 2], sv[e + 3]), scale2, negm2);
           unpack_f32x2(xa, a0, a1);
           a0 = ex2(a0); a1 = ex2(a1);
-          // 16 pairs per 32-column chunk; pair b of iteration ib = i/2 is emulated according to kEmu:
+          // pair b of iteration ib = i/2 is emulated according to kEmu:
           // 2 -> every b pair (50 % of all exponentials), 3 -> ib % 3 != 2 (37.5 %), 4 -> even ib (25 %), 8 -> ib % 4 == 0
           const int ib = i >> 1;
           const bool emu_b = (kEmu == 2) || (kEmu == 3 && (ib % 3) != 2) || (kEmu == 4 && (ib & 1) == 0) ||
@@ -525,14 +529,18 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           u[i] = pack_bf16(a0, a1);
           u[i + 1] = pack_bf16(b0, b1);
         }
-        if (c == 0 && !pv_waited) {
+        if (col0 == 0 && !pv_waited) {
           V2_TRACE((warp < 6 ? warp : 99), j, 6);
           mbar_wait(&bars->pv_done[t], (j - 1) & 1);
           tc_fence_after();
           V2_TRACE((warp < 6 ? warp : 99), j, 7);
         }
-        tmem_st16(p_taddr + c * 16, u);  // P as packed bf16 pairs
-      }
+        if (kCols == 32) tmem_st16(p_taddr + col0 / 2, u);  // P as packed bf16 pairs
+        else tmem_st8(p_taddr + col0 / 2, u);
+      };
+#pragma unroll
+      for (int c = 0; c < CW / 32; ++c) exp_chunk(c * 32, std::integral_constant<int, 32>{});
+      if (CW % 32) exp_chunk((CW / 32) * 32, std::integral_constant<int, 16>{});
       if (pingpong && !(t == 1 && j + 1 == n_tiles))  // (tile 1's last pass has nobody left to release)
         asm volatile("bar.arrive %0, %1;" ::"r"(3 + (t ^ 1)), "r"(2 * KS * 128) : "memory");
       float s0, s1, s2, s3;
@@ -637,6 +645,12 @@ int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, i
       case 40: AGENDA_V2_EMU(40, 3, 64, 1)
       case 64: AGENDA_V2_EMU(64, 3, 64, 1)
       default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 3-tile variant needs head dim 40 or 64, got %d", d);
+    }
+  }
+  if (tiles == 6) {  // three query tiles, 80-key tiles: the most keys per tile that fit TMEM at d = 40 (504 columns)
+    switch (d) {
+      case 40: AGENDA_V2_EMU(40, 3, 80, 1)
+      default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: 3x80 variant is for head dim 40, got %d", d);
     }
   }
   if (tiles == 5) {  // two query tiles, 64-key tiles: P gets its own TMEM columns at d = 80 (no S/P aliasing)

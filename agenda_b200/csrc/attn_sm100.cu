@@ -354,6 +354,8 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   // variants 20/22/23/24/28: the same emulation shares with three query tiles per CTA and 64-key tiles (d = 40 / 64)
   // variants 30/32/33/34/38: two query tiles, two softmax warpgroups per tile (half a row per thread; d = 40 / 64)
   // variants 40/42/43/44/48: two query tiles with 64-key tiles (d = 80: separate P columns instead of S/P aliasing)
+  // variants 50/52/53/54/58: three query tiles with 80-key tiles (d = 40)
+  if (variant >= 50) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 50, 6, stream);
   if (variant >= 40) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 40, 5, stream);
   if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream);
   if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream);

@@ -64,6 +64,21 @@ def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
+@pytest.mark.parametrize("variant", [50, 53, 54])
+@pytest.mark.parametrize("B,N,H,d", [(1, 128, 1, 40), (1, 256, 2, 40), (2, 1024, 8, 40), (2, 300, 2, 40), (1, 4096, 2, 40),
+                                     (1, 80, 1, 40), (1, 385, 3, 40)])
+def test_sm100_self_attention_d40_80key_tiles(lib, B, N, H, d, variant):
+    """d = 40 with three query tiles and 80-key tiles (32 + 32 + 16 score columns per thread and tile)."""
+    g = torch.Generator().manual_seed(N * 3 + variant)
+    q = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    k = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16()
+    v = (torch.randn(B, N, H * d, generator=g) * 0.25).bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, variant)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
+
+
 @pytest.mark.parametrize("variant", [40, 44])
 @pytest.mark.parametrize("B,N,H,d", [(2, 1024, 8, 80), (1, 200, 2, 80), (1, 64, 1, 80)])
 def test_sm100_self_attention_d80_64key_tiles(lib, B, N, H, d, variant):
@@ -78,7 +93,7 @@ def test_sm100_self_attention_d80_64key_tiles(lib, B, N, H, d, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34, 53])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
     B, N, H, d = 1, 1024, 2, 40
@@ -93,7 +108,7 @@ def test_sm100_peaked_softmax_and_rescale(lib, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 10, 14, 20, 30])
+@pytest.mark.parametrize("variant", [0, 10, 14, 20, 30, 53])
 def test_sm100_score_jump_beyond_lazy_max_guard(lib, variant):
     """Scores of a late key tile tower (by far more than 2^64) over everything before it: the lazy running-max path must
     re-run that tile against its own max instead of overflowing."""
