@@ -30,7 +30,7 @@ constexpr int kTraceTiles = 24, kTraceEvents = 8, kTraceActors = 8;
 __device__ long long g_v2_trace[kTraceActors * kTraceTiles * kTraceEvents];
 #define V2_TRACE(actor, j, ev)                                                                             \
   do {                                                                                                     \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (actor) < kTraceActors &&        \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (actor) < kTraceActors &&                           \
         (j) < kTraceTiles)                                                                                 \
       g_v2_trace[((actor) * kTraceTiles + (j)) * kTraceEvents + (ev)] = clock64();                         \
   } while (0)
@@ -161,8 +161,21 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   V2Barriers* bars = reinterpret_cast<V2Barriers*>(sV + ST * C::kKVBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int q0 = blockIdx.x * (128 * NT);
-  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  // 1-D grid, longest work first: the CTAs whose NT query tiles are all inside the sequence come first (n_full per
+  // (batch, head)), the partly filled last CTA of every (batch, head) at the end, where they fill the tail of the
+  // last wave instead of being sprinkled through it (N = 4096, NT = 3: 1280 full + 128 two-tile CTAs on 148 SMs).
+  const int n_full_ctas = N / (128 * NT);
+  const int n_bh = gridDim.x / (n_full_ctas + ((N % (128 * NT)) ? 1 : 0));
+  int bh, qt;
+  if (static_cast<int>(blockIdx.x) < n_bh * n_full_ctas) {
+    bh = blockIdx.x / n_full_ctas;
+    qt = blockIdx.x - bh * n_full_ctas;
+  } else {
+    bh = blockIdx.x - n_bh * n_full_ctas;
+    qt = n_full_ctas;
+  }
+  const int q0 = qt * (128 * NT);
+  const int b = bh / H, h = bh - b * H;
   const int n_tiles = (N + BN - 1) / BN;
   const int nt = min(NT, (N - q0 + 127) / 128);  // query tiles of this CTA that hold at least one row
 
@@ -613,7 +626,7 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
   constexpr size_t smem = sm100::v2_smem_bytes<C>();
   auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid((N + 128 * NT - 1) / (128 * NT), B * H);
+  dim3 grid(static_cast<unsigned>(((N + 128 * NT - 1) / (128 * NT)) * B * H));
   // measured on B200 (tools/bench_attn.py): one MMA warp per query tile (2) wins except where P aliases S (d = 80)
   int issue_order = C::kAliasP ? 0 : 2;
   if (const char* e = getenv("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only (+4: exp-pass ping-pong)
