@@ -515,20 +515,28 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
   return v;
 }
 
-template <int kThreads>
+// kCS > 1: the two streaming passes of a map are split over a cluster of kCS CTAs (min / max exchanged and the mask
+// words delivered to the leader through distributed shared memory, two cluster barriers); the other CTAs then exit
+// and the leader labels the map alone.  A quarter of a map is re-read ~4x sooner after it was first read, so pass 2
+// finds it in L2 instead of going back to HBM.
+template <int kThreads, int kCS>
 __global__ void __launch_bounds__(kThreads)
 ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
                     int32_t* __restrict__ boxes, int max_boxes, int H, int W, int cap, int hints) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ float red_min[32], red_max[32];
   __shared__ int red_nan[32], warp_tot[32];
+  __shared__ float x_min[kCS], x_max[kCS];
+  __shared__ int x_nan[kCS];
   __shared__ float sh_hstar;
   __shared__ int sh_mode, sh_total;
   __shared__ int sbox[kSmemBoxes * 5];
 
   constexpr int kWarps = kThreads / 32;
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const long long map = blockIdx.x;
+  const long long map = blockIdx.x / kCS;
+  const int rank = (kCS > 1) ? static_cast<int>(cluster.block_rank()) : 0;
   const int n_px = H * W;
   const int wpr = W >> 5;
   const int n_words = H * wpr;
@@ -537,6 +545,9 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   unsigned short* base = reinterpret_cast<unsigned short*>(slots + cap);  // first piece id of every word
   const float4* src4 = reinterpret_cast<const float4*>(heat + map * n_px);
   const int n4 = n_px >> 2;
+  // this CTA's share of the two passes: whole mask words (8 float4 each)
+  const int words_per_rank = (n_words + kCS - 1) / kCS;
+  const int i_begin = min(n4, rank * words_per_rank * 8), i_end = min(n4, (rank + 1) * words_per_rank * 8);
 
   // ---- pass 1: min / max / NaN ----
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
@@ -545,8 +556,8 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   {
     float lo = INFINITY, hi = -INFINITY;
     int nan = 0;
-    int i = tid;
-    for (; i + 3 * kThreads < n4; i += 4 * kThreads) {
+    int i = i_begin + tid;
+    for (; i + 3 * kThreads < i_end; i += 4 * kThreads) {
       const float4 a = ld1(i), b = ld1(i + kThreads), c = ld1(i + 2 * kThreads), d = ld1(i + 3 * kThreads);
       lo = fminf(fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w))), fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
       lo = fminf(fminf(fminf(lo, c.x), fminf(c.y, fminf(c.z, c.w))), fminf(fminf(d.x, d.y), fminf(d.z, d.w)));
@@ -556,7 +567,7 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
              (b.w != b.w) | (c.x != c.x) | (c.y != c.y) | (c.z != c.z) | (c.w != c.w) | (d.x != d.x) | (d.y != d.y) |
              (d.z != d.z) | (d.w != d.w);
     }
-    for (; i < n4; i += kThreads) {
+    for (; i < i_end; i += kThreads) {
       const float4 a = ld1(i);
       lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
       hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
@@ -567,12 +578,35 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
     if (lane == 0) { red_min[wid] = lo; red_max[wid] = hi; red_nan[wid] = nan; }
   }
   __syncthreads();
+  if (kCS > 1) {  // CTA partials -> every CTA of the cluster
+    if (wid == 0) {
+      float mn = lane < kWarps ? red_min[lane] : INFINITY;
+      float mx = lane < kWarps ? red_max[lane] : -INFINITY;
+      int any_nan = lane < kWarps ? red_nan[lane] : 0;
+      mn = warp_min(mn); mx = warp_max(mx);
+      any_nan = __any_sync(0xffffffffu, any_nan);
+      if (lane < kCS) {
+        *cluster.map_shared_rank(&x_min[rank], lane) = mn;
+        *cluster.map_shared_rank(&x_max[rank], lane) = mx;
+        *cluster.map_shared_rank(&x_nan[rank], lane) = any_nan;
+      }
+    }
+    cluster.sync();
+  }
 
   // ---- warp 0: smallest float h* with ((h*-min)/denom) > thr (32-ary search over ordered bit patterns) ----
   if (wid == 0) {
-    float mn = lane < kWarps ? red_min[lane] : INFINITY;
-    float mx = lane < kWarps ? red_max[lane] : -INFINITY;
-    int any_nan = lane < kWarps ? red_nan[lane] : 0;
+    float mn, mx;
+    int any_nan;
+    if (kCS > 1) {
+      mn = lane < kCS ? x_min[lane] : INFINITY;
+      mx = lane < kCS ? x_max[lane] : -INFINITY;
+      any_nan = lane < kCS ? x_nan[lane] : 0;
+    } else {
+      mn = lane < kWarps ? red_min[lane] : INFINITY;
+      mx = lane < kWarps ? red_max[lane] : -INFINITY;
+      any_nan = lane < kWarps ? red_nan[lane] : 0;
+    }
     mn = warp_min(mn); mx = warp_max(mx);
     any_nan = __any_sync(0xffffffffu, any_nan);
     const float denom = np_denominator(mn, mx);
@@ -612,24 +646,32 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   const float hstar = sh_hstar;
   const int mode = sh_mode;
 
-  // ---- pass 2 (reverse order: the end of the map is the most recently used part of L2): threshold -> mask words ----
+  // ---- pass 2 (reverse order: the end of the range is the most recently used part of L2): threshold -> mask words,
+  //      written into the LEADER's mask (its own shared memory when kCS == 1) ----
+  uint32_t* lead_bits = (kCS > 1) ? cluster.map_shared_rank(bits, 0) : bits;
   if (mode == 0) {
-    const int iters = (n4 + kThreads - 1) / kThreads;
+    const int span = i_end - i_begin;
+    const int iters = (span + kThreads - 1) / kThreads;
     for (int it = iters - 1; it >= 0; --it) {
-      const int i = it * kThreads + tid;
+      const int i = i_begin + it * kThreads + tid;
       uint32_t nib = 0;
-      if (i < n4) {
+      if (i < i_end) {
         const float4 v = ld2(i);
         nib = (v.x >= hstar ? 1u : 0u) | (v.y >= hstar ? 2u : 0u) | (v.z >= hstar ? 4u : 0u) | (v.w >= hstar ? 8u : 0u);
       }
       const uint32_t word = __reduce_or_sync(0xFFu << (lane & 24), nib << ((lane & 7) * 4));  // 8 lanes = one word
-      if ((lane & 7) == 0 && i < n4) bits[i >> 3] = word;
+      if ((lane & 7) == 0 && i < i_end) lead_bits[i >> 3] = word;
     }
   } else {
     const uint32_t fill = (mode == 2) ? 0xFFFFFFFFu : 0u;
-    for (int w = tid; w < n_words; w += kThreads) bits[w] = fill;
+    for (int w = (i_begin >> 3) + tid; w < (i_end >> 3); w += kThreads) lead_bits[w] = fill;
   }
-  __syncthreads();
+  if (kCS > 1) {
+    cluster.sync();          // the leader's mask is complete; nobody touches another CTA's shared memory after this
+    if (rank != 0) return;
+  } else {
+    __syncthreads();
+  }
 
   // ---- compact piece ids: thread t owns a contiguous word range; exclusive block scan of the piece counts ----
   const int wpt = (n_words + kThreads - 1) / kThreads;
@@ -855,11 +897,44 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
         cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define AGENDA_CCL_CTA(T)                                                                                              \
   do {                                                                                                                 \
-    AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                     static_cast<int>(smem_cta)));                                                     \
-    ccl_bbox_cta_kernel<T><<<n, T, smem_cta, st>>>(heat, thr, labels, counts, boxes, max_boxes, H, W,                  \
-                                                   static_cast<int>(cap), hints);                                      \
+    if (cta_cluster == 2) {                                                                                            \
+      AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       static_cast<int>(smem_cta)));                                                   \
+      cudaLaunchConfig_t c4 = {};                                                                                      \
+      c4.gridDim = dim3(static_cast<unsigned>(static_cast<long long>(n) * 2));                                         \
+      c4.blockDim = dim3(T);                                                                                           \
+      c4.dynamicSmemBytes = smem_cta;                                                                                  \
+      c4.stream = st;                                                                                                  \
+      cudaLaunchAttribute a4[1];                                                                                       \
+      a4[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+      a4[0].val.clusterDim.x = 2; a4[0].val.clusterDim.y = 1; a4[0].val.clusterDim.z = 1;                              \
+      c4.attrs = a4; c4.numAttrs = 1;                                                                                  \
+      AGENDA_CUDA(cudaLaunchKernelEx(&c4, ccl_bbox_cta_kernel<T, 2>, heat, thr, labels, counts, boxes, max_boxes, H,   \
+                                     W, static_cast<int>(cap), hints));                                                \
+    } else if (cta_cluster == 4) {                                                                                     \
+      AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       static_cast<int>(smem_cta)));                                                   \
+      cudaLaunchConfig_t c4 = {};                                                                                      \
+      c4.gridDim = dim3(static_cast<unsigned>(static_cast<long long>(n) * 4));                                         \
+      c4.blockDim = dim3(T);                                                                                           \
+      c4.dynamicSmemBytes = smem_cta;                                                                                  \
+      c4.stream = st;                                                                                                  \
+      cudaLaunchAttribute a4[1];                                                                                       \
+      a4[0].id = cudaLaunchAttributeClusterDimension;                                                                  \
+      a4[0].val.clusterDim.x = 4; a4[0].val.clusterDim.y = 1; a4[0].val.clusterDim.z = 1;                              \
+      c4.attrs = a4; c4.numAttrs = 1;                                                                                  \
+      AGENDA_CUDA(cudaLaunchKernelEx(&c4, ccl_bbox_cta_kernel<T, 4>, heat, thr, labels, counts, boxes, max_boxes, H,   \
+                                     W, static_cast<int>(cap), hints));                                                \
+    } else {                                                                                                           \
+      AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                       static_cast<int>(smem_cta)));                                                   \
+      ccl_bbox_cta_kernel<T, 1><<<n, T, smem_cta, st>>>(heat, thr, labels, counts, boxes, max_boxes, H, W,             \
+                                                        static_cast<int>(cap), hints);                                 \
+    }                                                                                                                  \
   } while (0)
+        int cta_cluster = 1;  // 4: split the two streaming passes of a map over a 4-CTA cluster
+        if (const char* e = getenv("AGENDA_CCL_CTA_CLUSTER")) { const int c = atoi(e); cta_cluster = (c == 4 || c == 2) ? c : 1; }
+        if (n_words < 64) cta_cluster = 1;
         int hints = 1;  // measured: +1-2 % (pass 2 still misses L2: ~300 MB of maps are in flight, L2 is 126 MB)
         if (const char* e = getenv("AGENDA_CCL_HINTS")) hints = atoi(e);
         int cta_threads = n_px >= 65536 ? 1024 : (n_px >= 16384 ? 256 : 128);
