@@ -57,7 +57,9 @@ class HeatmapPipeline:
         [n,S,S], counts int32 [n], boxes int32 [n,max_boxes,5] (x,y,w,h,area on the object-token map)."""
         proc = self.proc
         proc.clear(keep_context_kv=True)  # the captured graph reads the cached prompt K/V buffers
-        proc.refresh_context_kv()         # the prompt embedding may have been overwritten in place since the last run
+        # every run is a new batch of images: the prompt K/V are projected once per batch here (not once per denoising
+        # step as in the reference, hook.py:101-102) — also picks up an embedding overwritten in place since the last run
+        proc.refresh_context_kv(force=True)
         key = (tuple((k, v.data_ptr()) for k, v in sorted(hs.items())), ctx.data_ptr())
         if self.use_cuda_graph:
             if self._graph is None or self._graph_key != key:

@@ -134,13 +134,14 @@ class UNetCrossAttentionHooker:
         self._ctx_kv[id(attn)] = (ehs, state, key, value, attn)
         return key, value
 
-    def refresh_context_kv(self) -> None:
-        """Recompute every cached K / V IN PLACE from the tensor it was built from.  For callers that replay a captured
-        CUDA graph of the processor calls after overwriting the prompt embedding in place (HeatmapPipeline): the graph
-        reads the cached buffers, so they must be brought up to date outside the graph before the replays."""
+    def refresh_context_kv(self, force: bool = False) -> None:
+        """Recompute cached K / V IN PLACE from the tensor they were built from (only those whose source or weights
+        changed, or all of them with `force`).  For callers that replay a captured CUDA graph of the processor calls
+        after overwriting the prompt embedding in place (HeatmapPipeline): the graph reads the cached buffers, so they
+        must be brought up to date outside the graph before the replays."""
         for mod_id, (ehs, state, key, value, attn) in list(self._ctx_kv.items()):
             new_state = self._kv_state(attn, ehs)
-            if new_state == state:
+            if new_state == state and not force:
                 continue
             if new_state[1] != state[1]:   # shape changed: rebuilt on the next call
                 del self._ctx_kv[mod_id]

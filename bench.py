@@ -116,7 +116,8 @@ def workload_config(args, world):
                         "UNet forward, H=8, d=40/80/160, ctx 77x768), 512^2 image / 64^2 latent, 50 denoising steps, "
                         f"batch {args.images_per_step} images per GPU (CFG => UNet batch {2 * args.images_per_step}), "
                         "heat maps for 3 tokens + u8 stacks (112^2) + CCL boxes; non-attention UNet layers replaced by "
-                        "synthetic hidden states",
+                        "synthetic hidden states; to_k/to_v of the prompt embedding are projected once per image batch "
+                        "(loop-invariant over the denoising steps), everything else runs at every step",
             "images_per_step_per_gpu": args.images_per_step, "denoise_steps": NUM_DENOISE_STEPS, "tokens": len(TOKENS),
             "parallelism": f"dp{world} (seed-sharded, final NCCL all_gather of boxes+heat maps)",
             "l2": "per-step working set (hidden states 76 MB + Q/K/V/O activations > 300 MB) exceeds the 126 MB L2; "
