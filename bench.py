@@ -47,7 +47,7 @@ def parse():
 # CPU arm: the reference's algorithm (oracle port of hook.py + numpy/PIL/scipy post-processing) on the host cores
 # ------------------------------------------------------------------------------------------------------------
 
-def cpu_reference_sample(sample_steps: int = 2, seed: int = 0):
+def cpu_reference_sample(sample_steps: int = 6, seed: int = 0):
     """Times `sample_steps` of the 50 denoising steps for ONE image (UNet batch 2) through the oracle port, plus the
     aggregation and post-processing once, and extrapolates to a full image.  Returns (images/s, detail dict)."""
     import numpy as np
@@ -96,7 +96,7 @@ def run_reference(args):
     detail = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, detail = cpu_reference_sample(2)
+        v, detail = cpu_reference_sample(6)
         vals.append(v)
     wall = time.perf_counter() - t0
     value = sum(vals) / len(vals)
@@ -337,7 +337,7 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, d = cpu_reference_sample(2)
+        v, d = cpu_reference_sample(6)
         cpu = {"value": v, "unit": UNIT, "cores": d["cores"], "kind": "port", "sample": d["sample"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
