@@ -62,6 +62,27 @@ def test_pipeline_matches_oracle(cuda_ok, graph):
     assert torch.equal(out2["heat"], out["heat"]) and torch.equal(out2["boxes"], out["boxes"])
 
 
+def test_pipeline_sd21_config4_shapes(cuda_ok):
+    """BASELINE configs[3] at its real layer shapes: SD-2.1 768^2 -> 96^2 latent (N = 9216 / 2304 / 576 / 144, d = 64,
+    H = 5 / 10 / 20 / 20, context 77 x 1024), four vehicle-class tokens, one image, two denoising steps; heat maps against
+    the oracle, everything downstream bit-exact on our heat map."""
+    from agenda_b200.pipeline import sd21_pipeline
+    toks = [4, 5, 6, 7]
+    pipe = sd21_pipeline(tokens=toks, num_steps=2, use_cuda_graph=True, max_boxes=32)
+    hs, ctx = pipe.make_inputs(1, seed=11)
+    out = pipe.run_device(hs, ctx)
+    heat = out["heat"].cpu().numpy()
+    ref = _oracle_heat(pipe, hs, ctx, 2, toks)
+    assert heat.shape == ref.shape == (1, 4, 96, 96)
+    assert np.abs(heat - ref).max() < 2e-3 * ref.max() + 1e-5
+    planes = [O.heat_to_png_array(heat[0, t], 112) for t in range(3)]
+    rs, ri = O.stack_heatmaps(*planes)
+    assert np.array_equal(out["stack"][0].cpu().numpy(), rs) and np.array_equal(out["inv"][0].cpu().numpy(), ri)
+    rl, rb = O.ccl_bbox(heat[0, 0], 0.5)
+    assert out["counts"][0].item() == len(rb)
+    assert np.array_equal(out["boxes"][0, :min(len(rb), 32)].cpu().numpy(), rb[:32])
+
+
 def test_pipeline_host_api_equals_device_api(cuda_ok):
     from agenda_b200.pipeline import HeatmapPipeline
     pipe = HeatmapPipeline(_small_blocks(), 768, tokens=[1, 2, 3], num_steps=2, latent_hw=16, use_cuda_graph=True)
