@@ -36,11 +36,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--images-per-step", type=int, default=8)
+    ap.add_argument("--images-per-step", type=int, default=None, help="default 8 (sd15) / 16 (sd21)")
+    ap.add_argument("--workload", default="sd15", choices=["sd15", "sd21"],
+                    help="sd15 = BASELINE configs[1] (the headline metric); sd21 = configs[3] (SD-2.1 768^2, 96^2 latent, "
+                         "batch 16, 4 tokens) — informational")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ccl-maps", type=int, default=2048, help="512^2 maps for the post-process roofline probe")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.images_per_step is None:
+        a.images_per_step = 16 if a.workload == "sd21" else 8
+    return a
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -112,6 +118,15 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    if args.workload == "sd21":
+        return {"workload": "BASELINE configs[3]: SD-2.1-768 attention stack (16 transformer blocks, H=5/10/20/20, d=64, ctx "
+                            "77x1024), 768^2 image / 96^2 latent, 50 denoising steps, batch "
+                            f"{args.images_per_step} images per GPU (CFG => UNet batch {2 * args.images_per_step}), heat maps "
+                            "for 4 tokens + u8 stacks + CCL boxes; non-attention UNet layers replaced by synthetic hidden "
+                            "states; prompt K/V projected once per image batch",
+                "images_per_step_per_gpu": args.images_per_step, "denoise_steps": NUM_DENOISE_STEPS, "tokens": 4,
+                "parallelism": f"dp{world} (seed-sharded, final NCCL all_gather of boxes+heat maps)",
+                "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"}
     return {"workload": "BASELINE configs[1]: SD-1.5 attention stack (16 transformer blocks, 32 processor calls per "
                         "UNet forward, H=8, d=40/80/160, ctx 77x768), 512^2 image / 64^2 latent, 50 denoising steps, "
                         f"batch {args.images_per_step} images per GPU (CFG => UNet batch {2 * args.images_per_step}), "
@@ -181,7 +196,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from agenda_b200 import _lib, ops
-    from agenda_b200.pipeline import sd15_pipeline
+    from agenda_b200.pipeline import sd15_pipeline, sd21_pipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,7 +209,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     n_img = args.images_per_step
 
-    pipe = sd15_pipeline(tokens=TOKENS, num_steps=NUM_DENOISE_STEPS, device=dev, use_cuda_graph=not args.no_graph)
+    sd21 = args.workload == "sd21"
+    make_pipe = sd21_pipeline if sd21 else sd15_pipeline
+    pipe = make_pipe(tokens=(4, 5, 6, 7) if sd21 else TOKENS, num_steps=NUM_DENOISE_STEPS, device=dev,
+                     use_cuda_graph=not args.no_graph)
+    big_n, big_d = (9216, 64) if sd21 else (4096, 40)
     hs_dev, ctx_dev = pipe.make_inputs(n_img, seed=rank)
     hs_host, ctx_host = pipe.make_inputs(n_img, seed=rank, pinned_host=True)
     staging = pipe.make_staging(hs_host, ctx_host)
@@ -292,19 +311,21 @@ def run_ours(args):
     # args of agenda_attn_self_fwd[_strided]: q,k,v,out,dtype,B,H,N,d,[ld,]scale,stream
     self_calls = sink["agenda_attn_self_fwd"] + sink["agenda_attn_self_fwd_strided"]
     ms_k, flops, n_k = summarize(self_calls,
-                                 lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8] if a[7] == 4096 else None)
+                                 lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8] if a[7] == big_n else None)
     ms_all, flops_all, _ = summarize(self_calls, lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
-    roofline = {"kernel": "attn_self_sm100_v2_kernel<40,3,3,64,1> (N=4096, B*H=%d)" % (2 * n_img * 8), "bound": "tensor",
+    kname = ("attn_self_sm100_v2_kernel<64,4,2,128,1> (N=9216, B*H=%d)" % (2 * n_img * 5) if sd21 else
+             "attn_self_sm100_v2_kernel<40,3,3,64,1> (N=4096, B*H=%d)" % (2 * n_img * 8))
+    roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture
                 # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (125.9 MB + 28.5 MB)
-                "traffic": 154.4e6 if n_img == 8 else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+                "traffic": 154.4e6 if (n_img == 8 and not sd21) else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "avg_launch_ms": ms_k / max(n_k, 1), "launches_timed": n_k,
                 "share_of_step": (ms_k / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
                 "how": "CUDA events around each launch in an eager replay of 5 denoising steps; useful FLOPs "
-                       "4*B*N*N*C with unpadded d=40"}
+                       "4*B*N*N*C with unpadded d=%d" % big_d}
 
     # ---- HBM-bound kernels: CCL on 512^2 maps (config 5 shape), standalone probe inside this run ----
     from agenda_b200.synthetic import synthetic_heatmaps
