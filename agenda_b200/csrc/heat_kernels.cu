@@ -1,6 +1,8 @@
 // K3: streaming form of compute_global_heat_map (reference data_generation/hook.py:59-81).
 //   acc += clamp(bicubic_upsample(map), min=0)   per (layer, step) map;   out = acc / count at the end.
 // HBM-bound: per plane read h*w*4 B (stays in L1/L2 for the 16 taps) and read-modify-write L*L*4 B twice.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace agenda {
@@ -90,15 +92,14 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_kernel(const float* _
 // loads per output.  HBM traffic per plane = h*w*4 read + L*L*8 read-modify-write, the algorithmic minimum.
 // blockDim.x = L * k (k >= 1), so a thread's output column x = tid % L is fixed in pass 1.
 __global__ void __launch_bounds__(256) heat_upsample_accum_tiled_kernel(const float* __restrict__ maps,
-                                                                        float* __restrict__ acc, int h, int w, int L,
-                                                                        int T, int G) {
+                                                                        float* __restrict__ acc, int n_planes, int h,
+                                                                        int w, int L, int T, int G) {
   extern __shared__ __align__(16) float up_smem[];
   float* s_src = up_smem;                                   // [h*w]
   float* s_tmp = s_src + ((h * w + 3) & ~3);                // [h][L] horizontal sums
   float* s_wy = s_tmp + h * L;                              // [L][4]
   int* s_iy = reinterpret_cast<int*>(s_wy + 4 * L);         // [L][4] (row offsets into s_tmp)
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int plane = blockIdx.x;
   const float sy = static_cast<float>(h) / static_cast<float>(L);
   const float sx = static_cast<float>(w) / static_cast<float>(L);
   for (int y = tid; y < L; y += nthr) {
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_tiled_kernel(const fl
   const int x = tid % L, r0 = tid / L, r_step = nthr / L;
   int ix[4]; float wx[4];
   cubic_src(x, sx, w, ix, wx);
-  const int bp = plane / T, tt = plane - bp * T;
   const int quads_per_row = L >> 2;
+  for (int plane = blockIdx.x; plane < n_planes; plane += gridDim.x) {  // tables are shared by every plane of the CTA
+  const int bp = plane / T, tt = plane - bp * T;
   float4* dst_plane = reinterpret_cast<float4*>(acc + static_cast<long long>(plane) * L * L);
   for (int g = 0; g < G; ++g) {
     const float* __restrict__ src = maps + (static_cast<long long>(bp * G + g) * T + tt) * h * w;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_tiled_kernel(const fl
       a.w += fmaxf(o3, 0.f);
       dst_plane[q] = a;
     }
+  }
   }
 }
 
@@ -196,8 +199,10 @@ static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes,
                                          4 * L) + sizeof(int) * 4 * L;
     AGENDA_CUDA(cudaFuncSetAttribute(heat_upsample_accum_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
-    heat_upsample_accum_tiled_kernel<<<n_planes, threads_t, smem, static_cast<cudaStream_t>(stream)>>>(maps, acc, h, w,
-                                                                                                      L, T, G);
+    // small source planes: several planes per CTA (the tap tables are built once); larger ones: one CTA per plane
+    const int grid_t = (h * w <= 256) ? std::min(n_planes, num_sms() * 8) : n_planes;
+    heat_upsample_accum_tiled_kernel<<<grid_t, threads_t, smem, static_cast<cudaStream_t>(stream)>>>(maps, acc, n_planes,
+                                                                                                     h, w, L, T, G);
     AGENDA_LAUNCH_CHECK("heat_upsample_accum_tiled_kernel");
     return AGENDA_OK;
   }

@@ -39,8 +39,8 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 byts = 8192 * (3 * 64 * 64 * 4 + 3 * 112 * 112 * 2 + 112 * 112)
 print(f"heat_postprocess_stack n=8192: {ms:.3f} ms  {byts / ms / 1e6:.1f} GB/s")
-acc = torch.zeros((64, 77, 64, 64), device="cuda")
-m32 = torch.rand((64, 77, 32, 32), device="cuda")
+acc = torch.zeros((256, 77, 64, 64), device="cuda")
+m32 = torch.rand((256, 77, 32, 32), device="cuda")
 for _ in range(2):
     ops.heat_upsample_accum(m32, acc)
 torch.cuda.synchronize()
@@ -50,5 +50,5 @@ for _ in range(5):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-byts = 64 * 77 * (32 * 32 * 4 + 64 * 64 * 8)
-print(f"heat_upsample_accum 32->64 planes={64*77}: {ms:.3f} ms  {byts / ms / 1e6:.1f} GB/s")
+byts = 256 * 77 * (32 * 32 * 4 + 64 * 64 * 8)
+print(f"heat_upsample_accum 32->64 planes={256*77}: {ms:.3f} ms  {byts / ms / 1e6:.1f} GB/s")
