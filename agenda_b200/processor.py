@@ -164,6 +164,10 @@ class UNetCrossAttentionHooker:
         attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
         if attention_mask is not None:
             raise NotImplementedError("agenda_b200: attention masks are not supported (the SD UNet passes none)")
+        if torch.is_grad_enabled() and hidden_states.requires_grad:
+            # the kernels are forward only: silently returning tensors without a grad_fn would train on zero gradients
+            raise NotImplementedError("agenda_b200: the processor is forward only (no autograd through the CUDA "
+                                      "kernels); run it under torch.no_grad() — training is out of scope")
         if (encoder_hidden_states is None and self.fuse_qkv and self.precision == "bf16"
                 and hidden_states.dtype == torch.bfloat16 and hidden_states.is_cuda):
             w = self._fused_qkv_weight(attn)

@@ -140,6 +140,18 @@ def test_processor_context_kv_cache_invalidation(cuda_ok):
         assert len(cached._ctx_kv) == 0
 
 
+def test_processor_refuses_autograd(cuda_ok):
+    """Forward only: activations that require grad must fail loudly instead of silently dropping the graph."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    attn = SDAttention(320, None, 8, 40).cuda().bfloat16()
+    x = torch.randn(2, 64, 320, device="cuda").bfloat16().requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        UNetCrossAttentionHooker(is_train=True)(attn, x)
+    with torch.no_grad():
+        assert UNetCrossAttentionHooker(is_train=True)(attn, x).shape == x.shape
+
+
 def test_trace_shim_end_to_end(cuda_ok):
     """data_generation.py:57-77 call sequence against the shim."""
     from agenda_b200.sd_attention import AttentionStack
