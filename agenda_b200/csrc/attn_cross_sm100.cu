@@ -14,6 +14,8 @@
 // TMEM: S/P[2] (96 columns each) | O[2] (round16(d) columns each).
 // At the end each thread parks its accumulator in its own shared-memory row and emits the selected token columns:
 // consecutive threads = consecutive pixels, so every token plane is written with coalesced 128-byte stores.
+#include <cstdlib>
+
 #include "sm100_common.cuh"
 
 namespace agenda {
@@ -331,6 +333,10 @@ static int launch_cross(const void* q, const void* k, const void* v, void* out, 
              : launch_cross_t<D, false>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, stream);
 }
 
+int attn_cross_sm100_res(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
+                         float scale, const TokenList& tl, int b_first, float* maps, int accumulate, int QT,
+                         void* stream);
+
 // bf16 tensor-core path; returns AGENDA_ERR_UNSUPPORTED for shapes it does not cover.
 int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
                      float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream) {
@@ -342,6 +348,22 @@ int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "attn_cross_fwd_heat: q/k/v/out must be 16-byte aligned");
+  // Resident-K/V form (attn_cross_sm100_res.cu): d of one swizzle chunk, few heat tokens, all heads' K/V fit beside the
+  // Q ring.  QT query tiles per CTA: the smallest count that puts the whole launch into one wave of CTAs.
+  {
+    bool use_res = (d == 40 || d == 64) && H <= 8 && (maps == nullptr || tl.n <= sm100::kXFewTokens);
+    if (const char* e = getenv("AGENDA_XRES")) use_res = use_res && atoi(e) != 0;
+    if (use_res) {
+      const int n_tiles = (N + sm100::kXBlockM - 1) / sm100::kXBlockM, sms = num_sms();
+      int QT = 1;
+      while (QT < 32 && ((n_tiles + QT - 1) / QT) * B > sms) ++QT;
+      if (const char* e = getenv("AGENDA_XRES_QT")) { const int t = atoi(e); if (t >= 1 && t <= 64) QT = t; }
+      // one CTA per SM: pays off once every CTA amortises its K/V block over several query tiles (B = 16, N = 4096:
+      // 49 vs 55 us); small launches (QT = 1) keep the two-CTAs-per-SM kernel below
+      if (QT >= 2)
+        return attn_cross_sm100_res(q, k, v, out, B, H, N, M, d, scale, tl, b_first, maps, accumulate, QT, stream);
+    }
+  }
   switch (d) {
     case 40: return launch_cross<40>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);
     case 64: return launch_cross<64>(q, k, v, out, B, H, N, M, scale, tl, b_first, maps, accumulate, st);

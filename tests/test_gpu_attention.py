@@ -100,6 +100,45 @@ def test_cross_attention_heat_tensor_core(ops, B, N, H, d, T, is_train):
     assert torch.equal(out_nh, out)
 
 
+@pytest.mark.parametrize("qt", [2, 3])
+@pytest.mark.parametrize("B,N,H,d,T", [(4, 1024, 8, 40, [1, 5, 76]), (2, 576, 5, 64, [1, 2, 3, 4]), (2, 4096, 8, 40, [5, 6, 7]),
+                                        (2, 300, 2, 40, [0]), (2, 128, 1, 40, [7, 9]), (2, 640, 3, 64, None)])
+@pytest.mark.parametrize("is_train", [False, True])
+def test_cross_attention_resident_kv_kernel(ops, monkeypatch, B, N, H, d, T, is_train, qt):
+    """The resident-K/V form (attn_cross_sm100_res.cu: K/V of all heads in shared memory, qt query tiles per CTA, two
+    softmax warpgroups on alternate steps), forced through AGENDA_XRES_QT; must agree with the oracle and, bit for bit
+    on the heat maps' inputs, with the per-(tile, head) kernel."""
+    M = 77
+    q, k, v = _qkv(B, N, M, H, d, seed=N * 7 + d + qt, gain=1.5)
+    q, k, v = q.bfloat16(), k.bfloat16(), (v * 0.25).bfloat16()
+    ref, p = O.attention_core(q.float(), k.float(), v.float(), H)
+    b_first = 0 if is_train else B // 2
+    if T is None:  # no heat maps requested
+        monkeypatch.setenv("AGENDA_XRES_QT", str(qt))
+        out = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, None).float().cpu()
+        assert (out - ref).abs().max().item() < TOL_BF16_OUT
+        return
+    ref_maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)[:, T]
+    monkeypatch.setenv("AGENDA_XRES", "0")
+    maps0 = torch.zeros((B - b_first, len(T), N), device="cuda")
+    out0 = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps0, T, b_first, accumulate=False)
+    monkeypatch.setenv("AGENDA_XRES", "1")
+    monkeypatch.setenv("AGENDA_XRES_QT", str(qt))
+    maps = torch.full((B - b_first, len(T), N), 7.0, device="cuda")
+    out = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=False)
+    assert (out.float().cpu() - ref).abs().max().item() < TOL_BF16_OUT
+    assert (maps.cpu() - ref_maps).abs().max().item() < 2e-6
+    assert torch.equal(out, out0)                       # same MMAs, same softmax arithmetic
+    assert (maps - maps0).abs().max().item() < 1e-6     # head sums in a different order
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=True)
+    assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 4e-6
+    # DAAM-style per-head planes through the same kernel
+    heads = torch.zeros((B - b_first, H, len(T), N), device="cuda")
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, heads, T, b_first, accumulate=True, per_head=True)
+    ref_heads = p.reshape(B, H, N, M)[b_first:].permute(0, 1, 3, 2)[:, :, T]
+    assert (heads.cpu() - ref_heads).abs().max().item() < 2e-6
+
+
 def _golden_modules(g, name, tag, ctx_dim):
     from agenda_b200.sd_attention import SDAttention
     heads = int(g[f"{name}_heads"])
