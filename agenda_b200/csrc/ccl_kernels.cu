@@ -523,7 +523,7 @@ template <int kThreads, int kCS>
 __global__ void __launch_bounds__(kThreads)
 ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
                     int32_t* __restrict__ boxes, int max_boxes, int H, int W, int cap, int hints) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ float red_min[32], red_max[32];
   __shared__ int red_nan[32], warp_tot[32];
   __shared__ float x_min[kCS], x_max[kCS];
