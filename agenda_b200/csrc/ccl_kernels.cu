@@ -146,20 +146,15 @@ __device__ __forceinline__ void merge_with_row_above(const Forest& F, uint32_t m
   }
 }
 
-__global__ void __launch_bounds__(1024, 1)
-ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
-                int32_t* __restrict__ boxes, int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes,
-                int only_flagged) {
-  extern __shared__ __align__(128) unsigned char dyn_smem[];
-  __shared__ CclStatic sh;
-
+// One map on one cluster.  `mbar_parity`: phase of the bulk-copy mbarrier (the kernel below may run several maps).
+__device__ __forceinline__ void ccl_cluster_map(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels,
+                                                int32_t* __restrict__ counts, int32_t* __restrict__ boxes,
+                                                int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes,
+                                                CclStatic& sh, unsigned char* dyn_smem, long long map,
+                                                uint32_t mbar_parity) {
   cg::cluster_group cluster = cg::this_cluster();
   const int cs = static_cast<int>(cluster.num_blocks());
   const int rank = static_cast<int>(cluster.block_rank());
-  const long long map = blockIdx.x / cs;
-  // second-chance launch behind ccl_bbox_cta_kernel: only maps it flagged (piece table overflow) are processed;
-  // the flag is read by every CTA of the cluster before any of them can overwrite it (cluster.sync below)
-  if (only_flagged && __ldcg(counts + map) != kCtaOverflowFlag) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = blockDim.x >> 5, nthreads = blockDim.x;
 
   const int r0 = rank * R;
@@ -176,11 +171,6 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
 
   // ---- 1. strip -> shared memory (bulk async copy through the TMA engine when 16-B aligned) ----
   if (use_bulk) {
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.mbar)));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
     if (tid == 0) {
       const uint32_t bytes = static_cast<uint32_t>(n_px) * 4u;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sh.mbar)), "r"(bytes)
@@ -202,7 +192,7 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
           "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
           "selp.u32 %0, 1, 0, p;\n\t}"
           : "=r"(ok)
-          : "r"(smem_u32(&sh.mbar)), "r"(0u)
+          : "r"(smem_u32(&sh.mbar)), "r"(mbar_parity)
           : "memory");
     }
   } else {
@@ -479,6 +469,42 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
       mybox[k * 5 + 2] = x1 - x0 + 1;
       mybox[k * 5 + 3] = y1 - y0 + 1;
     }
+  }
+}
+
+// grid = n_clusters * cluster_size.  Direct use: one cluster per map.  As the second-chance launch behind
+// ccl_bbox_cta_kernel (`only_flagged`): a few persistent clusters walk over all maps and redo only those it flagged
+// (piece table overflow) — a no-op launch of one cluster per map cost 70 us per 2048 maps, 5 % of the whole call.
+// The flag of a map is read by every CTA of its cluster before any of them can overwrite it (first cluster.sync).
+__global__ void __launch_bounds__(1024, 1)
+ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
+                int32_t* __restrict__ boxes, int max_boxes, int H, int W, int R, int use_bulk, int strip_bytes,
+                int only_flagged, int n_maps) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ CclStatic sh;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = static_cast<int>(cluster.num_blocks());
+  const long long stride = gridDim.x / cs;
+  if (only_flagged) {
+    // common case: nothing to redo.  All threads look at this cluster's maps at once (a serial walk costs an L2 round
+    // trip per map); the answer is the same in every CTA of the cluster because only its own rank 0 clears its flags.
+    int any = 0;
+    for (long long map = blockIdx.x / cs + threadIdx.x * stride; map < n_maps; map += blockDim.x * stride)
+      any |= (__ldcg(counts + map) == kCtaOverflowFlag);
+    if (!__syncthreads_or(any)) return;
+  }
+  if (use_bulk) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sh.mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  uint32_t parity = 0;
+  for (long long map = blockIdx.x / cs; map < n_maps; map += stride) {
+    if (only_flagged && __ldcg(counts + map) != kCtaOverflowFlag) continue;
+    ccl_cluster_map(heat, thr, labels, counts, boxes, max_boxes, H, W, R, use_bulk, strip_bytes, sh, dyn_smem, map, parity);
+    if (use_bulk) parity ^= 1u;
   }
 }
 
@@ -954,7 +980,8 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   if (cs > 8) AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(static_cast<long long>(n) * cs));
+  const long long n_clusters = only_flagged ? std::min<long long>(n, 8) : n;  // persistent walkers for the fallback
+  cfg.gridDim = dim3(static_cast<unsigned>(n_clusters * cs));
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
@@ -966,6 +993,6 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   AGENDA_CUDA(cudaLaunchKernelEx(&cfg, ccl_bbox_kernel, heat, thr, labels, counts, boxes, max_boxes, H, W, R, use_bulk,
-                                 strip_bytes, only_flagged));
+                                 strip_bytes, only_flagged, n));
   return AGENDA_OK;
 }

@@ -143,6 +143,18 @@ def test_ccl_edge_cases(ops):
     _check_ccl(ops, heat, 0.5, max_boxes=64)
 
 
+def test_ccl_many_overflowing_maps_interleaved(ops):
+    """Maps whose piece table overflows in the one-CTA kernel are redone by a few persistent clusters, each walking
+    several maps (bulk-copy barrier reused with alternating phase): 40 maps, every third one salt-and-pepper noise or a
+    checkerboard, the rest ordinary heat maps."""
+    rng = np.random.default_rng(17)
+    heat = O.synthetic_heatmaps(40, 512, seed=3)
+    checker = ((np.indices((512, 512)).sum(0) & 1) * 1.0).astype(np.float32)
+    for i in range(0, 40, 3):
+        heat[i] = checker if i % 2 else rng.random((512, 512), dtype=np.float32)
+    _check_ccl(ops, heat, 0.5, max_boxes=32)
+
+
 @pytest.mark.parametrize("H,W", [(61, 45), (1, 1), (1, 300), (300, 1), (33, 32), (200, 1000), (1024, 512), (96, 96)])
 def test_ccl_ragged_shapes(ops, H, W):
     rng = np.random.default_rng(H * 1000 + W)
