@@ -355,6 +355,10 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   // variants 30/32/33/34/38: two query tiles, two softmax warpgroups per tile (half a row per thread; d = 40 / 64)
   // variants 40/42/43/44/48: two query tiles with 64-key tiles (d = 80: separate P columns instead of S/P aliasing)
   // variants 50/52/53/54/58: three query tiles with 80-key tiles (d = 40)
+  // variant 60: the shipped fast path (first-tile maximum + row-sum check + exact second pass)
+  if (variant >= 60)
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 103, stream)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 102, stream);
   if (variant >= 50) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 50, 6, stream);
   if (variant >= 40) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 40, 5, stream);
   if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream);
@@ -362,9 +366,14 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream);
   // defaults measured on B200 (tools/bench_attn.py): d = 40: three query tiles with 64-key tiles, 37.5 % of the
   // exponentials on the FMA pipe; otherwise two query tiles with 128-key tiles (64 at d = 160), 25 %
-  if (variant == 0 && N > 128)
-    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3, stream)
-                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2, stream);
+  // and the fast first pass (first-tile maximum + row-sum check, exact second pass for the CTAs that need it);
+  // AGENDA_V2_FAST=0 keeps the running maximum in a single pass (measurements)
+  if (variant == 0 && N > 128) {
+    static const int fast = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 100; }();
+    // (d = 160 only occurs at N <= 256 in the SD UNets: four key tiles do not amortise the fast pass's epilogue)
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3 + fast, stream)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2 + (d == 160 ? 0 : fast), stream);
+  }
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
     return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \

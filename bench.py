@@ -315,13 +315,13 @@ def run_ours(args):
     ms_all, flops_all, _ = summarize(self_calls, lambda a: 4.0 * a[5] * a[6] * a[7] * a[7] * a[8])
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
-    kname = ("attn_self_sm100_v2_kernel<64,4,2,128,1> (N=9216, B*H=%d)" % (2 * n_img * 5) if sd21 else
-             "attn_self_sm100_v2_kernel<40,3,3,64,1> (N=4096, B*H=%d)" % (2 * n_img * 8))
+    kname = ("attn_self_sm100_v2_kernel<64,4,2,128,1,true> (N=9216, B*H=%d)" % (2 * n_img * 5) if sd21 else
+             "attn_self_sm100_v2_kernel<40,3,3,64,1,true> (N=4096, B*H=%d)" % (2 * n_img * 8))
     roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture
-                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (125.9 MB + 28.5 MB)
-                "traffic": 154.4e6 if (n_img == 8 and not sd21) else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (200.0 MB read + 39.7 MB written)
+                "traffic": 239.7e6 if (n_img == 8 and not sd21) else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "avg_launch_ms": ms_k / max(n_k, 1), "launches_timed": n_k,
                 "share_of_step": (ms_k / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
                 "how": "CUDA events around each launch in an eager replay of 5 denoising steps; useful FLOPs "

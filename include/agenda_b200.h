@@ -64,7 +64,10 @@ int agenda_attn_self_fwd_strided(const void* q, const void* k, const void* v, vo
  * CTA, ping-pong softmax warpgroups, P through TMEM), 1 = one query tile per CTA with P through TMEM (TS-form
  * tcgen05.mma), 2 = one query tile per CTA with P through a 128B-swizzled shared-memory tile (SS-form);
  * 10+e = variant 0 with a share of the exponentials on the FMA pipe (e in {0,2,3,4,8} -> 0/50/37.5/25/12.5 %);
- * 20+e = the same with three query tiles per CTA and 64-key tiles (d = 40 or 64 only). */
+ * 20+e = the same with three query tiles per CTA and 64-key tiles (d = 40 or 64 only); 30+e two warpgroups per query
+ * tile; 40+e d = 80 with 64-key tiles; 50+e three query tiles with 80-key tiles (d = 40).  All of 10..59 track the
+ * exact running maximum in a single pass; 60 = the shipped default of each head dim WITH the fast first pass
+ * (first-tile maximum, row-sum check, exact second pass inside the CTA when the check fails). */
 int agenda_attn_self_fwd_variant(const void* q, const void* k, const void* v, void* out, int B, int H, int N,
                                  int d, float scale, int variant, void* stream);
 

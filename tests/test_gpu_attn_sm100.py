@@ -49,7 +49,7 @@ def test_sm100_self_attention(lib, B, N, H, d, variant):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("variant", [20, 23, 24, 30, 32, 34])
+@pytest.mark.parametrize("variant", [20, 23, 24, 30, 32, 34, 60])
 @pytest.mark.parametrize("B,N,H,d", [s for s in SHAPES if s[3] in (40, 64)] + [(1, 384, 2, 40), (1, 385, 1, 64)])
 def test_sm100_self_attention_three_tiles(lib, B, N, H, d, variant):
     """Three query tiles per CTA / 64-key tiles (20+) and two warpgroups per query tile with half a row per thread
@@ -93,7 +93,7 @@ def test_sm100_self_attention_d80_64key_tiles(lib, B, N, H, d, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34, 53])
+@pytest.mark.parametrize("variant", [0, 1, 2, 10, 12, 13, 18, 20, 24, 30, 34, 53, 60])
 def test_sm100_peaked_softmax_and_rescale(lib, variant):
     """Large logits that keep growing along the key axis force the lazy O-rescale path."""
     B, N, H, d = 1, 1024, 2, 40
@@ -108,7 +108,7 @@ def test_sm100_peaked_softmax_and_rescale(lib, variant):
     assert (out - ref).abs().max().item() < TOL
 
 
-@pytest.mark.parametrize("variant", [0, 10, 14, 20, 30, 53])
+@pytest.mark.parametrize("variant", [0, 10, 14, 20, 30, 53, 60])
 def test_sm100_score_jump_beyond_lazy_max_guard(lib, variant):
     """Scores of a late key tile tower (by far more than 2^64) over everything before it: the lazy running-max path must
     re-run that tile against its own max instead of overflowing."""
@@ -121,6 +121,45 @@ def test_sm100_score_jump_beyond_lazy_max_guard(lib, variant):
     q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
     ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
     out = _run(lib, q, k, v, H, variant)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("d", [40, 64])
+@pytest.mark.parametrize("boost", [8.0, 25.0, 60.0, 200.0])
+def test_sm100_fast_path_reference_maximum_and_second_pass(lib, d, boost):
+    """Variant 60 takes every exponential of a row relative to the maximum of its FIRST key tile and checks the row sum
+    afterwards; CTAs with a row outside [2^-80, 2^100] are redone by the exact-maximum kernel.  One late key (sitting in
+    a column whose exponential is emulated on the FMA pipe, where an unclamped 2^x would wrap silently) is boosted so
+    that rows exceed their reference by a little (no second pass), by 2^30..2^90 (still exact without one), and by far
+    more than 2^127 (second pass).  Only (batch 1, head 0) is affected, so most CTAs must survive the first pass."""
+    B, N, H = 2, 1024, 2
+    g = torch.Generator().manual_seed(int(boost) + d)
+    q = torch.randn(B, N, H * d, generator=g)
+    k = torch.randn(B, N, H * d, generator=g)
+    v = torch.randn(B, N, H * d, generator=g) * 0.25
+    k[1, 302, :d] *= boost
+    k[1, 815, :d] *= boost
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, 60)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
+    assert torch.equal(out, _run(lib, q, k, v, H, 60))  # deterministic, stamp fully overwritten
+
+
+def test_sm100_fast_path_very_negative_later_scores(lib):
+    """Rows whose first key tile towers over everything later: all later exponentials underflow towards 2^-126 and must
+    neither produce garbage (exponent wrap) nor a second pass that changes the result."""
+    B, N, H, d = 1, 1024, 2, 40
+    g = torch.Generator().manual_seed(21)
+    q = torch.randn(B, N, H * d, generator=g)
+    k = torch.randn(B, N, H * d, generator=g)
+    v = torch.randn(B, N, H * d, generator=g) * 0.25
+    k[:, :8] *= 150.0
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ref, _ = O.attention_core(q.float(), k.float(), v.float(), H)
+    out = _run(lib, q, k, v, H, 60)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < TOL
 
