@@ -14,6 +14,7 @@
 // TMEM: S/P[2] (96 columns each) | O[2] (round16(d) columns each).
 // At the end each thread parks its accumulator in its own shared-memory row and emits the selected token columns:
 // consecutive threads = consecutive pixels, so every token plane is written with coalesced 128-byte stores.
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 #include "sm100_common.cuh"
@@ -22,6 +23,8 @@ namespace agenda {
 
 
 namespace sm100 {
+
+namespace cg = cooperative_groups;
 
 constexpr int kXBlockM = 128;
 constexpr int kXThreads = 192;
@@ -75,6 +78,11 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   const int q0 = blockIdx.x * kXBlockM;
   const int b = blockIdx.y;
   const bool want_heat = (maps != nullptr) && (b >= b_first);
+  // Small layers (N <= 256: 16-32 (batch, query tile) pairs on 148 SMs) are launched as clusters of gridDim.z CTAs
+  // along z, each taking H / gridDim.z heads; the head sum of the heat map is then finished through the leader's
+  // shared memory in a fixed order (deterministic, no atomics).  gridDim.z = 1 is the plain one-CTA-per-tile kernel.
+  const int hpg = H / static_cast<int>(gridDim.z);  // heads of this CTA
+  const int h_begin = static_cast<int>(blockIdx.z) * hpg;
 
   if (tid == 4 * 32) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -91,11 +99,14 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
+  constexpr int kAcc = kFew ? kXFewTokens : kXMPad;
+  float acc[kAcc];  // softmax threads: per-row heat accumulator over this CTA's heads
   if (warp == 4) {
     // ============================== TMA producer (warp converged, one elected lane issues) ==============================
     int st = 0;
     uint32_t ph = 0;
-    for (int h = 0; h < H; ++h) {
+    for (int hl = 0; hl < hpg; ++hl) {
+      const int h = h_begin + hl;
       unsigned char* sQ = smem + st * C::kStageBytes;
       unsigned char* sK = sQ + C::kQBytes;
       unsigned char* sV = sK + C::kKVBytes;
@@ -137,7 +148,7 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     };
     int st = 0, st_prev = 0;
     uint32_t ph = 0;
-    for (int h = 0; h < H; ++h) {
+    for (int h = 0; h < hpg; ++h) {  // (local head index: only buffer parities depend on it here)
       const int sb = h & 1;
       mbar_wait(&bars->in_full[st], ph);
       tc_fence_after();
@@ -155,22 +166,20 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       st_prev = st;
       if (++st == C::kStages) { st = 0; ph ^= 1u; }
     }
-    issue_pv(H - 1, st_prev);
+    issue_pv(hpg - 1, st_prev);
   } else {
     // ============================== softmax warpgroup (thread == query row) ==============================
     const int row = tid;
     const int n = q0 + row;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    constexpr int kAcc = kFew ? kXFewTokens : kXMPad;
-    float acc[kAcc];
 #pragma unroll
     for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
 
-    auto drain_o = [&](int g) {  // O of head g: TMEM -> bf16 -> global
+    auto drain_o = [&](int g) {  // O of this CTA's g-th head: TMEM -> bf16 -> global
       const int ob = g & 1;
       mbar_wait(&bars->pv_done[ob], (g >> 1) & 1);
       tc_fence_after();
-      __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + g * D;
+      __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + (h_begin + g) * D;
 #pragma unroll
       for (int c = 0; c < C::kDP / 16; ++c) {
         float o[16];
@@ -188,9 +197,10 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       mbar_arrive(&bars->o_free[ob]);
     };
 
-    for (int h = 0; h < H; ++h) {
-      const int sb = h & 1;
-      mbar_wait(&bars->s_full[sb], (h >> 1) & 1);
+    for (int hl = 0; hl < hpg; ++hl) {
+      const int h = h_begin + hl;
+      const int sb = hl & 1;
+      mbar_wait(&bars->s_full[sb], (hl >> 1) & 1);
       tc_fence_after();
       float sv[96];
       float sel[kFew ? kXFewTokens : 1];
@@ -262,12 +272,12 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&bars->p_full[sb]);
-      if (h > 0) drain_o(h - 1);
+      if (hl > 0) drain_o(hl - 1);
     }
-    drain_o(H - 1);
+    drain_o(hpg - 1);
 
     // ---- heat epilogue: mean over heads, selected token columns, coalesced per token plane ----
-    if (want_heat && !(kFew && tl.per_head)) {
+    if (want_heat && !(kFew && tl.per_head) && gridDim.z == 1) {
       const float inv_h = 1.0f / static_cast<float>(H);
       float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n;
       if (kFew) {
@@ -297,6 +307,34 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     }
     tc_fence_before();
   }
+  if (kFew && gridDim.z > 1 && want_heat && !tl.per_head) {
+    // head groups -> one heat row: partial sums of ranks 1.. go to the leader's (now idle) stage buffers
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(blockIdx.z), hs = static_cast<int>(gridDim.z);
+    float* xacc = reinterpret_cast<float*>(smem);  // [hs - 1][kXFewTokens][128]
+    cluster.sync();  // every CTA of the cluster has finished its TMA loads and MMAs: the leader's stages are free
+    if (warp < 4 && rank > 0) {
+      float* remote = cluster.map_shared_rank(xacc, 0) + (rank - 1) * (kXFewTokens * kXBlockM) + tid;
+#pragma unroll
+      for (int t = 0; t < kXFewTokens; ++t)
+        if (t < tl.n) remote[t * kXBlockM] = acc[t];
+    }
+    cluster.sync();
+    if (warp < 4 && rank == 0 && q0 + tid < N) {
+      const float inv_h = 1.0f / static_cast<float>(H);
+      float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + q0 + tid;
+#pragma unroll
+      for (int t = 0; t < kXFewTokens; ++t) {
+        if (t < tl.n) {
+          float sum = acc[t];
+          for (int r = 1; r < hs; ++r) sum += xacc[((r - 1) * kXFewTokens + t) * kXBlockM + tid];  // fixed order
+          const float val = sum * inv_h;
+          float* ptr = dst + static_cast<long long>(t) * N;
+          *ptr = accumulate ? (*ptr + val) : val;
+        }
+      }
+    }
+  }
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
@@ -319,8 +357,25 @@ static int launch_cross_t(const void* q, const void* k, const void* v, void* out
   auto kern = sm100::attn_cross_sm100_kernel<D, kFew>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid((N + sm100::kXBlockM - 1) / sm100::kXBlockM, B);
-  kern<<<grid, sm100::kXThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), maps, tl, H, N, M,
-                                                 b_first, accumulate, scale * 1.4426950408889634f);
+  // few (batch, query tile) pairs: split the heads over a cluster along z while the grid still fits one wave
+  int hs = 1;
+  if (kFew) {
+    static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev);
+                                cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
+    // (measured on B200, tools/bench_cross.py: N = 256 26.7 -> 13.1 us and N = 64 19.3 -> 9.7 us at 4; 8 is slower)
+    while (hs < 4 && H % (hs * 2) == 0 && static_cast<long long>(grid.x) * grid.y * hs * 2 <= sms) hs *= 2;
+    if (const char* e = getenv("AGENDA_XSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && H % v == 0) hs = v; }
+  }
+  grid.z = hs;
+  const float scale_log2 = scale * 1.4426950408889634f;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(sm100::kXThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = hs;
+  cfg.attrs = attr; cfg.numAttrs = hs > 1 ? 1 : 0;
+  AGENDA_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, static_cast<__nv_bfloat16*>(out), maps, tl, H, N, M, b_first,
+                                 accumulate, scale_log2));
   AGENDA_LAUNCH_CHECK("attn_cross_sm100_kernel");
   return AGENDA_OK;
 }

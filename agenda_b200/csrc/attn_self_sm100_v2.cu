@@ -703,10 +703,15 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
                        int emu, int tiles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tiles >= 100) {  // fast path (first-tile maximum + row-sum check), instantiated for the shipped defaults only
+  if (tiles >= 100) {  // fast first pass, instantiated for the shipped defaults (+ two emulation shares for measurements)
     if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
+    if (d == 40 && tiles == 103 && emu == 2) return launch_v2<40, 2, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
+    if (d == 40 && tiles == 103 && emu == 4) return launch_v2<40, 4, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 64 && tiles == 102 && emu == 4) return launch_v2<64, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
+    if (d == 64 && tiles == 102 && emu == 3) return launch_v2<64, 3, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
+    if (d == 64 && tiles == 102 && emu == 2) return launch_v2<64, 2, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 80 && tiles == 102 && emu == 4) return launch_v2<80, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
+    if (d == 80 && tiles == 105 && emu == 4) return launch_v2<80, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 160 && tiles == 102 && emu == 4) return launch_v2<160, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
     tiles -= 100;
   }

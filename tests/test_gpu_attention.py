@@ -139,6 +139,47 @@ def test_cross_attention_resident_kv_kernel(ops, monkeypatch, B, N, H, d, T, is_
     assert (heads.cpu() - ref_heads).abs().max().item() < 2e-6
 
 
+@pytest.mark.parametrize("split", [2, 4, 8])
+@pytest.mark.parametrize("B,N,H,d,T", [(2, 256, 8, 160, [5, 6, 7]), (2, 64, 8, 160, [1]), (4, 130, 8, 40, [0, 76]),
+                                        (2, 1024, 8, 80, [7, 9, 11]), (2, 200, 4, 64, [1, 2, 3, 4, 5, 6, 7, 8])])
+@pytest.mark.parametrize("is_train", [False, True])
+def test_cross_attention_head_split_clusters(ops, monkeypatch, B, N, H, d, T, is_train, split):
+    """Small layers run as clusters of `split` CTAs along the head axis (H / split heads each) and finish the head sum of
+    the heat map through the leader's shared memory.  Forced through AGENDA_XSPLIT; must agree with the oracle, give
+    the same attention output bit for bit as the unsplit kernel, and support accumulate and per-head planes."""
+    if H % split:
+        pytest.skip("heads not divisible")
+    M = 77
+    q, k, v = _qkv(B, N, M, H, d, seed=N * 3 + d + split, gain=1.5)
+    q, k, v = q.bfloat16(), k.bfloat16(), (v * 0.25).bfloat16()
+    ref, p = O.attention_core(q.float(), k.float(), v.float(), H)
+    b_first = 0 if is_train else B // 2
+    ref_maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)[:, T]
+    monkeypatch.setenv("AGENDA_XRES", "0")
+    monkeypatch.setenv("AGENDA_XSPLIT", "1")
+    maps0 = torch.zeros((B - b_first, len(T), N), device="cuda")
+    out0 = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps0, T, b_first, accumulate=False)
+    monkeypatch.setenv("AGENDA_XSPLIT", str(split))
+    maps = torch.full((B - b_first, len(T), N), 7.0, device="cuda")
+    out = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=False)
+    assert (out.float().cpu() - ref).abs().max().item() < TOL_BF16_OUT
+    assert torch.equal(out, out0)
+    assert (maps.cpu() - ref_maps).abs().max().item() < 2e-6
+    assert (maps - maps0).abs().max().item() < 1e-6     # head sums grouped differently
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps, T, b_first, accumulate=True)
+    assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 4e-6
+    maps2 = torch.full_like(maps, 3.0)                  # deterministic: same grouping, same bits
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps2, T, b_first, accumulate=False)
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, maps2, T, b_first, accumulate=True)
+    assert torch.equal(maps2, maps)
+    heads = torch.zeros((B - b_first, H, len(T), N), device="cuda")
+    ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, heads, T, b_first, accumulate=True, per_head=True)
+    ref_heads = p.reshape(B, H, N, M)[b_first:].permute(0, 1, 3, 2)[:, :, T]
+    assert (heads.cpu() - ref_heads).abs().max().item() < 2e-6
+    out_nh = ops.attn_cross_heat(q.cuda(), k.cuda(), v.cuda(), H, None)
+    assert torch.equal(out_nh, out0)
+
+
 def _golden_modules(g, name, tag, ctx_dim):
     from agenda_b200.sd_attention import SDAttention
     heads = int(g[f"{name}_heads"])
