@@ -21,6 +21,10 @@ import tempfile
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports
+# NCCL_DEBUG) goes to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
