@@ -21,9 +21,12 @@ import tempfile
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports
-# NCCL_DEBUG) goes to stderr instead
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# "NCCL version ..." there when the box exports NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the whole run
+# and the result line goes out through a private duplicate of the original stdout.
+sys.stdout.flush()
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -118,7 +121,7 @@ def run_reference(args):
                              "sample": detail["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def workload_config(args, world):
@@ -375,7 +378,7 @@ def run_ours(args):
             "cpu_baseline": cpu}
     if graph_launch_note:
         line["gpu_launches_note"] = graph_launch_note
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
