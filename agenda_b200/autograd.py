@@ -1,0 +1,104 @@
+"""Training-mode attention (SURVEY.md §8 f N3): the reference's only in-tree caller of hook.py runs the processor with
+`is_train=True` under autograd (finetune_sd_token.py:754-757, 1043-1069): the fg/bg heat-map loss sends gradients
+through the selected-token probabilities into Q and K of every cross-attention layer, and from there through every
+self-attention layer of the UNet into the learned token embeddings.
+
+FIRST CORRECT VERSION.  The forward passes are the sm_100a kernels behind the C ABI (same entry points as inference).
+The backward passes are NOT hand-written kernels yet: they recompute the attention with library kernels —
+`F.scaled_dot_product_attention`'s own backward for self-attention, cuBLAS batched GEMMs + a softmax for the
+77-key cross-attention — in the dtype of the inputs.  A fused tcgen05 backward (dQ/dK/dV with recomputed P, heat
+gradient folded into dP) is the next step for this row; until then the backward runs at library speed.
+
+Gradient formulas (per batch element b and head h; P = softmax(scale * Q K^T), O = P V):
+    dV = P^T dO
+    dP = dO V^T  (+ dMaps[b', t, n] / H  on column token_idx[t], for b >= b_first: maps = mean over heads, hook.py:55)
+    dS = P * (dP - rowsum(P * dP))
+    dQ = scale * dS K,   dK = scale * dS^T Q
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _split_heads(x: torch.Tensor, heads: int) -> torch.Tensor:
+    B, S, C = x.shape
+    return x.view(B, S, heads, C // heads).transpose(1, 2)  # [B, H, S, d]
+
+
+def _merge_heads(x: torch.Tensor) -> torch.Tensor:
+    B, H, S, d = x.shape
+    return x.transpose(1, 2).reshape(B, S, H * d)
+
+
+class SelfAttentionFn(torch.autograd.Function):
+    """out = softmax(scale q k^T) v per head; q/k/v [B,N,H*d] (hook.py:104-115 with encoder_hidden_states None)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, precision: str):
+        out = ops.attn_self(q, k, v, heads, scale=scale, precision=precision)
+        ctx.save_for_backward(q, k, v)
+        ctx.heads, ctx.scale = heads, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v = ctx.saved_tensors
+        with torch.enable_grad():
+            qh, kh, vh = (_split_heads(t.detach(), ctx.heads).requires_grad_(True) for t in (q, k, v))
+            o = F.scaled_dot_product_attention(qh, kh, vh, scale=ctx.scale)
+        dq, dk, dv = torch.autograd.grad(o, (qh, kh, vh), _split_heads(d_out.to(o.dtype).contiguous(), ctx.heads))
+        return _merge_heads(dq), _merge_heads(dk), _merge_heads(dv), None, None, None
+
+
+class CrossAttentionHeatFn(torch.autograd.Function):
+    """(out, maps) = cross-attention + `_unravel_attn` (hook.py:28-56, 104-115): maps [B - b_first, T, N] fp32 is the
+    mean over heads of the probabilities of the key tokens `token_idx` (all M when None)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads: int, scale: float, token_idx: Optional[Sequence[int]], b_first: int):
+        B, N, _ = q.shape
+        M = k.shape[1]
+        T = M if token_idx is None else len(token_idx)
+        maps = torch.empty((B - b_first, T, N), dtype=torch.float32, device=q.device)
+        out = ops.attn_cross_heat(q, k, v, heads, maps, token_idx, b_first, accumulate=False, scale=scale)
+        ctx.save_for_backward(q, k, v)
+        ctx.heads, ctx.scale, ctx.b_first = heads, scale, b_first
+        ctx.token_idx = None if token_idx is None else [int(t) for t in token_idx]
+        return out, maps
+
+    @staticmethod
+    def backward(ctx, d_out, d_maps):
+        q, k, v = ctx.saved_tensors
+        H = ctx.heads
+        qf, kf, vf = (_split_heads(t.float(), H) for t in (q, k, v))           # [B,H,N|M,d]
+        p = torch.softmax(torch.matmul(qf, kf.transpose(-1, -2)) * ctx.scale, dim=-1)   # [B,H,N,M]
+        do = _split_heads(d_out.float().contiguous(), H)
+        dv = torch.matmul(p.transpose(-1, -2), do)
+        dp = torch.matmul(do, vf.transpose(-1, -2))
+        if d_maps is not None:
+            g = (d_maps.float() / H).permute(0, 2, 1).unsqueeze(1)              # [B',1,N,T]
+            g = g.expand(-1, H, -1, -1)
+            if ctx.token_idx is None:
+                dp[ctx.b_first:] += g
+            else:
+                idx = torch.tensor(ctx.token_idx, device=dp.device, dtype=torch.long)
+                dp[ctx.b_first:].index_add_(3, idx, g.contiguous())             # repeated tokens add up
+        ds = p * (dp - (p * dp).sum(dim=-1, keepdim=True))
+        dq = torch.matmul(ds, kf) * ctx.scale
+        dk = torch.matmul(ds.transpose(-1, -2), qf) * ctx.scale
+        return (_merge_heads(dq).to(q.dtype), _merge_heads(dk).to(k.dtype), _merge_heads(dv).to(v.dtype),
+                None, None, None, None)
+
+
+def global_heat_map_autograd(maps, latent_hw: int) -> torch.Tensor:
+    """hook.py:59-81 on tensors that carry a graph: bicubic -> clamp(min=0) per map, stack, mean — torch ops, so the
+    aggregation is differentiable exactly like the reference's."""
+    if len(maps) == 0:
+        raise RuntimeError('No heat maps found.')
+    up = [F.interpolate(m.float(), size=(latent_hw, latent_hw), mode='bicubic').clamp_(min=0) for m in maps]
+    return torch.stack(up, dim=0).mean(dim=0)

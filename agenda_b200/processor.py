@@ -19,8 +19,11 @@ Differences from the reference, by design:
     callers then read a handful, data_generation.py:74-77).  `tokens=None` keeps all of them, as the reference does.
   * `cross_attn_maps` is only populated when `record_maps=True` (the reference's list costs 415 MB/image at 50
     steps); aggregation never needs it.
-  * forward only: `is_train=True` keeps both batch halves (hook.py:48-49) but no autograd graph is built
-    (training is out of scope, SURVEY.md §8 f N3).
+  * training (`is_train=True` under autograd, finetune_sd_token.py:1043-1069; SURVEY.md §8 f N3): when any input of
+    a call requires grad, the call goes through `agenda_b200/autograd.py` — forward in the same CUDA kernels,
+    backward by recomputation with library kernels (first correct version) — every cross-attention map [B',T,h,w] is
+    appended to `cross_attn_maps` with its graph like the reference's list, and `compute_global_heat_map()` aggregates
+    them with differentiable torch ops (hook.py:59-81).
   * `aggregate="daam"` switches the aggregation to the `daam` package's (what data_generation.py:57-77 actually
     calls; un-vendored, parity unpinned — SURVEY.md §8 a5): per hooked layer one [B',H,T,h,w] buffer sums the per-head
     probabilities over the denoising steps at native resolution (the attention epilogue adds into it), layers whose
@@ -35,6 +38,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
+from . import autograd as _ag
 from . import ops
 
 
@@ -96,6 +100,11 @@ class UNetCrossAttentionHooker:
                 ops.heat_upsample_accum_heads(buf, acc)
                 pairs += buf.shape[1]
             return ops.heat_finalize(acc, pairs)    # mean over every (layer, head) map
+        if any(m.requires_grad for m in self.cross_attn_maps):   # training: differentiable aggregation
+            if self._count != len(self.cross_attn_maps):
+                raise RuntimeError("heat maps with and without an autograd graph were mixed; call clear() between "
+                                   "a no-grad pass and a training pass")
+            return _ag.global_heat_map_autograd(self.cross_attn_maps, self.latent_hw)
         if self._count == 0 or self._acc is None:
             raise RuntimeError('No heat maps found.')
         return ops.heat_finalize(self._acc, self._count)
@@ -158,16 +167,48 @@ class UNetCrossAttentionHooker:
             self._acc = torch.zeros((b_kept, n_tok, L, L), dtype=torch.float32, device=device)
         return self._acc
 
+    @staticmethod
+    def _wants_grad(attn, hidden_states, encoder_hidden_states) -> bool:
+        ts = [hidden_states, encoder_hidden_states]
+        for m in (attn.to_q, attn.to_k, attn.to_v):
+            ts.extend(m.parameters())
+        return any(t is not None and t.requires_grad for t in ts)
+
+    def _call_with_autograd(self, attn, hidden_states, encoder_hidden_states):
+        """hook.py:83-122 with a graph (finetune_sd_token.py:1043-1069): projections through their own modules, the
+        attention cores through autograd.Functions whose forward is the CUDA kernel."""
+        if self.aggregate != "hook":
+            raise NotImplementedError("agenda_b200: autograd is implemented for aggregate='hook' (the processor the "
+                                      "reference trains with), not for the DAAM aggregation")
+        batch_size, sequence_length, _ = hidden_states.shape
+        query = attn.to_q(hidden_states)
+        is_cross_attn = encoder_hidden_states is not None
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif attn.norm_cross is not None:
+            encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        heads, scale = attn.heads, float(attn.scale)
+        if is_cross_attn:
+            b_first = 0 if self.is_train else batch_size // 2  # hook.py:48-49
+            h = w = int(math.sqrt(sequence_length))
+            hidden_states, maps = _ag.CrossAttentionHeatFn.apply(query, key, value, heads, scale, self.tokens, b_first)
+            self.cross_attn_maps.append(maps.view(maps.shape[0], maps.shape[1], h, w))  # hook.py:110-112
+            self._count += 1
+        else:
+            hidden_states = _ag.SelfAttentionFn.apply(query, key, value, heads, scale, self.precision)
+        hidden_states = attn.to_out[0](hidden_states)
+        return attn.to_out[1](hidden_states)
+
     # ---- hook.py:83-122 ------------------------------------------------------------------------------------
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
         batch_size, sequence_length, _ = hidden_states.shape
         attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
         if attention_mask is not None:
             raise NotImplementedError("agenda_b200: attention masks are not supported (the SD UNet passes none)")
-        if torch.is_grad_enabled() and hidden_states.requires_grad:
-            # the kernels are forward only: silently returning tensors without a grad_fn would train on zero gradients
-            raise NotImplementedError("agenda_b200: the processor is forward only (no autograd through the CUDA "
-                                      "kernels); run it under torch.no_grad() — training is out of scope")
+        if torch.is_grad_enabled() and self._wants_grad(attn, hidden_states, encoder_hidden_states):
+            return self._call_with_autograd(attn, hidden_states, encoder_hidden_states)
         if (encoder_hidden_states is None and self.fuse_qkv and self.precision == "bf16"
                 and hidden_states.dtype == torch.bfloat16 and hidden_states.is_cuda):
             w = self._fused_qkv_weight(attn)
