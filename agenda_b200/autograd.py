@@ -4,10 +4,10 @@ through the selected-token probabilities into Q and K of every cross-attention l
 self-attention layer of the UNet into the learned token embeddings.
 
 FIRST CORRECT VERSION.  The forward passes are the sm_100a kernels behind the C ABI (same entry points as inference).
-The backward passes are NOT hand-written kernels yet: they recompute the attention with library kernels —
-`F.scaled_dot_product_attention`'s own backward for self-attention, cuBLAS batched GEMMs + a softmax for the
-77-key cross-attention — in the dtype of the inputs.  A fused tcgen05 backward (dQ/dK/dV with recomputed P, heat
-gradient folded into dP) is the next step for this row; until then the backward runs at library speed.
+Cross-attention backward (where the heat-map gradient enters) is `agenda_attn_cross_bwd`, an exact fp32 CUDA-core
+kernel (csrc/attn_cross_bwd.cu).  Self-attention backward is NOT a hand-written kernel yet: it recomputes through
+`F.scaled_dot_product_attention` and uses that library's backward, in the dtype of the inputs.  A fused tcgen05
+backward (dQ/dK/dV with recomputed P) is the next step for this row.
 
 Gradient formulas (per batch element b and head h; P = softmax(scale * Q K^T), O = P V):
     dV = P^T dO
@@ -17,6 +17,7 @@ Gradient formulas (per batch element b and head h; P = softmax(scale * Q K^T), O
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -73,6 +74,16 @@ class CrossAttentionHeatFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_maps):
+        q, k, v = ctx.saved_tensors
+        if os.environ.get("AGENDA_TORCH_CROSS_BWD", "0") != "1":
+            dq, dk, dv = ops.attn_cross_bwd(q, k, v, d_out.to(q.dtype), d_maps, ctx.heads, ctx.token_idx, ctx.b_first,
+                                            scale=ctx.scale)
+            return dq, dk, dv, None, None, None, None
+        return CrossAttentionHeatFn._backward_torch(ctx, d_out, d_maps)
+
+    @staticmethod
+    def _backward_torch(ctx, d_out, d_maps):
+        """The same gradients with cuBLAS batched GEMMs + softmax (kept as a cross-check: AGENDA_TORCH_CROSS_BWD=1)."""
         q, k, v = ctx.saved_tensors
         H = ctx.heads
         qf, kf, vf = (_split_heads(t.float(), H) for t in (q, k, v))           # [B,H,N|M,d]

@@ -119,6 +119,34 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     return out
 
 
+def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
+                   d_maps: Optional[torch.Tensor], heads: int, token_idx: Optional[Sequence[int]] = None,
+                   b_first: int = 0, scale: Optional[float] = None):
+    """Backward of attn_cross_heat (training mode): returns (dq, dk, dv) in the dtypes of q / k / v.  d_maps is the
+    gradient of the head-mean maps, fp32 [B-b_first, T, N] (or any trailing shape of N elements), or None."""
+    q = _dev(q, "q")
+    k, v, d_out = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype), _dev(d_out, "d_out", q.dtype)
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    dq = torch.empty_like(q)
+    dk = torch.zeros((B, M, C), dtype=torch.float32, device=q.device)
+    dv = torch.zeros_like(dk)
+    if d_maps is not None:
+        d_maps = _dev(d_maps, "d_maps", torch.float32)
+        T = M if token_idx is None else len(token_idx)
+        if d_maps.numel() != (B - b_first) * T * N:
+            raise ValueError(f"d_maps must hold {(B - b_first)}x{T}x{N} elements, got {tuple(d_maps.shape)}")
+        idx = None if token_idx is None else (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
+        mp = d_maps.data_ptr()
+    else:
+        T, idx, mp = 0, None, None
+    _lib.call("agenda_attn_cross_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), mp, dq.data_ptr(),
+              dk.data_ptr(), dv.data_ptr(), _dtype_code(q), B, heads, N, M, d, scale, idx, T, int(b_first), _stream())
+    return dq, dk.to(k.dtype), dv.to(v.dtype)
+
+
 # ------------------------------------------------------------------ heat maps (hook.py:59-81) -----------------
 
 def heat_upsample_accum(maps: torch.Tensor, acc: torch.Tensor) -> None:

@@ -101,6 +101,16 @@ int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v
                                      const int32_t* token_idx, int T, int b_first,
                                      float* maps, int accumulate, void* stream);
 
+/* Backward of agenda_attn_cross_fwd_heat (training mode, SURVEY.md §8 f N3: autograd of hook.py:104-115 and of
+ * _unravel_attn hook.py:28-56 as exercised by finetune_sd_token.py:1043-1069).  Given d_out [B,N,H*d] (same dtype as
+ * q/k/v) and d_maps fp32 [B-b_first, T, N] (gradient of the head-mean maps; NULL when the maps were not used), writes
+ * dq [B,N,H*d] (dtype of q) and ADDS dK / dV into the fp32 accumulators dk, dv [B,M,H*d], which the caller zero-fills
+ * (many CTAs per (batch, head) add into them with atomics: the last bits of dK / dV are not reproducible run to run).
+ * P is recomputed in fp32; M <= 96.  token_idx / T / b_first as in the forward call. */
+int agenda_attn_cross_bwd(const void* q, const void* k, const void* v, const void* d_out, const float* d_maps,
+                          void* dq, float* dk, float* dv, int dtype, int B, int H, int N, int M, int d, float scale,
+                          const int32_t* token_idx, int T, int b_first, void* stream);
+
 /* Test hook: same contract, forcing the exact fp32 CUDA-core kernel (bf16 inputs otherwise take the tcgen05
  * tensor-core kernel; fp32 inputs always take the fp32 kernel). */
 int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, void* out, int dtype,

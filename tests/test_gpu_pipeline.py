@@ -140,6 +140,45 @@ def test_processor_context_kv_cache_invalidation(cuda_ok):
         assert len(cached._ctx_kv) == 0
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,N,H,d,M,T,b_first", [(2, 256, 8, 40, 77, [2, 5], 0), (2, 64, 8, 160, 77, None, 1),
+                                                 (3, 100, 2, 64, 77, [7, 7, 0], 1), (1, 33, 1, 80, 50, [49], 0),
+                                                 (2, 1024, 8, 80, 77, None, 0), (2, 40, 3, 24, 96, [95, 1], 0)])
+def test_cross_attention_backward_kernel(cuda_ok, monkeypatch, dtype, B, N, H, d, M, T, b_first):
+    """agenda_attn_cross_bwd (csrc/attn_cross_bwd.cu) against fp32 autograd of the oracle's attention + head-mean maps on
+    the same (dtype-rounded) inputs: dq, dk, dv with gradients arriving through BOTH the output and the maps, ragged
+    N, repeated tokens, all tokens, a dropped unconditional half.  Tolerance relative to the largest entry: 1e-5 for
+    fp32 tensors (fp32 math, different summation order), 1e-2 for bf16 tensors (gradients rounded to bf16)."""
+    from agenda_b200.autograd import CrossAttentionHeatFn
+    from oracle import hook_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(N + d)
+    C = H * d
+    q0 = torch.randn(B, N, C, device="cuda", generator=g).to(dtype)
+    k0 = torch.randn(B, M, C, device="cuda", generator=g).to(dtype)
+    v0 = torch.randn(B, M, C, device="cuda", generator=g).to(dtype)
+    go = torch.randn(B, N, C, device="cuda", generator=g).to(dtype)
+    nt = M if T is None else len(T)
+    gm = torch.randn(B - b_first, nt, N, device="cuda", generator=g)
+    q, k, v = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+    out, maps = CrossAttentionHeatFn.apply(q, k, v, H, d ** -0.5, T, b_first)
+    torch.autograd.backward((out, maps), (go, gm))
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q0, k0, v0))
+    ref, p = O.attention_core(qr, kr, vr, H)
+    ref_maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)[:, list(range(M)) if T is None else T]
+    torch.autograd.backward((ref, ref_maps), (go.float(), gm))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a, b_, name in ((q.grad, qr.grad, "dq"), (k.grad, kr.grad, "dk"), (v.grad, vr.grad, "dv")):
+        assert a.dtype == dtype
+        assert (a.float() - b_).abs().max().item() < tol * b_.abs().max().item(), name
+    # the library-kernel formulation of the same backward agrees too
+    monkeypatch.setenv("AGENDA_TORCH_CROSS_BWD", "1")
+    q2, k2, v2 = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+    out2, maps2 = CrossAttentionHeatFn.apply(q2, k2, v2, H, d ** -0.5, T, b_first)
+    torch.autograd.backward((out2, maps2), (go, gm))
+    for a, b_ in ((q2.grad, qr.grad), (k2.grad, kr.grad), (v2.grad, vr.grad)):
+        assert (a.float() - b_).abs().max().item() < tol * b_.abs().max().item()
+
+
 def _train_modules(C, heads, ctx_dim, seed):
     from agenda_b200.sd_attention import SDAttention
     torch.manual_seed(seed)
