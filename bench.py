@@ -327,8 +327,8 @@ def run_ours(args):
     roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture
-                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (200.0 MB read + 39.7 MB written)
-                "traffic": 239.7e6 if (n_img == 8 and not sd21) else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
+                # summarised in profiles/r01_self_attn_d40_full_key_metrics.txt (194.6 MB read + 39.6 MB written)
+                "traffic": 234.2e6 if (n_img == 8 and not sd21) else None, "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "avg_launch_ms": ms_k / max(n_k, 1), "launches_timed": n_k,
                 "share_of_step": (ms_k / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
                 "how": "CUDA events around each launch in an eager replay of 5 denoising steps; useful FLOPs "
