@@ -20,7 +20,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
 # full-set captures of the top kernels (eager replay so every launch is visible)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_self_sm100_v2 -s 0 -c 1 \
   -o gpurun_out/self_attn_full -f python tools/run_steps.py 1 8 > gpurun_out/ncu_self.log 2>&1; echo "ncu self rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_cross_sm100 -s 2 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_cross_sm100_res -s 0 -c 1 \
   -o gpurun_out/cross_attn_full -f python tools/run_steps.py 1 8 > gpurun_out/ncu_cross.log 2>&1; echo "ncu cross rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ccl_bbox_cta -s 1 -c 1 \
   -o gpurun_out/ccl_full -f python tools/bench_ccl.py > gpurun_out/ncu_ccl.log 2>&1; echo "ncu ccl rc=$?"
