@@ -90,6 +90,12 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     maps is [B-b_first, H, T, N] and no head mean is taken.  Returns out [B,N,H*d]."""
     q = _dev(q, "q")
     k, v = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype)
+    if q.dtype == torch.float16:
+        # fp16 pipelines (torch_dtype=torch.float16): the tensor-core kernels take bf16 (same 16-bit storage, fp32
+        # softmax and accumulation inside); the attention output goes back to fp16, the heat maps are fp32 anyway
+        out = attn_cross_heat(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), heads, maps, token_idx,
+                              b_first, accumulate, scale, force_f32_kernel, per_head)
+        return out.to(torch.float16)
     B, N, C = q.shape
     M = k.shape[1]
     d = C // heads

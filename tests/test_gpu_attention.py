@@ -240,3 +240,31 @@ def test_processor_token_subset_and_fused_accumulate(ops, golden_dir):
     heat = proc.compute_global_heat_map().cpu().numpy()
     assert heat.shape == (1, 3, 16, 16)
     assert np.abs(heat - g["global"][:, toks]).max() < 1e-5
+
+
+def test_processor_fp16_pipeline(ops):
+    """Pipelines loaded with torch_dtype=torch.float16: modules and activations are fp16.  The processor runs the bf16
+    tensor-core kernels on them and hands fp16 back; outputs and heat maps stay within the bf16 tolerances of an fp32
+    evaluation of the same fp16-rounded weights and inputs (oracle processor_call, hook.py:83-122)."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    torch.manual_seed(4)
+    C, H, hw = 320, 8, 16
+    a_self = SDAttention(C, None, H, C // H).cuda().half()
+    a_cross = SDAttention(C, 768, H, C // H).cuda().half()
+    x = torch.randn(2, hw * hw, C, device="cuda").half()
+    ctx = torch.randn(2, 77, 768, device="cuda").half()
+    proc = UNetCrossAttentionHooker(is_train=False, latent_hw=hw, tokens=[3, 9])
+    with torch.no_grad():
+        y = proc(a_self, x)
+        z = proc(a_cross, x, ctx)
+    assert y.dtype == torch.float16 and z.dtype == torch.float16
+    w = lambda m: m.weight.detach().float().cpu()
+    yr, _ = O.processor_call(x.float().cpu(), None, w(a_self.to_q), w(a_self.to_k), w(a_self.to_v), w(a_self.to_out[0]),
+                             a_self.to_out[0].bias.detach().float().cpu(), H, False)
+    zr, mr = O.processor_call(x.float().cpu(), ctx.float().cpu(), w(a_cross.to_q), w(a_cross.to_k), w(a_cross.to_v),
+                              w(a_cross.to_out[0]), a_cross.to_out[0].bias.detach().float().cpu(), H, False)
+    assert (y.float().cpu() - yr).abs().max().item() < TOL_BF16_OUT * 3
+    assert (z.float().cpu() - zr).abs().max().item() < TOL_BF16_OUT * 3
+    heat = proc.compute_global_heat_map().cpu()
+    assert (heat - mr[:, [3, 9]]).abs().max().item() < 2e-3   # q/k rounded fp16 -> bf16 before the scores
