@@ -223,22 +223,32 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         for (int i = 0; i < kXMPad; ++i)
           if (i >= M) sv[i] = -INFINITY;
       }
-      float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+      // packed f32x2 forms and the 3-input max: same roundings and the same summation order as the scalar code (even /
+      // odd partial sums), half the issue slots — this stretch, not HBM, bounds the kernel at N = 4096
+      static_assert((kXMPad - 6) % 4 == 2, "max reduction below assumes 80 columns");
+      float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
 #pragma unroll
-      for (int i = 4; i < kXMPad; i += 4) {
-        mx0 = fmaxf(mx0, sv[i]); mx1 = fmaxf(mx1, sv[i + 1]); mx2 = fmaxf(mx2, sv[i + 2]); mx3 = fmaxf(mx3, sv[i + 3]);
+      for (int i = 6; i + 4 <= kXMPad; i += 4) {
+        mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
       }
-      const float m = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      float sum0 = 0.f, sum1 = 0.f;
+      mx0 = fmax3(mx0, sv[kXMPad - 2], sv[kXMPad - 1]);
+      const float m = fmaxf(mx0, mx1) * scale_log2;
+      const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2), negm2 = pack_f32x2(-m, -m);
+      uint64_t sum2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kXMPad; i += 2) {
-        sv[i] = ex2(fmaf(sv[i], scale_log2, -m));
-        sv[i + 1] = ex2(fmaf(sv[i + 1], scale_log2, -m));
-        sum0 += sv[i]; sum1 += sv[i + 1];
+        float a, b2;
+        unpack_f32x2(ffma2(pack_f32x2(sv[i], sv[i + 1]), scale2, negm2), a, b2);
+        sv[i] = ex2(a); sv[i + 1] = ex2(b2);
+        sum2 = fadd2(sum2, pack_f32x2(sv[i], sv[i + 1]));
       }
+      float sum0, sum1;
+      unpack_f32x2(sum2, sum0, sum1);
       const float inv_l = 1.0f / (sum0 + sum1);
+      const uint64_t inv2 = pack_f32x2(inv_l, inv_l);
 #pragma unroll
-      for (int i = 0; i < kXMPad; ++i) sv[i] *= inv_l;  // normalised probabilities: PV needs no later division
+      for (int i = 0; i < kXMPad; i += 2)  // normalised probabilities: PV needs no later division
+        unpack_f32x2(fmul2(pack_f32x2(sv[i], sv[i + 1]), inv2), sv[i], sv[i + 1]);
       if (want_heat) {
         if (kFew) {
 #pragma unroll

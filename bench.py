@@ -363,6 +363,22 @@ def run_ours(args):
                                       "tiled, labels + boxes written; algorithmic bytes = H*W*(4 read + 4 written) per map; "
                                       "traffic = ncu dram bytes per map (the two-pass one-CTA kernel re-reads the map)"}}
 
+    # cross-attention + heat epilogue (K2, HBM-bound): the same eager replay, in-pipeline cache state (Q was just
+    # written by the to_q GEMM).  args: q,k,v,out,dtype,B,H,N,M,d,scale,token_idx,T,b_first,maps,accumulate,stream
+    def cross_bytes(a):
+        B_, H_, N_, M_, d_, T_, bf_ = a[5], a[6], a[7], a[8], a[9], a[12], a[13]
+        return 2.0 * B_ * N_ * H_ * d_ * 2 + 2.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
+    cross_calls = sink["agenda_attn_cross_fwd_heat"]
+    ms_x, bytes_x, n_x = summarize(cross_calls, lambda a: cross_bytes(a) if a[7] == big_n else None)
+    ms_x_all, _, _ = summarize(cross_calls, cross_bytes)
+    if n_x:
+        gbs = bytes_x / (ms_x / 1000.0) / 1e9
+        extra["cross_attention_heat"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
+                                         "frac": gbs / hbm_gbs, "avg_launch_ms": ms_x / n_x, "launches_timed": n_x,
+                                         "ms_per_denoise_step_all_layers": ms_x_all / 5.0,
+                                         "note": "N=%d layers; algorithmic bytes = Q in + O out + K,V in + selected-"
+                                                 "token heat planes out" % big_n}
+
     cpu = None
     if not args.no_cpu_baseline:
         v, d = cpu_reference_sample(6)
