@@ -170,3 +170,26 @@ def test_trace_shim_plumbing_cpu():
     assert torch.equal(g.compute_word_heat_map("aerial cars").heatmap, (g.heat_maps[1] + g.heat_maps[2]) / 2)
     with pytest.raises(ValueError):
         g.token_indices("truck")
+
+
+def test_processor_autograd_routing_is_decided_on_every_input():
+    """Training mode (finetune_sd_token.py:754-757): with a frozen UNet only the prompt embedding requires grad.  The
+    processor must route a call through its autograd path when ANY of hidden_states / encoder_hidden_states / to_q,
+    to_k, to_v parameters requires grad (host logic only; the GPU tests check the gradients)."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    attn = SDAttention(64, 32, 2, 32)
+    x, c = torch.zeros(1, 4, 64), torch.zeros(1, 3, 32)
+    wants = UNetCrossAttentionHooker._wants_grad
+    assert wants(attn, x, c)                                    # fresh nn.Linear weights require grad
+    for p in attn.parameters():
+        p.requires_grad_(False)
+    assert not wants(attn, x, c) and not wants(attn, x, None)
+    assert wants(attn, x, c.clone().requires_grad_(True))       # learned-token embedding
+    assert wants(attn, x.clone().requires_grad_(True), None)    # activations downstream of a cross-attention layer
+    attn.to_out[0].weight.requires_grad_(True)                  # to_out runs outside the attention core
+    assert not wants(attn, x, c)
+    # a CPU tensor never reaches a kernel silently, with or without a graph
+    proc = UNetCrossAttentionHooker(is_train=True)
+    with pytest.raises(RuntimeError):
+        proc(attn, x.clone().requires_grad_(True))
