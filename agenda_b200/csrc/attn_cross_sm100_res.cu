@@ -227,9 +227,38 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
       mbar_arrive(&bars->o_free[ob]);
     };
 
+    // warpgroup 0: mean over heads of query tile `qt` from the two parked halves -> global (after warpgroup 1's signal)
+    auto combine_heat = [&](int qt, int n_row, bool rmw, const float* old_heat) {
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + (qt & 1)) : "memory");
+      if (n_row < N) {
+        const float inv_h = 1.0f / static_cast<float>(H);
+        float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n_row;
+#pragma unroll
+        for (int t = 0; t < kRFew; ++t) {
+          if (t < tl.n) {
+            const float val = (bars->xacc[qt & 1][0][t][row] + bars->xacc[qt & 1][1][t][row]) * inv_h;
+            dst[static_cast<long long>(t) * N] = rmw ? (old_heat[t] + val) : val;
+          }
+        }
+      }
+    };
     int prev_s = -1;  // this warpgroup's previous step, whose O is drained after the next P has been handed over
     for (int qt = 0; qt < n_qt; ++qt) {
       const int n = (tile0 + qt) * 128 + row;
+      // The head sums of a query tile are combined ONE TILE LATE (by warpgroup 0, at the end of the next tile): by
+      // then warpgroup 1's half has long arrived, so neither warpgroup ever waits for the other at a tile boundary
+      // (event trace: the boundary cost warpgroup 0 ~4500 cycles per tile, 10 of the kernel's 43 us).  In accumulate
+      // mode the old heat values of the tile to be combined are fetched here, a whole tile ahead of the add.
+      float old_heat[kRFew];
+      const int n_prev = n - 128;  // row of this thread in the previous query tile
+      const bool combine_prev = want_heat && !tl.per_head && wg == 0 && qt > 0;
+      const bool rmw = combine_prev && accumulate && n_prev < N;
+      if (rmw) {
+        const float* src = maps + static_cast<long long>(b - b_first) * tl.n * N + n_prev;
+#pragma unroll
+        for (int t = 0; t < kRFew; ++t)
+          if (t < tl.n) old_heat[t] = __ldcg(src + static_cast<long long>(t) * N);
+      }
       for (int h = 0; h < H; ++h) {
         const int s = qt * H + h;
         if ((s & 1) != wg) continue;
@@ -324,28 +353,36 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         XR_TRACE((warp & 3) == 0 ? wg : 9, s, 2);
         prev_s = s;
       }
-      // ---- heat of the finished query tile: the two warpgroups' head sums meet in shared memory; warpgroup 0 takes
-      //      the mean over heads and writes one coalesced store per token plane (fixed summation order) ----
+      // ---- heat: both warpgroups park their head sums of this tile; warpgroup 1 signals and moves on; warpgroup 0
+      //      combines the PREVIOUS tile (fixed summation order, one coalesced store per token plane).  Barrier ids and
+      //      xacc buffers alternate per query tile: the warpgroups cannot drift a whole tile apart (the MMA warp issues
+      //      their steps in order and blocks on the slower one's s_free within two steps). ----
       if (want_heat && !tl.per_head) {
 #pragma unroll
         for (int t = 0; t < kRFew; ++t) {
           if (t < tl.n) bars->xacc[qt & 1][wg][t][row] = acc[t];
           acc[t] = 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (wg == 0 && n < N) {
-          const float inv_h = 1.0f / static_cast<float>(H);
-          float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + n;
-#pragma unroll
-          for (int t = 0; t < kRFew; ++t) {
-            if (t < tl.n) {
-              const float val = (bars->xacc[qt & 1][0][t][row] + bars->xacc[qt & 1][1][t][row]) * inv_h;
-              float* ptr = dst + static_cast<long long>(t) * N;
-              *ptr = accumulate ? (*ptr + val) : val;
-            }
-          }
+        if (wg == 1) {
+          __threadfence_block();
+          asm volatile("bar.arrive %0, 256;" ::"r"(1 + (qt & 1)) : "memory");
+        } else if (qt > 0) {
+          combine_heat(qt - 1, n_prev, rmw, old_heat);
         }
       }
+    }
+    if (want_heat && !tl.per_head && wg == 0) {  // the last tile: this one does wait for warpgroup 1
+      const int qt = n_qt - 1;
+      const int n_last = (tile0 + qt) * 128 + row;
+      float old_heat[kRFew];
+      const bool rmw = accumulate && n_last < N;
+      if (rmw) {
+        const float* src = maps + static_cast<long long>(b - b_first) * tl.n * N + n_last;
+#pragma unroll
+        for (int t = 0; t < kRFew; ++t)
+          if (t < tl.n) old_heat[t] = __ldcg(src + static_cast<long long>(t) * N);
+      }
+      combine_heat(qt, n_last, rmw, old_heat);
     }
     if (prev_s >= 0) drain_o(prev_s);
     tc_fence_before();

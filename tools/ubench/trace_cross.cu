@@ -29,6 +29,27 @@ int main() {
     if (rc) { printf("error %d %s\n", rc, agenda_last_error()); return 1; }
   }
   cudaDeviceSynchronize();
+  {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int it = 0; it < 20; ++it)
+      agenda_attn_cross_fwd_heat(q, k, v, o, 1, B, H, N, M, d, 1.f / sqrtf(float(d)), toks, T, B / 2, maps, 1, nullptr);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("B=%d N=%d H=%d d=%d T=%d: %.1f us per launch (traced build, same buffers every launch)\n", B, N, H, d, T, ms * 50.f);
+    for (int it = 0; it < 20; ++it)
+      agenda_attn_cross_fwd_heat(q, k, v, o, 1, B, H, N, M, d, 1.f / sqrtf(float(d)), toks, T, B, maps, 1, nullptr);
+    cudaEventRecord(e0);
+    for (int it = 0; it < 20; ++it)
+      agenda_attn_cross_fwd_heat(q, k, v, o, 1, B, H, N, M, d, 1.f / sqrtf(float(d)), toks, 0, B / 2, nullptr, 1, nullptr);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("  without the heat epilogue: %.1f us per launch\n", ms * 50.f);
+    // the traced CTA is (tile 0, batch 0): b_first = 0 so that it runs the heat epilogue
+    float* maps_all; cudaMalloc(&maps_all, size_t(B) * T * N * 4); cudaMemset(maps_all, 0, size_t(B) * T * N * 4);
+    agenda_attn_cross_fwd_heat(q, k, v, o, 1, B, H, N, M, d, 1.f / sqrtf(float(d)), toks, T, 0, maps_all, 1, nullptr);
+    cudaDeviceSynchronize();
+  }
   std::vector<long long> tr(640);
   if (agenda_xres_trace_read(tr.data(), 640) < 0) { printf("trace read failed\n"); return 1; }
   auto at = [&](int a, int s, int e) { return tr[(a * 40 + s) * 4 + e]; };
