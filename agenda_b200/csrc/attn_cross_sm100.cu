@@ -258,7 +258,8 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
               if (tl.per_head) {  // DAAM-style: one plane per (batch, head, token), no head mean
                 if (n < N) {
                   float* ptr = maps + ((static_cast<long long>(b - b_first) * H + h) * tl.n + t) * N + n;
-                  *ptr = accumulate ? (*ptr + pt) : pt;
+                  if (accumulate) atomicAdd(ptr, pt);  // result-less RED: one thread per element and launch, no load in the softmax warps
+                  else *ptr = pt;
                 }
               } else {
                 acc[t] += pt;
@@ -297,7 +298,8 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             if (t < tl.n) {
               const float val = acc[t] * inv_h;
               float* ptr = dst + static_cast<long long>(t) * N;
-              *ptr = accumulate ? (*ptr + val) : val;
+              if (accumulate) atomicAdd(ptr, val);  // (RED: same value as load + add + store, no load)
+          else *ptr = val;
             }
           }
         }
@@ -310,7 +312,8 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           for (int t = 0; t < tl.n; ++t) {
             const float val = srow[tl.idx[t]] * inv_h;
             float* ptr = dst + static_cast<long long>(t) * N;
-            *ptr = accumulate ? (*ptr + val) : val;
+            if (accumulate) atomicAdd(ptr, val);  // (RED: same value as load + add + store, no load)
+          else *ptr = val;
           }
         }
       }
@@ -340,7 +343,8 @@ attn_cross_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           for (int r = 1; r < hs; ++r) sum += xacc[((r - 1) * kXFewTokens + t) * kXBlockM + tid];  // fixed order
           const float val = sum * inv_h;
           float* ptr = dst + static_cast<long long>(t) * N;
-          *ptr = accumulate ? (*ptr + val) : val;
+          if (accumulate) atomicAdd(ptr, val);  // (RED: same value as load + add + store, no load)
+          else *ptr = val;
         }
       }
     }

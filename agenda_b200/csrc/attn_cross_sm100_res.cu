@@ -228,7 +228,11 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     };
 
     // warpgroup 0: mean over heads of query tile `qt` from the two parked halves -> global (after warpgroup 1's signal)
-    auto combine_heat = [&](int qt, int n_row, bool rmw, const float* old_heat) {
+    // Accumulate mode adds with a result-less atomic (RED): every heat element is touched by exactly one thread per
+    // launch, so the value is the same as load + add + store, but no global LOAD sits in the softmax warps — a load's
+    // scoreboard is shared with the tcgen05.ld of the next score tile, and waiting for that tile then also waited out
+    // a full global-memory round trip (event trace: ~2800 cycles at every query-tile boundary).
+    auto combine_heat = [&](int qt, int n_row) {
       asm volatile("bar.sync %0, 256;" ::"r"(1 + (qt & 1)) : "memory");
       if (n_row < N) {
         const float inv_h = 1.0f / static_cast<float>(H);
@@ -237,7 +241,8 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
         for (int t = 0; t < kRFew; ++t) {
           if (t < tl.n) {
             const float val = (bars->xacc[qt & 1][0][t][row] + bars->xacc[qt & 1][1][t][row]) * inv_h;
-            dst[static_cast<long long>(t) * N] = rmw ? (old_heat[t] + val) : val;
+            if (accumulate) atomicAdd(dst + static_cast<long long>(t) * N, val);
+            else dst[static_cast<long long>(t) * N] = val;
           }
         }
       }
@@ -246,19 +251,8 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
     for (int qt = 0; qt < n_qt; ++qt) {
       const int n = (tile0 + qt) * 128 + row;
       // The head sums of a query tile are combined ONE TILE LATE (by warpgroup 0, at the end of the next tile): by
-      // then warpgroup 1's half has long arrived, so neither warpgroup ever waits for the other at a tile boundary
-      // (event trace: the boundary cost warpgroup 0 ~4500 cycles per tile, 10 of the kernel's 43 us).  In accumulate
-      // mode the old heat values of the tile to be combined are fetched here, a whole tile ahead of the add.
-      float old_heat[kRFew];
+      // then warpgroup 1's half has long arrived, so neither warpgroup ever waits for the other at a tile boundary.
       const int n_prev = n - 128;  // row of this thread in the previous query tile
-      const bool combine_prev = want_heat && !tl.per_head && wg == 0 && qt > 0;
-      const bool rmw = combine_prev && accumulate && n_prev < N;
-      if (rmw) {
-        const float* src = maps + static_cast<long long>(b - b_first) * tl.n * N + n_prev;
-#pragma unroll
-        for (int t = 0; t < kRFew; ++t)
-          if (t < tl.n) old_heat[t] = __ldcg(src + static_cast<long long>(t) * N);
-      }
       for (int h = 0; h < H; ++h) {
         const int s = qt * H + h;
         if ((s & 1) != wg) continue;
@@ -324,7 +318,8 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
               if (tl.per_head) {  // DAAM-style: one plane per (batch, head, token), no head mean
                 if (n < N) {
                   float* ptr = maps + ((static_cast<long long>(b - b_first) * H + h) * tl.n + t) * N + n;
-                  *ptr = accumulate ? (*ptr + pt) : pt;
+                  if (accumulate) atomicAdd(ptr, pt);  // result-less RED: one thread per element and launch
+                  else *ptr = pt;
                 }
               } else {
                 acc[t] += pt;
@@ -367,22 +362,14 @@ attn_cross_sm100_res_kernel(const __grid_constant__ CUtensorMap map_q, const __g
           __threadfence_block();
           asm volatile("bar.arrive %0, 256;" ::"r"(1 + (qt & 1)) : "memory");
         } else if (qt > 0) {
-          combine_heat(qt - 1, n_prev, rmw, old_heat);
+          combine_heat(qt - 1, n_prev);
         }
       }
     }
     if (want_heat && !tl.per_head && wg == 0) {  // the last tile: this one does wait for warpgroup 1
       const int qt = n_qt - 1;
       const int n_last = (tile0 + qt) * 128 + row;
-      float old_heat[kRFew];
-      const bool rmw = accumulate && n_last < N;
-      if (rmw) {
-        const float* src = maps + static_cast<long long>(b - b_first) * tl.n * N + n_last;
-#pragma unroll
-        for (int t = 0; t < kRFew; ++t)
-          if (t < tl.n) old_heat[t] = __ldcg(src + static_cast<long long>(t) * N);
-      }
-      combine_heat(qt, n_last, rmw, old_heat);
+      combine_heat(qt, n_last);
     }
     if (prev_s >= 0) drain_o(prev_s);
     tc_fence_before();
