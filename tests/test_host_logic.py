@@ -193,3 +193,27 @@ def test_processor_autograd_routing_is_decided_on_every_input():
     proc = UNetCrossAttentionHooker(is_train=True)
     with pytest.raises(RuntimeError):
         proc(attn, x.clone().requires_grad_(True))
+
+
+@pytest.mark.parametrize("tokens,b_first", [([2, 5], 0), (None, 1), ([7, 7, 0], 1)])
+def test_cross_attention_backward_formulas_cpu(tokens, b_first):
+    """The gradient formulas of the training-mode cross-attention (agenda_b200/autograd.py docstring; the CUDA kernel
+    agenda_attn_cross_bwd implements the same ones) against autograd of the oracle's attention + head-mean maps
+    (hook.py:104-115, 28-56), on CPU in fp32: dq, dk, dv with gradients arriving through the output AND the maps."""
+    from types import SimpleNamespace
+    from agenda_b200.autograd import CrossAttentionHeatFn
+    from oracle import hook_oracle as O
+    g = torch.Generator().manual_seed(11)
+    B, N, M, H, d = 2, 16, 9, 2, 8
+    q, k, v = (torch.randn(B, s, H * d, generator=g) for s in (N, M, M))
+    go = torch.randn(B, N, H * d, generator=g)
+    T = M if tokens is None else len(tokens)
+    gm = torch.randn(B - b_first, T, N, generator=g)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out, p = O.attention_core(qr, kr, vr, H)
+    maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)[:, list(range(M)) if tokens is None else tokens]
+    torch.autograd.backward((out, maps), (go, gm))
+    ctx = SimpleNamespace(saved_tensors=(q, k, v), heads=H, scale=d ** -0.5, b_first=b_first, token_idx=tokens)
+    dq, dk, dv = CrossAttentionHeatFn._backward_torch(ctx, go, gm)[:3]
+    for a, b_ in ((dq, qr.grad), (dk, kr.grad), (dv, vr.grad)):
+        assert (a - b_).abs().max().item() < 1e-5 * max(1.0, b_.abs().max().item())
