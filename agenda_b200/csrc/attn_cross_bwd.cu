@@ -10,8 +10,9 @@
 // Exact fp32 CUDA-core kernel (first native version; the work is 5 * 2 * N * 77 * d FLOP per (batch, head) — small
 // next to the self-attention layers — so it is bound by reading Q / dO and writing dQ once).  CTA = (32 query rows,
 // one (batch, head)); K_h, V_h, the Q and dO tiles and the tile's P / dS live in shared memory as fp32.
-//   phase 1 (warp per row): scores and dP with lanes over keys, softmax by warp shuffles, dQ with lanes over channels
-//   phase 2 (thread per (key, channel)): the tile's contribution to dK / dV, added to the fp32 outputs with atomicAdd
+//   phase 1 (warp per 4 rows, taken together): scores and dP with lanes over keys — every K / V element read from
+//           shared memory feeds 4 FMAs — softmax by warp shuffles, dQ with lanes over channels
+//   phase 2 (thread per (key, 4 channels)): the tile's contribution to dK / dV, added to the fp32 outputs with atomicAdd
 // dk / dv are fp32 [B, M, H*d] accumulators the CALLER zero-fills (128 CTAs per (batch, head) add into them; the
 // order of those additions is not fixed, so dK / dV can differ in the last bits between runs).
 #include "common.cuh"
@@ -31,6 +32,10 @@ __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float
 __device__ __forceinline__ void from_f(float* p, float x) { *p = x; }
 __device__ __forceinline__ void from_f(__nv_bfloat16* p, float x) { *p = __float2bfloat16(x); }
 
+constexpr int kBwdRowsPerWarp = kBwdRows / (kBwdThreads / 32);  // 4 rows per warp, processed together
+
+__host__ __device__ inline int bwd_align4(int x) { return (x + 3) & ~3; }
+
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads)
 attn_cross_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
@@ -41,10 +46,10 @@ attn_cross_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
   const int ldk = d + 1;   // K / V rows padded: lanes walk keys, so consecutive rows must hit different banks
   const int mp = M + 1;
   float* Ks = reinterpret_cast<float*>(smem_raw);   // [M][d+1]
-  float* Vs = Ks + M * ldk;                         // [M][d+1]
-  float* Qs = Vs + M * ldk;                         // [32][d]
-  float* Os = Qs + kBwdRows * d;                    // [32][d]   dO tile
-  float* DS = Os + kBwdRows * d;                    // [32][M+1] dS * scale
+  float* Vs = Ks + bwd_align4(M * ldk);             // [M][d+1]
+  float* Qs = Vs + bwd_align4(M * ldk);             // [32][d]   (16-byte aligned: float4 reads in phase 2)
+  float* Os = Qs + bwd_align4(kBwdRows * d);        // [32][d]   dO tile
+  float* DS = Os + bwd_align4(kBwdRows * d);        // [32][M+1] dS * scale
   float* PS = DS + kBwdRows * mp;                   // [32][M+1] P
   float* GS = PS + kBwdRows * mp;                   // [8 warps][M+1] heat gradient per key of the warp's current row
 
@@ -68,34 +73,47 @@ attn_cross_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
   }
   __syncthreads();
 
+  // ---- phase 1: a warp takes 4 query rows TOGETHER (every K / V element read from shared memory feeds 4 FMAs) ----
   const bool heat = (d_maps != nullptr) && (b >= b_first) && tl.n > 0;
   const float inv_h = 1.0f / static_cast<float>(H);
   float* gs = GS + warp * mp;
-  for (int r = warp; r < kBwdRows; r += kBwdThreads / 32) {
-    const int n = n0 + r;
-    float* ds_row = DS + r * mp;
-    float* p_row = PS + r * mp;
-    if (n >= N) {  // padding row: contributes nothing to dK / dV
+  const int rbase = warp * kBwdRowsPerWarp;
+  float sc[kBwdRowsPerWarp][3], dp[kBwdRowsPerWarp][3];
+#pragma unroll
+  for (int r = 0; r < kBwdRowsPerWarp; ++r)
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) { sc[r][jj] = 0.f; dp[r][jj] = 0.f; }
+  int jrow[3];  // this lane's keys (clamped: lanes past M recompute the last key and drop the result)
+#pragma unroll
+  for (int jj = 0; jj < 3; ++jj) jrow[jj] = min(lane + 32 * jj, M - 1) * ldk;
+  for (int c = 0; c < d; ++c) {
+    float qv[kBwdRowsPerWarp], ov[kBwdRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kBwdRowsPerWarp; ++r) { qv[r] = Qs[(rbase + r) * d + c]; ov[r] = Os[(rbase + r) * d + c]; }
+#pragma unroll
+    for (int jj = 0; jj < 3; ++jj) {
+      const float kk = Ks[jrow[jj] + c], vv = Vs[jrow[jj] + c];
+#pragma unroll
+      for (int r = 0; r < kBwdRowsPerWarp; ++r) {
+        sc[r][jj] = fmaf(qv[r], kk, sc[r][jj]);
+        dp[r][jj] = fmaf(ov[r], vv, dp[r][jj]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kBwdRowsPerWarp; ++r) {
+    const int n = n0 + rbase + r;
+    float* ds_row = DS + (rbase + r) * mp;
+    float* p_row = PS + (rbase + r) * mp;
+    if (n >= N) {  // padding row: contributes nothing to dK / dV (warp-uniform branch)
       for (int j = lane; j < M; j += 32) { ds_row[j] = 0.f; p_row[j] = 0.f; }
       continue;
     }
-    const float* qr = Qs + r * d;
-    const float* orow = Os + r * d;
-    float s[3], dp[3];
+    float s[3], g[3];
 #pragma unroll
     for (int jj = 0; jj < 3; ++jj) {
-      const int j = lane + 32 * jj;
-      float a = 0.f, g = 0.f;
-      if (j < M) {
-        const float* kr = Ks + j * ldk;
-        const float* vr = Vs + j * ldk;
-        for (int c = 0; c < d; ++c) {
-          a = fmaf(qr[c], kr[c], a);
-          g = fmaf(orow[c], vr[c], g);
-        }
-      }
-      s[jj] = (j < M) ? a * scale : -INFINITY;
-      dp[jj] = g;
+      s[jj] = (lane + 32 * jj < M) ? sc[r][jj] * scale : -INFINITY;
+      g[jj] = dp[r][jj];
     }
     if (heat) {  // d_maps / H lands on the selected key columns (a token listed twice gets both planes)
       for (int j = lane; j < M; j += 32) gs[j] = 0.f;
@@ -106,8 +124,9 @@ attn_cross_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 #pragma unroll
       for (int jj = 0; jj < 3; ++jj) {
         const int j = lane + 32 * jj;
-        if (j < M) dp[jj] += gs[j];
+        if (j < M) g[jj] += gs[j];
       }
+      __syncwarp();  // gs is reused by the next row
     }
     const float mx = warp_max(fmaxf(fmaxf(s[0], s[1]), s[2]));
     float e[3], sum = 0.f;
@@ -121,37 +140,71 @@ attn_cross_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T*
 #pragma unroll
     for (int jj = 0; jj < 3; ++jj) {
       e[jj] *= inv_sum;  // P
-      delta = fmaf(e[jj], dp[jj], delta);
+      delta = fmaf(e[jj], g[jj], delta);
     }
     delta = warp_sum(delta);
 #pragma unroll
     for (int jj = 0; jj < 3; ++jj) {
       const int j = lane + 32 * jj;
       if (j < M) {
-        ds_row[j] = e[jj] * (dp[jj] - delta) * scale;
+        ds_row[j] = e[jj] * (g[jj] - delta) * scale;
         p_row[j] = e[jj];
       }
     }
-    __syncwarp();
-    T* dq_row = dq + q_base + static_cast<long long>(n) * C;
-    for (int c = lane; c < d; c += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < M; ++j) acc = fmaf(ds_row[j], Ks[j * ldk + c], acc);
-      from_f(dq_row + c, acc);
+  }
+  __syncwarp();
+  // dQ rows of this warp: lanes over channels, the 4 rows share every K element
+  for (int c = lane; c < d; c += 32) {
+    float acc[kBwdRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kBwdRowsPerWarp; ++r) acc[r] = 0.f;
+    for (int j = 0; j < M; ++j) {
+      const float kk = Ks[j * ldk + c];
+#pragma unroll
+      for (int r = 0; r < kBwdRowsPerWarp; ++r) acc[r] = fmaf(DS[(rbase + r) * mp + j], kk, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kBwdRowsPerWarp; ++r) {
+      const int n = n0 + rbase + r;
+      if (n < N) from_f(dq + q_base + static_cast<long long>(n) * C + c, acc[r]);
     }
   }
   __syncthreads();
 
-  for (int i = tid; i < M * d; i += kBwdThreads) {
-    const int j = i / d, c = i - j * d;
-    float ak = 0.f, av = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < kBwdRows; ++r) {
-      ak = fmaf(DS[r * mp + j], Qs[r * d + c], ak);
-      av = fmaf(PS[r * mp + j], Os[r * d + c], av);
+  // ---- phase 2: the tile's dK / dV; a thread owns (key j, 4 consecutive channels) ----
+  const int d4 = (d + 3) >> 2;
+  const bool vec = (d & 3) == 0;
+  for (int i = tid; i < M * d4; i += kBwdThreads) {
+    const int j = i / d4, c0 = (i - j * d4) * 4;
+    float ak[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+#pragma unroll 4
+      for (int r = 0; r < kBwdRows; ++r) {
+        const float ds = DS[r * mp + j], ps = PS[r * mp + j];
+        const float4 qv = *reinterpret_cast<const float4*>(Qs + r * d + c0);
+        const float4 ov = *reinterpret_cast<const float4*>(Os + r * d + c0);
+        ak[0] = fmaf(ds, qv.x, ak[0]); ak[1] = fmaf(ds, qv.y, ak[1]); ak[2] = fmaf(ds, qv.z, ak[2]); ak[3] = fmaf(ds, qv.w, ak[3]);
+        av[0] = fmaf(ps, ov.x, av[0]); av[1] = fmaf(ps, ov.y, av[1]); av[2] = fmaf(ps, ov.z, av[2]); av[3] = fmaf(ps, ov.w, av[3]);
+      }
+    } else {
+      for (int r = 0; r < kBwdRows; ++r) {
+        const float ds = DS[r * mp + j], ps = PS[r * mp + j];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < d) {
+            ak[u] = fmaf(ds, Qs[r * d + c0 + u], ak[u]);
+            av[u] = fmaf(ps, Os[r * d + c0 + u], av[u]);
+          }
+        }
+      }
     }
-    atomicAdd(dk + kv_base + static_cast<long long>(j) * C + c, ak);
-    atomicAdd(dv + kv_base + static_cast<long long>(j) * C + c, av);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c0 + u < d) {
+        atomicAdd(dk + kv_base + static_cast<long long>(j) * C + c0 + u, ak[u]);
+        atomicAdd(dv + kv_base + static_cast<long long>(j) * C + c0 + u, av[u]);
+      }
+    }
   }
 }
 
@@ -159,7 +212,8 @@ template <typename T>
 int launch_bwd(const void* q, const void* k, const void* v, const void* d_out, const float* d_maps, void* dq, float* dk,
                float* dv, const TokenList& tl, int B, int H, int N, int M, int d, int b_first, float scale,
                cudaStream_t stream) {
-  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(M) * (d + 1) + 2 * static_cast<size_t>(kBwdRows) * d +
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(bwd_align4(M * (d + 1))) +
+                                       2 * static_cast<size_t>(bwd_align4(kBwdRows * d)) +
                                        2 * static_cast<size_t>(kBwdRows) * (M + 1) + (kBwdThreads / 32) * (M + 1));
   if (smem > 200 * 1024)
     return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross_bwd: M=%d, d=%d needs %zu B of shared memory (> 200 KB)", M, d, smem);
