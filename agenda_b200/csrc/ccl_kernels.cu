@@ -873,6 +873,7 @@ using namespace agenda;
 
 extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, int32_t* counts, int32_t* boxes,
                                int max_boxes, int n, int H, int W, void* stream) {
+  if (n == 0) return AGENDA_OK;  // (an empty batch has no buffers to point at)
   if (!heat) return fail(AGENDA_ERR_NULL_POINTER, "ccl_bbox: heat is null");
   if (n < 0 || H <= 0 || W <= 0 || max_boxes < 0) return fail(AGENDA_ERR_BAD_SHAPE, "ccl_bbox: bad shape");
   if (boxes == nullptr) max_boxes = 0;

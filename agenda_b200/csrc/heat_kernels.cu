@@ -186,6 +186,7 @@ extern "C" int agenda_heat_upsample_accum_heads(const float* maps, float* acc, i
 
 static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes, int h, int w, int L, int T, int G,
                                     void* stream) {
+  if (n_planes == 0) return AGENDA_OK;  // (an empty batch has no buffers to point at)
   if (!maps || !acc) return fail(AGENDA_ERR_NULL_POINTER, "heat_upsample_accum: null pointer");
   if (n_planes < 0 || h <= 0 || w <= 0 || L <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: bad shape");
   if (L % 4 != 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_upsample_accum: latent_hw must be a multiple of 4 (got %d)", L);
@@ -218,6 +219,7 @@ static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes,
 }
 
 extern "C" int agenda_heat_finalize(const float* acc, float* out, int64_t n_elems, int count, void* stream) {
+  if (n_elems == 0) return AGENDA_OK;
   if (!acc || !out) return fail(AGENDA_ERR_NULL_POINTER, "heat_finalize: null pointer");
   if (n_elems < 0 || count < 1) return fail(AGENDA_ERR_BAD_SHAPE, "heat_finalize: need n_elems>=0, count>=1");
   if ((reinterpret_cast<uintptr_t>(acc) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))

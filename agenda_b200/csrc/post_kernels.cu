@@ -292,6 +292,7 @@ static int resize_shape_check(const char* who, int n, int Hi, int Wi, int Ho, in
 using namespace agenda;
 
 extern "C" int agenda_heat_normalize_u8(const float* heat, uint8_t* out, int n, int hw, void* stream) {
+  if (n == 0) return AGENDA_OK;  // (an empty batch has no buffers to point at)
   if (!heat || !out) return fail(AGENDA_ERR_NULL_POINTER, "heat_normalize_u8: null pointer");
   if (n < 0 || hw <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "heat_normalize_u8: bad shape");
   if (n == 0) return AGENDA_OK;
@@ -303,6 +304,7 @@ extern "C" int agenda_heat_normalize_u8(const float* heat, uint8_t* out, int n, 
 template <int MODE>
 static int launch_resize(const char* who, const void* in, uint8_t* out, int n, int Hi, int Wi, int Ho, int Wo,
                          void* stream) {
+  if (n == 0) return AGENDA_OK;
   if (!in || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   size_t smem = 0;
   int rc = resize_shape_check(who, n, Hi, Wi, Ho, Wo, 1, &smem);
@@ -326,6 +328,7 @@ extern "C" int agenda_heat_to_u8_image(const float* heat, uint8_t* out, int n, i
 
 extern "C" int agenda_stack_heatmaps_u8(const uint8_t* obj, const uint8_t* fg, const uint8_t* bg, uint8_t* stack,
                                         uint8_t* inv, int n, int H, int W, void* stream) {
+  if (n == 0) return AGENDA_OK;
   if (!obj || !fg || !bg || !stack) return fail(AGENDA_ERR_NULL_POINTER, "stack_heatmaps_u8: null pointer");
   if (n < 0 || H <= 0 || W <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "stack_heatmaps_u8: bad shape");
   if (n == 0) return AGENDA_OK;
@@ -346,6 +349,7 @@ extern "C" int agenda_stack_heatmaps_u8(const uint8_t* obj, const uint8_t* fg, c
 
 extern "C" int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes, uint8_t* stack, uint8_t* inv, int n,
                                              int Hi, int Wi, int Ho, int Wo, void* stream) {
+  if (n == 0) return AGENDA_OK;
   if (!heat || !stack) return fail(AGENDA_ERR_NULL_POINTER, "heat_postprocess_stack: null pointer");
   size_t smem = 0;
   int rc = resize_shape_check("heat_postprocess_stack", n, Hi, Wi, Ho, Wo, 3, &smem);

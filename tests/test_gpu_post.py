@@ -204,3 +204,19 @@ def test_errors_are_loud(ops):
         ops.ccl_bbox(torch.zeros((1, 4096, 4096), device="cuda"))  # does not fit a cluster's shared memory
     with pytest.raises(AgendaError):
         ops.heat_upsample_accum(torch.zeros((1, 8, 8), device="cuda"), torch.zeros((1, 30, 30), device="cuda"))
+
+
+def test_empty_batches(ops):
+    """n = 0 images / maps / planes: every post-processing entry point returns empty outputs without launching."""
+    dev = "cuda"
+    assert ops.heat_normalize_u8(torch.zeros((0, 64, 64), device=dev)).shape == (0, 64, 64)
+    assert ops.heat_to_u8_image(torch.zeros((0, 64, 64), device=dev), 112).shape == (0, 112, 112)
+    assert ops.resize_bicubic_u8(torch.zeros((0, 64, 64), dtype=torch.uint8, device=dev), 112).shape == (0, 112, 112)
+    z8 = torch.zeros((0, 112, 112), dtype=torch.uint8, device=dev)
+    st, inv = ops.stack_heatmaps_u8(z8, z8, z8)
+    assert st.shape == (0, 112, 112, 3) and inv.shape == (0, 112, 112)
+    labels, counts, boxes = ops.ccl_bbox(torch.zeros((0, 512, 512), device=dev), 0.5, max_boxes=16)
+    assert labels.shape == (0, 512, 512) and counts.shape == (0,) and boxes.shape == (0, 16, 5)
+    acc = torch.zeros((0, 3, 64, 64), device=dev)
+    ops.heat_upsample_accum(torch.zeros((0, 3, 32, 32), device=dev), acc)
+    torch.cuda.synchronize()
