@@ -131,7 +131,10 @@ struct Ex2Emu {
 // tiles.  The row sum tells whether that was legitimate: a row whose later scores exceed the first tile's maximum by
 // 2^100, or whose sum underflows, ends with l outside [2^-80, 2^100] (or NaN).  A CTA with such a row re-initialises
 // its barriers and runs a second, exact-maximum pass over its own query tiles (same code, kFast switched off).
-template <int D, int kEmu, int NT, int BN_, int KS, bool kFast>
+// kUnit (with kFast): the caller has folded scale * log2(e) into Q (the processor scales W_q once), so the scores ARE
+// the exponents: the fast pass uses reference 0 instead of the first tile's maximum and the MUFU columns need no FMA
+// at all; the row-sum proof is the same (|exponent| beyond ~100 sends the CTA into the exact pass).
+template <int D, int kEmu, int NT, int BN_, int KS, bool kFast, bool kUnit = false>
 __global__ void __launch_bounds__(NT * KS * 128 + 32 + 32 * NT, 1)
 attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
@@ -429,7 +432,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     constexpr int kOChunks = C::kDP / 16;
     const int oc_begin = (KS == 1) ? 0 : (half == 0 ? 0 : (kOChunks + 1) / 2);
     const int oc_end = (KS == 1) ? kOChunks : (half == 0 ? (kOChunks + 1) / 2 : kOChunks);
-    float m_used = -INFINITY;
+    float m_used = (kUnit && fast) ? 0.f : -INFINITY;  // (kUnit fast pass: fixed reference 0)
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
     const bool pingpong = (NT == 2) && (nt == 2) && ((issue_order & 3) >= 2) && (issue_order & 4);
@@ -439,6 +442,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     auto softmax_tile = [&](const int j, auto masked_c, auto fast_c) {
       constexpr bool kMasked = decltype(masked_c)::value;
       constexpr bool kSkipMax = decltype(fast_c)::value;  // fast pass: only the first tile's maximum is taken
+      constexpr bool kNoShift = kUnit && kSkipMax;        // ... and not even that when the scores are the exponents
       V2_TRACE((warp < 6 ? warp : 99), j, 0);
       mbar_wait(&bars->s_full[t], j & 1);
       tc_fence_after();
@@ -469,7 +473,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       // rescale touches it.  The rescale is rare, so the wait normally happens right before the first P store, after
       // the first 32 columns have been exponentiated (the PV MMA group needs ~500 cycles from p_full to pv_done).
       bool pv_waited = (j == 0);
-      if (!kSkipMax || j == 0) {
+      if (!kSkipMax || (j == 0 && !kNoShift)) {
       float mx;
       {
         float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
@@ -538,9 +542,13 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         for (int i = 0; i < kCols / 2; i += 2) {
           const int e = col0 + 2 * i;
           float a0, a1, b0, b1;
-          const uint64_t xa = ffma2(pack_f32x2(sv[e], sv[e + 1]), scale2, negm2);
-          unpack_f32x2(xa, a0, a1);
-          a0 = ex2(a0); a1 = ex2(a1);
+          if (kNoShift) {
+            a0 = ex2(sv[e]); a1 = ex2(sv[e + 1]);
+          } else {
+            const uint64_t xa = ffma2(pack_f32x2(sv[e], sv[e + 1]), scale2, negm2);
+            unpack_f32x2(xa, a0, a1);
+            a0 = ex2(a0); a1 = ex2(a1);
+          }
           // pair b of iteration ib = i/2 is emulated according to kEmu:
           // 2 -> every b pair (50 % of all exponentials), 3 -> ib % 3 != 2 (37.5 %), 4 -> even ib (25 %), 8 -> ib % 4 == 0
           const int ib = i >> 1;
@@ -549,9 +557,13 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           if (emu_pair) {
             ex2_emu(sv[e + 2], sv[e + 3], emu_a, emu_b, b0, b1);
           } else {
-            const uint64_t xb = ffma2(pack_f32x2(sv[e + 2], sv[e + 3]), scale2, negm2);
-            unpack_f32x2(xb, b0, b1);
-            b0 = ex2(b0); b1 = ex2(b1);
+            if (kNoShift) {
+              b0 = ex2(sv[e + 2]); b1 = ex2(sv[e + 3]);
+            } else {
+              const uint64_t xb = ffma2(pack_f32x2(sv[e + 2], sv[e + 3]), scale2, negm2);
+              unpack_f32x2(xb, b0, b1);
+              b0 = ex2(b0); b1 = ex2(b1);
+            }
           }
           if (!C::kSumInMma) {
             sum2a = fadd2(sum2a, pack_f32x2(a0, a1));
@@ -643,7 +655,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 
 }  // namespace sm100
 
-template <int D, int kEmu, int NT, int BN, int KS = 1, bool kFast = false>
+template <int D, int kEmu, int NT, int BN, int KS = 1, bool kFast = false, bool kUnit = false>
 static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
                      cudaStream_t stream) {
   using C = sm100::V2Cfg<D, NT, BN, KS>;
@@ -653,7 +665,7 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
   if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::v2_smem_bytes<C>();
-  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS, kFast>;
+  auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS, kFast, kUnit>;
   AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(((N + 128 * NT - 1) / (128 * NT)) * B * H));
   // measured on B200 (tools/bench_attn.py): one MMA warp per query tile (2) wins except where P aliases S (d = 80)
@@ -663,7 +675,7 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
   if (const char* e = getenv("AGENDA_V2_SKEW")) stagger = atoi(e);
   issue_order |= stagger << 8;
   kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
-                                            scale * 1.4426950408889634f, issue_order);
+                                            kUnit ? 1.0f : scale * 1.4426950408889634f, issue_order);
   AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");
   return AGENDA_OK;
 }
@@ -675,6 +687,7 @@ int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, i
                        int emu, int tiles, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tiles >= 100) {  // fast first pass, instantiated for the shipped defaults (+ two emulation shares for measurements)
+    if (d == 40 && tiles == 203 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 40 && tiles == 103 && emu == 2) return launch_v2<40, 2, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
     if (d == 40 && tiles == 103 && emu == 4) return launch_v2<40, 4, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);

@@ -372,6 +372,12 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   // exponentials on the FMA pipe; otherwise two query tiles with 128-key tiles (64 at d = 160), 25 %
   // and the fast first pass (first-tile maximum + row-sum check, exact second pass for the CTAs that need it);
   // AGENDA_V2_FAST=0 keeps the running maximum in a single pass (measurements)
+  // scale == 0 (agenda_attn_self_fwd_strided only): q already carries scale * log2(e)
+  if (scale == 0.0f) {
+    scale = 0.6931471805599453f;  // kernels without the unit-scale form: scale * log2(e) = 1
+    static const int fast0 = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 1; }();
+    if (variant == 0 && N > 128 && d == 40 && fast0) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 203, stream);
+  }
   if (variant == 0 && N > 128) {
     static const int fast = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 100; }();
     // (d = 160 only occurs at N <= 256 in the SD UNets: four key tiles do not amortise the fast pass's epilogue)

@@ -62,7 +62,8 @@ def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     return out
 
 
-def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
+def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = None,
+                        prescaled: bool = False) -> torch.Tensor:
     """Self-attention on the output of ONE fused q/k/v projection: qkv bf16 [B,N,3C] with q = [..,:C], k = [..,C:2C],
     v = [..,2C:].  The kernel reads the three column slices in place (row stride 3C); returns out [B,N,C]."""
     qkv = _dev(qkv, "qkv", torch.bfloat16)
@@ -71,7 +72,8 @@ def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = 
         raise ValueError("qkv last dim must be 3*C")
     C = C3 // 3
     d = C // heads
-    scale = float(d ** -0.5 if scale is None else scale)
+    # prescaled: the q columns already carry scale * log2(e) (folded into W_q) -> the ABI's scale == 0 convention
+    scale = 0.0 if prescaled else float(d ** -0.5 if scale is None else scale)
     out = torch.empty((B, N, C), dtype=torch.bfloat16, device=qkv.device)
     p = qkv.data_ptr()
     _lib.call("agenda_attn_self_fwd_strided", p, p + 2 * C, p + 4 * C, out.data_ptr(), _lib.BF16, B, heads, N, d, C3,

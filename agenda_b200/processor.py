@@ -53,6 +53,7 @@ class UNetCrossAttentionHooker:
         # GEMM with the concatenated weights (hidden_states read once instead of three times) and the attention kernel
         # reads q/k/v as column slices of its output.  id(attn) -> (weight versions, fused [3C,C] weight)
         self.fuse_qkv = os.environ.get("AGENDA_FUSE_QKV", "1") != "0"
+        self.prescale_q = os.environ.get("AGENDA_PRESCALE_Q", "1") != "0"
         self._qkv_weights = {}
         # cross-attention: to_k / to_v of the prompt embedding (hook.py:101-102) do not depend on the latent, yet the
         # reference recomputes them in every block at every denoising step.  K and V are kept per module for as long as
@@ -115,17 +116,23 @@ class UNetCrossAttentionHooker:
         mods = (attn.to_q, attn.to_k, attn.to_v)
         ws = [getattr(m, "weight", None) for m in mods]
         if any(w is None or w.dtype != torch.bfloat16 or not w.is_cuda for w in ws):
-            return None
+            return None, False
         if any(getattr(m, "bias", None) is not None for m in mods) or not (ws[0].shape == ws[1].shape == ws[2].shape):
-            return None
+            return None, False
         if type(attn.to_q) is not torch.nn.Linear or ws[0].shape[0] % 8:
-            return None
-        key = tuple((w.data_ptr(), w._version) for w in ws)
+            return None, False
+        # d = 40 layers: scale * log2(e) is folded into the q rows (one rounding of the scaled fp32 weight to bf16), so the
+        # attention kernel's scores are the base-2 exponents themselves (ABI: scale == 0)
+        prescale = self.prescale_q and ws[0].shape[0] // attn.heads == 40
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (prescale, float(attn.scale))
         hit = self._qkv_weights.get(id(attn))
         if hit is None or hit[0] != key:
-            hit = (key, torch.cat([w.detach() for w in ws], 0).contiguous())
+            wq = ws[0].detach()
+            if prescale:
+                wq = (wq.float() * (float(attn.scale) * 1.4426950408889634)).to(torch.bfloat16)
+            hit = (key, torch.cat([wq, ws[1].detach(), ws[2].detach()], 0).contiguous(), prescale)
             self._qkv_weights[id(attn)] = hit
-        return hit[1]
+        return hit[1], hit[2]
 
     @staticmethod
     def _kv_state(attn, ehs):
@@ -211,10 +218,10 @@ class UNetCrossAttentionHooker:
             return self._call_with_autograd(attn, hidden_states, encoder_hidden_states)
         if (encoder_hidden_states is None and self.fuse_qkv and self.precision == "bf16"
                 and hidden_states.dtype == torch.bfloat16 and hidden_states.is_cuda):
-            w = self._fused_qkv_weight(attn)
+            w, prescaled = self._fused_qkv_weight(attn)
             if w is not None:
                 qkv = torch.nn.functional.linear(hidden_states, w)
-                hidden_states = ops.attn_self_fused_qkv(qkv, attn.heads, scale=float(attn.scale))
+                hidden_states = ops.attn_self_fused_qkv(qkv, attn.heads, scale=float(attn.scale), prescaled=prescaled)
                 hidden_states = attn.to_out[0](hidden_states)
                 return attn.to_out[1](hidden_states)
         query = attn.to_q(hidden_states)

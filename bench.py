@@ -323,7 +323,7 @@ def run_ours(args):
     achieved = flops / (ms_k / 1000.0) / 1e12 if ms_k > 0 else 0.0
     step_ms_eager_share = None
     kname = ("attn_self_sm100_v2_kernel<64,4,2,128,1,true> (N=9216, B*H=%d)" % (2 * n_img * 5) if sd21 else
-             "attn_self_sm100_v2_kernel<40,3,3,64,1,true> (N=4096, B*H=%d)" % (2 * n_img * 8))
+             "attn_self_sm100_v2_kernel<40,3,3,64,1,true,true> (N=4096, B*H=%d)" % (2 * n_img * 8))
     roofline = {"kernel": kname, "bound": "tensor",
                 "achieved": achieved, "peak": tf_sust, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B*H=128 from the ncu --set full capture

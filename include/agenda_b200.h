@@ -56,7 +56,8 @@ int agenda_attn_self_fwd(const void* q, const void* k, const void* v, void* out,
 /* Same, with q/k/v rows `ld` elements apart (batch stride N*ld): q, k, v may be column slices [.., 0:C], [.., C:2C],
  * [.., 2C:3C] of ONE fused projection output [B,N,3C] (to_q/to_k/to_v of hook.py:93,101-102 act on the same
  * hidden_states in self-attention, so one GEMM with the concatenated weights reads them once).  out stays packed
- * [B,N,H*d].  ld >= H*d, ld % 8 == 0, pointers 16-byte aligned. */
+ * [B,N,H*d].  ld >= H*d, ld % 8 == 0, pointers 16-byte aligned. * scale == 0 means the caller has already multiplied q by scale * log2(e) (the processor folds it into W_q): the
+ * scores are then the base-2 exponents themselves and the d = 40 kernel skips the scale/shift FMA. */
 int agenda_attn_self_fwd_strided(const void* q, const void* k, const void* v, void* out, int dtype,
                                  int B, int H, int N, int d, long long ld, float scale, void* stream);
 

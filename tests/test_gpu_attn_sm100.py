@@ -208,3 +208,25 @@ def test_processor_fused_qkv_projection(lib):
         a2, b2 = fused(attn, x), plain(attn, x)
         assert (a2.float() - b2.float()).abs().max().item() < 2e-2
         assert (a2.float() - a.float()).abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("B,N,H,boost", [(2, 1024, 8, 1.0), (1, 4096, 2, 1.0), (1, 300, 2, 1.0), (2, 1024, 2, 40.0)])
+def test_sm100_prescaled_q_unit_scale_path(lib, B, N, H, boost):
+    """ABI convention scale == 0 (agenda_attn_self_fwd_strided): q already carries scale * log2(e), the d = 40 kernel
+    takes exp2 of the raw scores with reference 0 (no scale/shift FMA, no maximum) and proves it with the row sum.
+    Oracle: the same attention on q / (scale * log2 e).  boost = 40 makes some exponents exceed 2^100 so that those
+    CTAs take the exact second pass."""
+    from agenda_b200 import ops
+    d = 40
+    c = d ** -0.5 * 1.4426950408889634
+    g = torch.Generator().manual_seed(N + H)
+    q = torch.randn(B, N, H * d, generator=g) * 1.5
+    k = torch.randn(B, N, H * d, generator=g) * 1.5
+    v = torch.randn(B, N, H * d, generator=g) * 0.25
+    k[:, 70:74] *= boost
+    q_pre = (q * c).bfloat16()
+    qkv = torch.cat([q_pre, k.bfloat16(), v.bfloat16()], dim=-1).cuda().contiguous()
+    out = ops.attn_self_fused_qkv(qkv, H, prescaled=True).float().cpu()
+    ref, _ = O.attention_core(q_pre.float() / c, k.bfloat16().float(), v.bfloat16().float(), H)
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < TOL
