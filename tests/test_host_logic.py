@@ -217,3 +217,13 @@ def test_cross_attention_backward_formulas_cpu(tokens, b_first):
     dq, dk, dv = CrossAttentionHeatFn._backward_torch(ctx, go, gm)[:3]
     for a, b_ in ((dq, qr.grad), (dk, kr.grad), (dv, vr.grad)):
         assert (a - b_).abs().max().item() < 1e-5 * max(1.0, b_.abs().max().item())
+
+
+def test_fused_qkv_weight_declines_on_cpu_modules():
+    """The one-GEMM q/k/v projection (and the scale fold into W_q) only applies to CUDA bf16 Linear layers; everything
+    else must decline with a (None, False) pair so that the processor falls through to the separate projections."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    proc = UNetCrossAttentionHooker(is_train=False)
+    assert proc._fused_qkv_weight(SDAttention(320, None, 8, 40)) == (None, False)            # fp32 on CPU
+    assert proc._fused_qkv_weight(SDAttention(320, None, 8, 40).bfloat16()) == (None, False)  # bf16 but not CUDA
