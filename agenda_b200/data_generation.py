@@ -21,23 +21,42 @@ import numpy as np
 import torch
 
 
-def parse_args(argv=None):
-    parser = argparse.ArgumentParser(description="Image and attention map generation.")
-    parser.add_argument("--save-dir", type=str, default="Data/Synthetic", help="Directory to save images (and heatmaps if enabled).")
-    parser.add_argument("--pretrained-model-path", type=str, default="output/LINZ-Utah/sd1.4-token-finetune-stage-two/full_model_step_4500", help="Path or repo-id of the pretrained model to load.")
-    parser.add_argument("--learnable-tokens-embedding-path", type=str, default="output/LINZ-Utah/sd1.4-token-finetune-stage-one/learned_embeds_steps_9000.bin", help="Path to the learned token embeddings.")
-    parser.add_argument("--prompt", type=str, default="An aerial view image with {} cars in {} Utah", help="Prompt template for image generation.")
-    parser.add_argument("--initialize_token", type=str, default=["cars", "Utah", "New Zealand"], nargs="+", help="The initialization for learnable tokens in the first stage")
-    parser.add_argument("--word_token_heatmaps", type=str, default=None, nargs="+", help="word tokens to compute DAAM heatmaps.")
-    parser.add_argument("--store_learnable_token_heatmaps", action="store_true", help="Whether to store DAAM heatmaps for learnable tokens.")
-    parser.add_argument("--num-images", type=int, default=10000, help="Number of images to generate.")
-    parser.add_argument("--image-size", type=int, default=112, help="Size of the generated images.")
-    # additions
-    parser.add_argument("--synthetic", action="store_true", help="Random-weight SD-1.5 attention stack instead of a diffusers pipeline.")
-    parser.add_argument("--token-indices", type=int, nargs="+", default=None, help="Context-token rows of the words (needed when no tokenizer vocabulary is available).")
+# The reference's command line (data_generation.py:11-23): flag -> (type, default, extra argparse keywords).  Names
+# and defaults are the drop-in surface; the help texts below are ours.
+_REFERENCE_FLAGS = (
+    ("--save-dir", str, "Data/Synthetic", {}, "output root: images/ and daam_<word>_heatmaps/ are created below it"),
+    ("--pretrained-model-path", str, "output/LINZ-Utah/sd1.4-token-finetune-stage-two/full_model_step_4500", {},
+     "Stable Diffusion checkpoint (directory or hub id)"),
+    ("--learnable-tokens-embedding-path", str,
+     "output/LINZ-Utah/sd1.4-token-finetune-stage-one/learned_embeds_steps_9000.bin", {},
+     "file with the embeddings of the learned tokens"),
+    ("--prompt", str, "An aerial view image with {} cars in {} Utah", {}, "prompt template; {} = learned tokens"),
+    ("--initialize_token", str, ["cars", "Utah", "New Zealand"], {"nargs": "+"},
+     "words the learned tokens were initialised from (stage one)"),
+    ("--word_token_heatmaps", str, None, {"nargs": "+"}, "ordinary words whose heat maps are wanted"),
+    ("--num-images", int, 10000, {}, "how many seeds to run"),
+    ("--image-size", int, 112, {}, "side of the saved images and heat maps"),
+)
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="Heat-map-labelled image generation on the B200 kernels.")
+    for flag, typ, default, extra, text in _REFERENCE_FLAGS:
+        parser.add_argument(flag, type=typ, default=default, help=text, **extra)
+    parser.add_argument("--store_learnable_token_heatmaps", action="store_true",
+                        help="also save the heat maps of the learned tokens")
+    # not in the reference
+    parser.add_argument("--synthetic", action="store_true",
+                        help="random-weight SD-1.5 attention stack instead of a diffusers pipeline")
+    parser.add_argument("--token-indices", type=int, nargs="+", default=None,
+                        help="context rows of the words (when no tokenizer vocabulary is available)")
     parser.add_argument("--num-inference-steps", type=int, default=20)
-    parser.add_argument("--batch-size", type=int, default=8, help="Images per batch in --synthetic mode.")
-    return parser.parse_args(argv)
+    parser.add_argument("--batch-size", type=int, default=8, help="images per batch in --synthetic mode")
+    return parser
+
+
+def parse_args(argv=None):
+    return build_parser().parse_args(argv)
 
 
 def save_word_heatmaps(save_dir, word, seeds, heat, image_size):
@@ -84,45 +103,52 @@ def run_synthetic(args):
     return done
 
 
+def _install_learned_tokens(pipeline, args):
+    """data_generation.py:40-54: register the learned tokens that the prompt template uses with the tokenizer and copy
+    their embeddings into the text encoder.  Returns (token strings used in the prompt, words to draw heat maps for)."""
+    learned = torch.load(args.learnable_tokens_embedding_path)
+    used, words = [], list(args.word_token_heatmaps or [])
+    for init_word, token in zip(args.initialize_token, learned.keys()):
+        if init_word not in args.prompt:
+            continue
+        used.append(token)
+        if args.store_learnable_token_heatmaps:
+            words.append(token)
+    tok, enc = pipeline.tokenizer, pipeline.text_encoder
+    tok.add_tokens(used)
+    enc.resize_token_embeddings(len(tok))
+    rows = tok.convert_tokens_to_ids(used)
+    with torch.no_grad():
+        table = enc.get_input_embeddings().weight
+        table.data[rows] = torch.stack([learned[t] for t in used]).to(table.device, table.dtype)
+    return used, words
+
+
 def run_pipeline(args):
     try:
         from diffusers import StableDiffusionPipeline
     except ImportError as e:  # pragma: no cover - not installable offline
         raise SystemExit("diffusers is not installed: real generation needs the reference's environment "
                          "(requirements.txt). Use --synthetic for the attention-stack workload.") from e
-    from PIL import Image
     from . import trace as trace_mod
-    os.makedirs(args.save_dir, exist_ok=True)
     pipeline = StableDiffusionPipeline.from_pretrained(args.pretrained_model_path).to("cuda")
-    embeds_dict = torch.load(args.learnable_tokens_embedding_path)
-    all_new_tokens = list(embeds_dict.keys())
-    all_words = list(args.word_token_heatmaps) if args.word_token_heatmaps is not None else []
-    new_tokens = []
-    for t, n in zip(args.initialize_token, all_new_tokens):
-        if t in args.prompt:
-            if args.store_learnable_token_heatmaps:
-                all_words.append(n)
-            new_tokens.append(n)
-    embeds = torch.stack([embeds_dict[token] for token in new_tokens]).to("cuda")
-    pipeline.tokenizer.add_tokens(new_tokens)
-    new_token_ids = pipeline.tokenizer.convert_tokens_to_ids(new_tokens)
-    pipeline.text_encoder.resize_token_embeddings(len(pipeline.tokenizer))
-    with torch.no_grad():
-        pipeline.text_encoder.get_input_embeddings().weight.data[new_token_ids] = embeds
-    prompt = args.prompt.format(*new_tokens)
+    used, words = _install_learned_tokens(pipeline, args)
+    prompt = args.prompt.format(*used)
+    image_dir = os.path.join(args.save_dir, "images")
+    os.makedirs(image_dir, exist_ok=True)
     for seed in range(args.num_images):
-        with trace_mod.trace(pipeline, prompt=prompt) as trc:
-            generator = torch.Generator(device="cuda").manual_seed(seed)
-            output_image = pipeline(prompt, num_inference_steps=args.num_inference_steps, generator=generator).images[0]
-            output_image = output_image.resize((args.image_size, args.image_size))
-            if np.max(np.asarray(output_image)) < 1e-5:  # NSFW content filter (data_generation.py:61-62)
+        rng = torch.Generator(device="cuda").manual_seed(seed)
+        with trace_mod.trace(pipeline, prompt=prompt) as tracer:          # daam.trace(pipeline), :57
+            image = pipeline(prompt, num_inference_steps=args.num_inference_steps, generator=rng).images[0]
+            image = image.resize((args.image_size, args.image_size))
+            if np.asarray(image).max() < 1e-5:                            # all-black = filtered image, :61-62
                 continue
-            heat = trc.compute_global_heat_map()
-        os.makedirs(os.path.join(args.save_dir, "images"), exist_ok=True)
-        output_image.save(os.path.join(args.save_dir, "images", f"{seed}.png"))
-        for word in all_words:
-            hm = heat.compute_word_heat_map(word).heatmap
-            save_word_heatmaps(args.save_dir, word, [seed], hm[None], args.image_size)
+            heat = tracer.compute_global_heat_map()
+        image.save(os.path.join(image_dir, f"{seed}.png"))
+        for word in words:
+            plane = heat.compute_word_heat_map(word).heatmap              # :74-77
+            save_word_heatmaps(args.save_dir, word, [seed], plane[None], args.image_size)
+    return args.num_images
 
 
 def main(argv=None):

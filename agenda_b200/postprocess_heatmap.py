@@ -16,16 +16,28 @@ import os
 import numpy as np
 
 
+# The reference's command line (postprocess_heatmap.py:8-17): flag -> default.  Names and defaults are the drop-in
+# surface; all six take a string.
+_REFERENCE_FLAGS = (
+    ("--save-dir", "Data/Synthetic", "root that holds the heat-map directories"),
+    ("--object-heatmap-path", None, "sub-directory with the object word's heat maps"),
+    ("--fg-heatmap-path", None, "sub-directory with the foreground token's heat maps"),
+    ("--bg-heatmap-path", None, "sub-directory with the background token's heat maps"),
+    ("--stack-heatmap-save-path", "daam_stack_heatmaps", "sub-directory for the RGB stacks"),
+    ("--inv-heatmap-save-path", "daam_inv_heatmaps", "sub-directory for the inverted background maps"),
+)
+
+
+def build_parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(description="Invert the background heat map and stack object / fg / bg into RGB.")
+    for flag, default, text in _REFERENCE_FLAGS:
+        parser.add_argument(flag, type=str, default=default, help=text)
+    parser.add_argument("--batch", type=int, default=1024, help="images per GPU launch (not in the reference)")
+    return parser
+
+
 def parse_args(argv=None):
-    parser = argparse.ArgumentParser(description="Stack attention map.")
-    parser.add_argument("--save-dir", type=str, default="Data/Synthetic", help="Directory to save images (and heatmaps if enabled).")
-    parser.add_argument("--object-heatmap-path", type=str, default=None, help="Path to the object token heatmaps.")
-    parser.add_argument("--fg-heatmap-path", type=str, default=None, help="Path to the foreground learnable token heatmaps.")
-    parser.add_argument("--bg-heatmap-path", type=str, default=None, help="Path to the background learnable token heatmaps.")
-    parser.add_argument("--stack-heatmap-save-path", type=str, default="daam_stack_heatmaps", help="Path to save the stacked heatmaps.")
-    parser.add_argument("--inv-heatmap-save-path", type=str, default="daam_inv_heatmaps", help="Path to save the inverted heatmaps of the learnable background token.")
-    parser.add_argument("--batch", type=int, default=1024, help="Images per GPU launch.")
-    return parser.parse_args(argv)
+    return build_parser().parse_args(argv)
 
 
 def main(argv=None):
