@@ -300,6 +300,8 @@ static EncodeTiledFn get_encode_fn() {
 // of agenda_attn_self_fwd_strided (q/k/v as column slices of one fused-projection output) — thread-local call scratch,
 // not library state.
 static thread_local long long g_row_stride = 0;
+// Same lifetime: q of the current agenda_attn_self_fwd_strided call already carries scale * log2(e) (its scale == 0).
+static thread_local bool g_q_prescaled = false;
 
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -372,8 +374,8 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   // exponentials on the FMA pipe; otherwise two query tiles with 128-key tiles (64 at d = 160), 25 %
   // and the fast first pass (first-tile maximum + row-sum check, exact second pass for the CTAs that need it);
   // AGENDA_V2_FAST=0 keeps the running maximum in a single pass (measurements)
-  // scale == 0 (agenda_attn_self_fwd_strided only): q already carries scale * log2(e)
-  if (scale == 0.0f) {
+  // agenda_attn_self_fwd_strided with scale == 0: q already carries scale * log2(e)
+  if (g_q_prescaled) {
     scale = 0.6931471805599453f;  // kernels without the unit-scale form: scale * log2(e) = 1
     static const int fast0 = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 1; }();
     if (variant == 0 && N > 128 && d == 40 && fast0) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 203, stream);
@@ -421,8 +423,10 @@ extern "C" int agenda_attn_self_fwd_strided(const void* q, const void* k, const 
   if (ld < static_cast<long long>(H) * d || (ld & 7))
     return fail(AGENDA_ERR_BAD_SHAPE, "attn_self_fwd_strided: ld=%lld must be >= H*d=%d and a multiple of 8", ld, H * d);
   g_row_stride = ld;
+  g_q_prescaled = (scale == 0.0f);
   rc = attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
   g_row_stride = 0;
+  g_q_prescaled = false;
   return rc;
 }
 
