@@ -1,0 +1,581 @@
+// K2x3: cross-attention + heat epilogue with fp32-accurate logits on the bf16 tensor cores (sm_100a).
+//
+//   out  = softmax(scale * Q K^T) V                                    (data_generation/hook.py:108,114)
+//   maps[b', t, n] (=|+=) mean_h softmax(...)[b, h, n, token_idx[t]]    (_unravel_attn, hook.py:28-56)
+//
+// Why: the reference runs in fp32 and the heat maps are held to 1e-4 max-abs.  A bf16 Q / K carries a
+// relative error of 2^-9 per element, i.e. logit errors of ~1e-3..1e-2 and probability errors up to ~2.5e-3; tf32
+// (truncated to 10 mantissa bits by the tensor core) is borderline.  This kernel takes Q in fp32 and K as a
+// pre-split pair K = K_hi + K_lo (both bf16, K_lo = bf16(K - K_hi)), splits every Q tile the same way on chip and
+// accumulates S = Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T in the fp32 TMEM accumulator: products of bf16 values are
+// exact in fp32, the dropped Q_lo K_lo^T term is 2^-18 relative, so the logits match an fp32 baddbmm to ~1e-5 and the
+// probabilities to ~1e-6.  Cross-attention is 3 % of the attention FLOPs, so the 3x MMA count is free;
+// the kernel stays HBM-bound (Q fp32 in, O out).
+//
+// Loop order is HEAD-OUTER: a CTA owns QT consecutive 128-query tiles of one batch element; for each head it keeps
+// K_hi / K_lo / V of that head resident (30 KB at d = 40, double-buffered so the next head's block arrives under the
+// current head's steps) and streams the head's Q column chunks of all its query tiles.  Step s = head * QT + tile.
+//
+//   warps 0-3 / 4-7   two softmax warpgroups (thread == query row), even / odd steps, own S / P / O TMEM slots
+//   warp  8           TMA producer: K/V blocks per head, fp32 Q chunks [128 x W] through a ring (W = 40 or 64 columns)
+//   warp  9           TMEM allocator + tcgen05.mma issuer
+//   warps 10-11       converters: fp32 Q chunk -> bf16 hi / lo operand tiles in the 128B-swizzled K-major UMMA layout
+//
+// Heat: every softmax thread adds its selected-token probabilities into a shared-memory row of its own
+// ([warpgroup][tile][token][row]); after the last head warpgroup 0 adds the two halves in a fixed order and writes
+// mean over heads (deterministic, no atomics between CTAs).  Small launches split the heads over a cluster along z
+// and finish the sum through the leader's shared memory in rank order, like attn_cross_sm100.cu.
+#include <cooperative_groups.h>
+#include <cstdlib>
+#include <type_traits>
+
+#include "sm100_common.cuh"
+
+namespace agenda {
+namespace sm100 {
+
+namespace cg = cooperative_groups;
+
+constexpr int kTThreads = 384;
+constexpr int kTConvWarp0 = 10;    // first converter warp
+constexpr int kTConvThreads = 64;
+constexpr int kTMPad = 80;         // 77 prompt tokens padded to a multiple of 16
+constexpr int kTSlot = 80;         // TMEM columns per S buffer
+constexpr int kTPSlot = 48;        // TMEM columns per P buffer (80 bf16 = 40 packed columns, stored as 3 x 16)
+constexpr int kTFew = 8;           // heat tokens handled
+constexpr int kTMaxQT = 4;         // query tiles per CTA (heat rows in shared memory)
+constexpr int kTTile = kTMPad * 128;  // one 80-row, 128B-swizzled K / V tile
+
+template <int D>
+struct TCfg {
+  static constexpr int kW = (D % 64 == 0) ? 64 : 40;     // Q / K column chunk (d = 40: 1, 64: 1, 80: 2, 160: 4 chunks)
+  static constexpr int kNC = D / kW;
+  static constexpr int kWP = (kW + 15) / 16 * 16;        // K extent of a chunk inside the MMAs (zero-padded Q columns)
+  static constexpr int kDP = (D + 15) / 16 * 16;         // N extent of the PV MMA
+  static constexpr int kVC = (D + 63) / 64;              // 64-column swizzle chunks of V
+  static constexpr int kQ32Bytes = 128 * kW * 4;         // one fp32 Q chunk, dense rows (no swizzle)
+  static constexpr int kQBBytes = 2 * 128 * 128;         // bf16 hi tile + lo tile
+  static constexpr int kKVBytes = (2 * kNC + kVC) * kTTile;
+  static constexpr int kKVBufs = (D <= 64) ? 2 : 1;
+  static constexpr int kQStages = (D == 40) ? 3 : 2;
+  static constexpr int kQBBufs = 2;
+  static constexpr bool kAliasP = (2 * kTSlot + 2 * kTPSlot + 2 * kDP > 512);  // d = 160: P overwrites its S slot
+  static constexpr int kColP = kAliasP ? 0 : 2 * kTSlot;
+  static constexpr int kPStride = kAliasP ? kTSlot : kTPSlot;
+  static constexpr int kColO = kAliasP ? 2 * kTSlot : 2 * kTSlot + 2 * kTPSlot;
+  static constexpr int kMaxQT = (D == 160) ? 1 : kTMaxQT;
+  static_assert(D % kW == 0, "head dim must be a whole number of chunks");
+  static_assert(kColO + 2 * kDP <= 512, "TMEM overflow");
+};
+
+struct TBarriers {
+  uint64_t kv_full[2], kv_empty[2];
+  uint64_t q32_full[3], q32_empty[3];
+  uint64_t qb_full[2], qb_empty[2];
+  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2], o_free[2];
+  uint32_t tmem_base;
+};
+
+template <int D>
+inline size_t t_smem_bytes(int QT) {
+  using C = TCfg<D>;
+  return 1024 + static_cast<size_t>(C::kQStages) * C::kQ32Bytes + C::kQBBufs * C::kQBBytes + C::kKVBufs * C::kKVBytes +
+         static_cast<size_t>(2) * QT * kTFew * 128 * 4 + sizeof(TBarriers) + 64;
+}
+
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int D, typename OutT>
+__global__ void __launch_bounds__(kTThreads, 1)
+attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_khi,
+                           const __grid_constant__ CUtensorMap map_klo, const __grid_constant__ CUtensorMap map_v,
+                           OutT* __restrict__ out, float* __restrict__ maps, const TokenList tl, int H, int N, int M,
+                           int QT, int b_first, int accumulate, float scale_log2) {
+  using C = TCfg<D>;
+  constexpr int W = C::kW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ32 = smem;                                        // kQStages fp32 Q chunks
+  unsigned char* sQB = sQ32 + C::kQStages * C::kQ32Bytes;            // kQBBufs x (hi tile, lo tile)
+  unsigned char* sKV = sQB + C::kQBBufs * C::kQBBytes;               // kKVBufs x (K_hi chunks, K_lo chunks, V chunks)
+  float* xacc = reinterpret_cast<float*>(sKV + C::kKVBufs * C::kKVBytes);  // [2][QT][kTFew][128]
+  TBarriers* bars = reinterpret_cast<TBarriers*>(xacc + 2 * QT * kTFew * 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int tile0 = blockIdx.x * QT;
+  const int n_qt = min(QT, (N + 127) / 128 - tile0);
+  const int hpg = H / static_cast<int>(gridDim.z);        // heads of this CTA (gridDim.z > 1: cluster along the heads)
+  const int h_begin = static_cast<int>(blockIdx.z) * hpg;
+  const int n_steps = hpg * n_qt;                          // step s = hl * n_qt + qt
+  const bool want_heat = (maps != nullptr) && (b >= b_first);
+
+  if (tid == 8 * 32) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_v);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&bars->q32_full[i], 1); mbar_init(&bars->q32_empty[i], kTConvThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->qb_full[i], kTConvThreads); mbar_init(&bars->qb_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 128); mbar_init(&bars->p_full[i], 128);
+      mbar_init(&bars->pv_done[i], 1); mbar_init(&bars->o_free[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  float hsum[kTFew];  // softmax warpgroup 0 after the last head: this row's head sums (query tile 0) for the cluster combine
+#pragma unroll
+  for (int t = 0; t < kTFew; ++t) hsum[t] = 0.f;
+
+  if (warp == 8) {
+    // ============================== TMA producer ==============================
+    int st = 0;
+    uint32_t ph = 0;
+    for (int hl = 0; hl < hpg; ++hl) {
+      const int h = h_begin + hl, kvb = hl % C::kKVBufs;
+      mbar_wait(&bars->kv_empty[kvb], ((hl / C::kKVBufs) & 1) ^ 1);
+      if (elect_one()) {
+        unsigned char* base = sKV + kvb * C::kKVBytes;
+        mbar_expect_tx(&bars->kv_full[kvb], C::kKVBytes);
+#pragma unroll
+        for (int c = 0; c < C::kNC; ++c) {
+          tma_load_4d(&map_khi, &bars->kv_full[kvb], base + c * kTTile, c * W, h, 0, b);
+          tma_load_4d(&map_klo, &bars->kv_full[kvb], base + (C::kNC + c) * kTTile, c * W, h, 0, b);
+        }
+#pragma unroll
+        for (int c = 0; c < C::kVC; ++c)
+          tma_load_4d(&map_v, &bars->kv_full[kvb], base + (2 * C::kNC + c) * kTTile, c * 64, h, 0, b);
+      }
+      __syncwarp();
+      for (int qt = 0; qt < n_qt; ++qt) {
+        for (int c = 0; c < C::kNC; ++c) {
+          mbar_wait(&bars->q32_empty[st], ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&bars->q32_full[st], C::kQ32Bytes);
+            tma_load_4d(&map_q, &bars->q32_full[st], sQ32 + st * C::kQ32Bytes, c * W, h, (tile0 + qt) * 128, b);
+          }
+          __syncwarp();
+          if (++st == C::kQStages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================== MMA issuer (warp converged; tcgen05.mma / commit under elect.sync) ==============
+    constexpr uint32_t idesc_qk = make_idesc(128, kTMPad, 0);
+    constexpr uint32_t idesc_pv = make_idesc(128, C::kDP, 1);
+    const uint64_t qb_desc0 = make_sdesc(smem_u32(sQB), 16, 1024);
+    const uint64_t k_desc0 = make_sdesc(smem_u32(sKV), 16, 1024);
+    const uint64_t v_desc0 = make_sdesc(smem_u32(sKV), kTTile, 1024);
+    int gq = 0;          // running Q chunk counter (operand-buffer ring position)
+    int kv_waited = -1;  // last head whose K/V block has been observed
+    auto issue_qk = [&](int j) {  // S[j & 1] = Q(step j) K_h^T as three bf16 MMA groups per column chunk
+      const int sb = j & 1, hl = j / n_qt, kvb = hl % C::kKVBufs;
+      if (hl > kv_waited) {
+        mbar_wait(&bars->kv_full[kvb], (hl / C::kKVBufs) & 1);
+        kv_waited = hl;
+      }
+      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j - 2) >> 1) & 1);  // S(j-2) is in the softmax warpgroup's registers
+      for (int c = 0; c < C::kNC; ++c, ++gq) {
+        const int cb = gq % C::kQBBufs;
+        mbar_wait(&bars->qb_full[cb], (gq / C::kQBBufs) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = cb * C::kQBBytes, a_lo = a_hi + 128 * 128;
+          const uint32_t b_hi = kvb * C::kKVBytes + c * kTTile, b_lo = b_hi + C::kNC * kTTile;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {  // hi*hi, lo*hi, hi*lo
+            const uint32_t ao = (g == 1) ? a_lo : a_hi, bo = (g == 2) ? b_lo : b_hi;
+#pragma unroll
+            for (int kk = 0; kk < C::kWP / 16; ++kk)
+              umma_ss(tmem + sb * kTSlot, qb_desc0 + static_cast<uint64_t>((ao + kk * 32) >> 4),
+                      k_desc0 + static_cast<uint64_t>((bo + kk * 32) >> 4), idesc_qk, !(c == 0 && g == 0 && kk == 0));
+          }
+          umma_commit(&bars->qb_empty[cb]);
+          if (c == C::kNC - 1) umma_commit(&bars->s_full[sb]);
+        }
+        __syncwarp();
+      }
+    };
+    auto issue_pv = [&](int s) {
+      const int sb = s & 1, hl = s / n_qt, kvb = hl % C::kKVBufs;
+      const uint32_t php = (s >> 1) & 1;
+      mbar_wait(&bars->p_full[sb], php);
+      mbar_wait(&bars->o_free[sb], php ^ 1);  // O[sb] of step s-2 drained
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < kTMPad / 16; ++kk)
+          umma_ts(tmem + C::kColO + sb * C::kDP, tmem + C::kColP + sb * C::kPStride + kk * 8,
+                  v_desc0 + static_cast<uint64_t>((kvb * C::kKVBytes + 2 * C::kNC * kTTile + kk * 2048) >> 4), idesc_pv,
+                  kk != 0);
+        umma_commit(&bars->pv_done[sb]);
+        if (s == hl * n_qt + n_qt - 1) umma_commit(&bars->kv_empty[kvb]);  // last step of this head: its K/V block is free
+      }
+      __syncwarp();
+    };
+    // QK runs up to two steps ahead of PV (one when P aliases S), but never into a head whose K/V block cannot be
+    // resident yet (the block of head h + kKVBufs replaces head h's, which PV(last step of h) still reads)
+    int nq = 0;
+    for (int s = 0; s < n_steps; ++s) {
+      const int hs = s / n_qt;
+      while (nq < n_steps && nq <= s + (C::kAliasP ? 1 : 2) && (nq / n_qt) <= hs + (C::kKVBufs - 1)) {
+        issue_qk(nq);
+        ++nq;
+      }
+      issue_pv(s);
+    }
+  } else if (warp >= kTConvWarp0) {
+    // ============================== converters: fp32 Q chunk -> bf16 hi / lo UMMA operand tiles ======================
+    const int ct = tid - kTConvWarp0 * 32;
+    int st = 0, g = 0;
+    uint32_t ph = 0;
+    const int n_chunks = n_steps * C::kNC;
+    for (; g < n_chunks; ++g) {
+      const int cb = g % C::kQBBufs;
+      mbar_wait(&bars->q32_full[st], ph);
+      mbar_wait(&bars->qb_empty[cb], ((g / C::kQBBufs) & 1) ^ 1);  // the MMAs that read this operand buffer have completed
+      tc_fence_after();
+      const unsigned char* src = sQ32 + st * C::kQ32Bytes;
+      unsigned char* dhi = sQB + cb * C::kQBBytes;
+      unsigned char* dlo = dhi + 128 * 128;
+#pragma unroll
+      for (int rr = 0; rr < 128 / kTConvThreads; ++rr) {
+        const int r = ct + rr * kTConvThreads;
+        const float4* p = reinterpret_cast<const float4*>(src + r * (W * 4));
+        unsigned char* rhi = dhi + r * 128;
+        unsigned char* rlo = dlo + r * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < W / 8; ++c16) {
+          const float4 x = p[2 * c16], y = p[2 * c16 + 1];
+          const float f[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+          uint32_t uh[4], ul[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uh[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+            const float h0 = __uint_as_float(uh[i] << 16), h1 = __uint_as_float(uh[i] & 0xFFFF0000u);
+            ul[i] = pack_bf16(f[2 * i] - h0, f[2 * i + 1] - h1);
+          }
+          const int off = (c16 ^ (r & 7)) << 4;  // 128B swizzle: 16-byte piece index XOR row-in-atom
+          st_shared_v4(rhi + off, uh[0], uh[1], uh[2], uh[3]);
+          st_shared_v4(rlo + off, ul[0], ul[1], ul[2], ul[3]);
+        }
+#pragma unroll
+        for (int c16 = W / 8; c16 < C::kWP / 8; ++c16) {  // zero padding up to the MMA K extent (d chunk 40 -> 48)
+          const int off = (c16 ^ (r & 7)) << 4;
+          st_shared_v4(rhi + off, 0u, 0u, 0u, 0u);
+          st_shared_v4(rlo + off, 0u, 0u, 0u, 0u);
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's shared-memory reads
+      mbar_arrive(&bars->qb_full[cb]);
+      mbar_arrive(&bars->q32_empty[st]);
+      if (++st == C::kQStages) { st = 0; ph ^= 1u; }
+    }
+  } else {
+    // ============================== softmax warpgroups (thread == query row) ==============================
+    const int wg = warp >> 2;  // takes the steps s with s % 2 == wg (its own S/P and O slots)
+    const int row = tid & 127;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    float* myacc = xacc + static_cast<size_t>(wg) * QT * kTFew * 128 + row;  // + (qt * kTFew + t) * 128
+    for (int i = 0; i < QT * kTFew; ++i) myacc[i * 128] = 0.f;
+
+    auto drain_o = [&](int g) {  // O of step g: TMEM -> OutT -> global
+      const int ob = g & 1, ghl = g / n_qt, gq = g - ghl * n_qt;
+      const int n = (tile0 + gq) * 128 + row;
+      mbar_wait(&bars->pv_done[ob], (g >> 1) & 1);
+      tc_fence_after();
+      OutT* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + (h_begin + ghl) * D;
+#pragma unroll
+      for (int c = 0; c < C::kDP / 16; ++c) {
+        float o[16];
+        tmem_ld16(tmem + lane_base + C::kColO + ob * C::kDP + c * 16, o);
+        tmem_wait_ld();
+        if (n < N) {
+          if constexpr (std::is_same<OutT, float>::value) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (c * 16 + q4 * 4 + 4 <= D)
+                *reinterpret_cast<float4*>(orow + c * 16 + q4 * 4) = make_float4(o[q4 * 4], o[q4 * 4 + 1], o[q4 * 4 + 2], o[q4 * 4 + 3]);
+          } else {
+            uint4 lo, hi;
+            lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
+            hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
+            if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+            if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->o_free[ob]);
+    };
+
+    int prev_s = -1;
+    for (int s = wg; s < n_steps; s += 2) {
+      const int sb = wg, hl = s / n_qt, qt = s - hl * n_qt, h = h_begin + hl;
+      const int n = (tile0 + qt) * 128 + row;
+      mbar_wait(&bars->s_full[sb], (s >> 1) & 1);
+      tc_fence_after();
+      float sv[96];
+      float sel[kTFew];
+      const uint32_t s_taddr = tmem + lane_base + sb * kTSlot;
+      tmem_ld32(s_taddr, sv);
+      tmem_ld32(s_taddr + 32, sv + 32);
+      tmem_ld16(s_taddr + 64, sv + 64);
+      if (want_heat) {
+#pragma unroll
+        for (int t = 0; t < kTFew; ++t)
+          if (t < tl.n) sel[t] = tmem_ld1(s_taddr + tl.idx[t]);
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bars->s_free[sb]);  // S(s) is in registers
+      if (M >= 64) {
+#pragma unroll
+        for (int i = 64; i < kTMPad; ++i)
+          if (i >= M) sv[i] = -INFINITY;
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTMPad; ++i)
+          if (i >= M) sv[i] = -INFINITY;
+      }
+      static_assert((kTMPad - 6) % 4 == 2, "max reduction below assumes 80 columns");
+      float mx0 = fmax3(sv[0], sv[1], sv[2]), mx1 = fmax3(sv[3], sv[4], sv[5]);
+#pragma unroll
+      for (int i = 6; i + 4 <= kTMPad; i += 4) {
+        mx0 = fmax3(mx0, sv[i], sv[i + 1]); mx1 = fmax3(mx1, sv[i + 2], sv[i + 3]);
+      }
+      mx0 = fmax3(mx0, sv[kTMPad - 2], sv[kTMPad - 1]);
+      const float m = fmaxf(mx0, mx1) * scale_log2;
+      const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2), negm2 = pack_f32x2(-m, -m);
+      uint64_t sum2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < kTMPad; i += 2) {
+        float a, b2;
+        unpack_f32x2(ffma2(pack_f32x2(sv[i], sv[i + 1]), scale2, negm2), a, b2);
+        sv[i] = ex2(a); sv[i + 1] = ex2(b2);
+        sum2 = fadd2(sum2, pack_f32x2(sv[i], sv[i + 1]));
+      }
+      float sum0, sum1;
+      unpack_f32x2(sum2, sum0, sum1);
+      const float inv_l = 1.0f / (sum0 + sum1);
+      const uint64_t inv2 = pack_f32x2(inv_l, inv_l);
+#pragma unroll
+      for (int i = 0; i < kTMPad; i += 2)  // normalised probabilities: PV needs no later division
+        unpack_f32x2(fmul2(pack_f32x2(sv[i], sv[i + 1]), inv2), sv[i], sv[i + 1]);
+      if (want_heat) {
+#pragma unroll
+        for (int t = 0; t < kTFew; ++t) {
+          if (t < tl.n) {
+            const float pt = ex2(fmaf(sel[t], scale_log2, -m)) * inv_l;  // same ops as sv[idx[t]] above
+            if (tl.per_head) {  // DAAM-style: one plane per (batch, head, token), no head mean
+              if (n < N) {
+                float* ptr = maps + ((static_cast<long long>(b - b_first) * H + h) * tl.n + t) * N + n;
+                if (accumulate) atomicAdd(ptr, pt);  // result-less RED: one thread per element and launch
+                else *ptr = pt;
+              }
+            } else {
+              myacc[(qt * kTFew + t) * 128] += pt;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = kTMPad; i < 96; ++i) sv[i] = 0.f;
+      if (prev_s >= 0) drain_o(prev_s);  // also: PV(prev_s) has finished reading this slot's P columns
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t u[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = pack_bf16(sv[c * 32 + 2 * i], sv[c * 32 + 2 * i + 1]);
+        tmem_st16(tmem + lane_base + C::kColP + sb * C::kPStride + c * 16, u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->p_full[sb]);
+      prev_s = s;
+    }
+    if (prev_s >= 0) drain_o(prev_s);
+    tc_fence_before();
+    // ---- heat: warpgroup 0 adds the two warpgroups' head sums (fixed order) and writes the mean over heads ----
+    if (want_heat && !tl.per_head) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (wg == 0) {
+        const float* other = myacc + static_cast<size_t>(QT) * kTFew * 128;
+        const float inv_h = 1.0f / static_cast<float>(H);
+        for (int qt = 0; qt < n_qt; ++qt) {
+          const int n = (tile0 + qt) * 128 + row;
+#pragma unroll
+          for (int t = 0; t < kTFew; ++t) {
+            if (t < tl.n) {
+              const float sum = myacc[(qt * kTFew + t) * 128] + other[(qt * kTFew + t) * 128];
+              if (gridDim.z > 1) {
+                if (qt == 0) hsum[t] = sum;  // (cluster launches have QT == 1)
+              } else if (n < N) {
+                float* ptr = maps + (static_cast<long long>(b - b_first) * tl.n + t) * N + n;
+                if (accumulate) atomicAdd(ptr, sum * inv_h);  // (RED: same value as load + add + store, no load)
+                else *ptr = sum * inv_h;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (gridDim.z > 1 && want_heat && !tl.per_head) {
+    // head groups -> one heat row: partial sums of ranks 1.. go to the leader's (now idle) Q ring
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = static_cast<int>(blockIdx.z), hsz = static_cast<int>(gridDim.z);
+    float* xc = reinterpret_cast<float*>(smem);  // [hsz - 1][kTFew][128]
+    cluster.sync();  // every CTA of the cluster has finished its TMA loads and MMAs
+    if (warp < 4 && rank > 0) {
+      float* remote = cluster.map_shared_rank(xc, 0) + (rank - 1) * (kTFew * 128) + tid;
+#pragma unroll
+      for (int t = 0; t < kTFew; ++t)
+        if (t < tl.n) remote[t * 128] = hsum[t];
+    }
+    cluster.sync();
+    if (warp < 4 && rank == 0 && tile0 * 128 + tid < N) {
+      const float inv_h = 1.0f / static_cast<float>(H);
+      float* dst = maps + static_cast<long long>(b - b_first) * tl.n * N + tile0 * 128 + tid;
+#pragma unroll
+      for (int t = 0; t < kTFew; ++t) {
+        if (t < tl.n) {
+          float sum = hsum[t];
+          for (int r = 1; r < hsz; ++r) sum += xc[((r - 1) * kTFew + t) * 128 + tid];  // fixed order
+          float* ptr = dst + static_cast<long long>(t) * N;
+          if (accumulate) atomicAdd(ptr, sum * inv_h);
+          else *ptr = sum * inv_h;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace sm100
+
+typedef CUresult (*EncodeTiledFnX3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 [B, rows, H*d] viewed as (d, H, rows, B); box (box_cols, 1, box_rows, 1), dense rows (no swizzle), zero fill
+static int make_head_map_f32(CUtensorMap* map, const void* base, int B, int H, int rows, int d, int box_cols, int box_rows) {
+  static EncodeTiledFnX3 enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFnX3>(p);
+  }();
+  if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t C = static_cast<cuuint64_t>(H) * d;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(rows),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(d) * 4, C * 4, static_cast<cuuint64_t>(rows) * C * 4};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 Q) failed (CUresult %d)", static_cast<int>(r));
+  return AGENDA_OK;
+}
+
+template <int D, typename OutT>
+static int launch_cross_x3(const float* q, const void* k_hi, const void* k_lo, const void* v, void* out, int B, int H,
+                           int N, int M, float scale, const TokenList& tl, int b_first, float* maps, int accumulate,
+                           cudaStream_t stream) {
+  using C = sm100::TCfg<D>;
+  CUtensorMap mq, mkh, mkl, mv;
+  int rc;
+  if ((rc = make_head_map_f32(&mq, q, B, H, N, D, C::kW, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mkh, k_hi, B, H, M, D, sm100::kTMPad)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mkl, k_lo, B, H, M, D, sm100::kTMPad)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, M, D, sm100::kTMPad)) != AGENDA_OK) return rc;
+  const int n_tiles = (N + 127) / 128, sms = num_sms();
+  // query tiles per CTA: the smallest count that puts the launch into one wave (amortises the per-head K/V block)
+  int QT = 1;
+  while (QT < C::kMaxQT && ((n_tiles + QT - 1) / QT) * B > sms) ++QT;
+  dim3 grid((n_tiles + QT - 1) / QT, B, 1);
+  // few (batch, query tile) pairs: split the heads over a cluster along z while the grid still fits one wave
+  int hs = 1;
+  if (QT == 1 && !(maps && tl.per_head))
+    while (hs < 4 && H % (hs * 2) == 0 && static_cast<long long>(grid.x) * grid.y * hs * 2 <= sms) hs *= 2;
+  grid.z = hs;
+  const size_t smem = sm100::t_smem_bytes<D>(QT);
+  auto kern = sm100::attn_cross_sm100_x3_kernel<D, OutT>;
+  static bool attr_set = false;  // (per template instantiation; the value is the maximum any launch needs)
+  if (!attr_set) {
+    AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(sm100::t_smem_bytes<D>(C::kMaxQT))));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(sm100::kTThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = hs;
+  cfg.attrs = attr; cfg.numAttrs = hs > 1 ? 1 : 0;
+  AGENDA_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mkh, mkl, mv, static_cast<OutT*>(out), maps, tl, H, N, M, QT, b_first,
+                                 accumulate, scale * 1.4426950408889634f));
+  AGENDA_LAUNCH_CHECK("attn_cross_sm100_x3_kernel");
+  return AGENDA_OK;
+}
+
+int build_token_list(const char* who, const int32_t* token_idx, int T, int M, TokenList* tl);
+
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" int agenda_attn_cross_fwd_heat_x3(const float* q, const void* k_hi, const void* k_lo, const void* v, void* out,
+                                             int out_dtype, int B, int H, int N, int M, int d, float scale,
+                                             const int32_t* token_idx, int T, int b_first, int per_head, float* maps,
+                                             int accumulate, void* stream) {
+  const char* who = "attn_cross_fwd_heat_x3";
+  if (!q || !k_hi || !k_lo || !v || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (out_dtype != AGENDA_F32 && out_dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "%s: out_dtype %d", who, out_dtype);
+  if (B <= 0 || H <= 0 || N <= 0 || M <= 0 || d <= 0 || B > 65535)
+    return fail(AGENDA_ERR_BAD_SHAPE, "%s: B=%d H=%d N=%d M=%d d=%d", who, B, H, N, M, d);
+  if (M > sm100::kTMPad) return fail(AGENDA_ERR_UNSUPPORTED, "%s: M=%d > %d", who, M, sm100::kTMPad);
+  if (b_first < 0 || b_first > B) return fail(AGENDA_ERR_BAD_SHAPE, "%s: b_first=%d, B=%d", who, b_first, B);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_hi) | reinterpret_cast<uintptr_t>(k_lo) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: q/k_hi/k_lo/v/out must be 16-byte aligned", who);
+  TokenList tl;
+  tl.n = 0;
+  tl.per_head = 0;
+  if (maps != nullptr) {
+    int rc = build_token_list(who, token_idx, T, M, &tl);
+    if (rc != AGENDA_OK) return rc;
+    if (tl.n > sm100::kTFew) return fail(AGENDA_ERR_UNSUPPORTED, "%s: T=%d > %d heat tokens", who, tl.n, sm100::kTFew);
+    if (reinterpret_cast<uintptr_t>(maps) & 3) return fail(AGENDA_ERR_MISALIGNED, "%s: maps", who);
+    tl.per_head = per_head ? 1 : 0;
+  }
+  float* mp = tl.n ? maps : nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define AGENDA_X3(DD)                                                                                                    \
+  case DD:                                                                                                               \
+    return out_dtype == AGENDA_F32                                                                                       \
+               ? launch_cross_x3<DD, float>(q, k_hi, k_lo, v, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st)  \
+               : launch_cross_x3<DD, __nv_bfloat16>(q, k_hi, k_lo, v, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st);
+  switch (d) {
+    AGENDA_X3(40)
+    AGENDA_X3(64)
+    AGENDA_X3(80)
+    AGENDA_X3(160)
+    default: return fail(AGENDA_ERR_UNSUPPORTED, "%s: head dim %d not in {40,64,80,160}", who, d);
+  }
+#undef AGENDA_X3
+}

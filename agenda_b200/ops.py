@@ -127,6 +127,61 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     return out
 
 
+def split_bf16(x: torch.Tensor):
+    """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): x == hi + lo to 2^-17 relative.  The operand form
+    of the split-precision cross-attention kernel (agenda_attn_cross_fwd_heat_x3) for the key projection."""
+    x = x.float()
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def attn_cross_heat_x3(q: torch.Tensor, k_hi: torch.Tensor, k_lo: torch.Tensor, v: torch.Tensor, heads: int,
+                       maps: Optional[torch.Tensor], token_idx: Optional[Sequence[int]] = None, b_first: int = 0,
+                       accumulate: bool = False, scale: Optional[float] = None, per_head: bool = False,
+                       out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Cross-attention + heat epilogue with fp32-accurate logits on the bf16 tensor cores (hook.py:108-114 at the
+    reference's fp32 precision; heat maps to ~1e-6 of an fp32 softmax).
+
+    q fp32 [B,N,H*d] (to_q output with fp32 accumulation); k_hi / k_lo = split_bf16(K) of the fp32 key projection
+    [B,M,H*d]; v bf16 [B,M,H*d].  maps / token_idx / b_first / accumulate / per_head as in attn_cross_heat (at most 8
+    tokens).  Returns out [B,N,H*d] in `out_dtype` (bf16 or fp32)."""
+    q = _dev(q, "q", torch.float32)
+    k_hi, k_lo = _dev(k_hi, "k_hi", torch.bfloat16), _dev(k_lo, "k_lo", torch.bfloat16)
+    v = _dev(v, "v", torch.bfloat16)
+    B, N, C = q.shape
+    M = k_hi.shape[1]
+    if k_lo.shape != k_hi.shape or v.shape != k_hi.shape or k_hi.shape[0] != B or k_hi.shape[2] != C:
+        raise ValueError(f"k_hi/k_lo/v must be [{B},M,{C}], got {tuple(k_hi.shape)} {tuple(k_lo.shape)} {tuple(v.shape)}")
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out_dtype must be bfloat16 or float32")
+    out = torch.empty((B, N, C), dtype=out_dtype, device=q.device)
+    if maps is not None:
+        if token_idx is None:
+            raise ValueError("attn_cross_heat_x3 needs explicit token indices (at most 8)")
+        maps = _dev(maps, "maps", torch.float32)
+        T = len(token_idx)
+        lead = (B - b_first, heads, T) if per_head else (B - b_first, T)
+        n_lead = 1
+        for x in lead:
+            n_lead *= x
+        if tuple(maps.shape[:len(lead)]) != lead or maps.numel() != N * n_lead:
+            raise ValueError(f"maps must be {list(lead)} + [{N}] (any trailing shape of {N} elements), "
+                             f"got {tuple(maps.shape)}")
+        if not maps.is_contiguous():
+            raise ValueError("maps must be contiguous (it is written in place)")
+        idx = (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
+        mp = maps.data_ptr()
+    else:
+        T, idx, mp = 0, None, None
+    _lib.call("agenda_attn_cross_fwd_heat_x3", q.data_ptr(), k_hi.data_ptr(), k_lo.data_ptr(), v.data_ptr(),
+              out.data_ptr(), _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32, B, heads, N, M, d, scale, idx, T,
+              int(b_first), int(bool(per_head)), mp, int(bool(accumulate)), _stream())
+    return out
+
+
 def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
                    d_maps: Optional[torch.Tensor], heads: int, token_idx: Optional[Sequence[int]] = None,
                    b_first: int = 0, scale: Optional[float] = None):

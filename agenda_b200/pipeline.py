@@ -16,6 +16,7 @@ import torch
 
 from . import ops
 from .processor import UNetCrossAttentionHooker
+from .mixed import compensate_cross_projections
 from .sd_attention import AttentionStack, BlockSpec, sd15_blocks, sd21_blocks
 
 
@@ -23,10 +24,17 @@ class HeatmapPipeline:
     def __init__(self, blocks: Optional[List[BlockSpec]] = None, context_dim: int = 768,
                  tokens: Sequence[int] = (5, 6, 7), num_steps: int = 50, latent_hw: int = 64, image_size: int = 112,
                  dtype: torch.dtype = torch.bfloat16, device="cuda", thr: float = 0.5, max_boxes: int = 64,
-                 seed: int = 0, precision: str = "bf16", use_cuda_graph: bool = True):
+                 seed: int = 0, precision: str = "bf16", use_cuda_graph: bool = True, cross_logits: str = "fp32",
+                 compensate_weights: bool = True):
         self.device = torch.device(device)
         self.blocks = blocks if blocks is not None else sd15_blocks(latent_hw)
-        self.stack = AttentionStack(self.blocks, context_dim, seed).to(device=self.device, dtype=dtype)
+        # the "checkpoint" is fp32 (AttentionStack(blocks, context_dim, seed) reproduces it for a reference run); a 16-bit
+        # pipeline keeps the fp32 value of the projections that feed the heat-map logits as weight + weight_lo
+        self._weight_seed = seed
+        stack = AttentionStack(self.blocks, context_dim, seed)
+        if dtype != torch.float32 and compensate_weights and cross_logits == "fp32":
+            compensate_cross_projections(stack)
+        self.stack = stack.to(device=self.device, dtype=dtype)
         self.tokens = list(tokens)
         if len(self.tokens) < 3:
             raise ValueError("need at least (object, fg, bg) token indices")
@@ -37,16 +45,27 @@ class HeatmapPipeline:
         self.thr = thr
         self.max_boxes = max_boxes
         self.proc = UNetCrossAttentionHooker(is_train=False, latent_hw=latent_hw, tokens=self.tokens,
-                                             precision=precision)
+                                             precision=precision, cross_logits=cross_logits)
         self.stack.set_attn_processor(self.proc)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._graph_key = None
 
+    def reference_stack(self) -> AttentionStack:
+        """The fp32 "checkpoint" this pipeline was built from, on the CPU (deterministic in (blocks, context_dim, seed)):
+        what a reference run, or the oracle in the tests, uses."""
+        return AttentionStack(self.blocks, self.stack.context_dim, self._weight_seed)
+
     # ------------------------------------------------------------------------------------------------------
-    def make_inputs(self, n_images: int, seed: int = 0, pinned_host: bool = False):
-        """Synthetic inputs for `n_images` (UNet batch = 2*n_images with classifier-free guidance)."""
-        hs, ctx = self.stack.make_inputs(2 * n_images, "cpu", self.dtype, seed)
+    def make_inputs(self, n_images: int, seed: int = 0, pinned_host: bool = False, seeds: Optional[Sequence[int]] = None):
+        """Synthetic inputs for `n_images` (UNet batch = 2*n_images with classifier-free guidance).  With `seeds` (one
+        per image) every image's inputs depend on its own seed only, whatever batch or rank it lands in."""
+        if seeds is not None:
+            if len(seeds) != n_images:
+                raise ValueError("need one seed per image")
+            hs, ctx = self.stack.make_inputs_for_seeds(seeds, "cpu", self.dtype)
+        else:
+            hs, ctx = self.stack.make_inputs(2 * n_images, "cpu", self.dtype, seed)
         if pinned_host:
             return {k: v.pin_memory() for k, v in hs.items()}, ctx.pin_memory()
         return {k: v.to(self.device) for k, v in hs.items()}, ctx.to(self.device)
@@ -60,7 +79,8 @@ class HeatmapPipeline:
         # every run is a new batch of images: the prompt K/V are projected once per batch here (not once per denoising
         # step as in the reference, hook.py:101-102) — also picks up an embedding overwritten in place since the last run
         proc.refresh_context_kv(force=True)
-        key = (tuple((k, v.data_ptr()) for k, v in sorted(hs.items())), ctx.data_ptr())
+        key = (tuple((k, v.data_ptr(), tuple(v.shape), v.dtype) for k, v in sorted(hs.items())), ctx.data_ptr(),
+               tuple(ctx.shape), ctx.dtype)
         if self.use_cuda_graph:
             if self._graph is None or self._graph_key != key:
                 # warm the allocator/cuBLAS handles outside capture, then capture one denoising step's 32 calls

@@ -44,11 +44,21 @@ from . import ops
 
 class UNetCrossAttentionHooker:
     def __init__(self, is_train: bool = True, latent_hw: int = 64, tokens: Optional[Sequence[int]] = None,
-                 precision: str = "bf16", record_maps: bool = False, aggregate: str = "hook"):
+                 precision: str = "bf16", record_maps: bool = False, aggregate: str = "hook",
+                 cross_logits: str = "fp32"):
         if aggregate not in ("hook", "daam"):
             raise ValueError("aggregate must be 'hook' or 'daam'")
+        if cross_logits not in ("fp32", "bf16"):
+            raise ValueError("cross_logits must be 'fp32' (split-precision tensor-core kernel) or 'bf16'")
         self.aggregate = aggregate
+        # precision="bf16" runs the attention cores on the tensor cores.  For cross-attention, whose probabilities ARE
+        # the product (the heat maps, held to 1e-4 against the reference's fp32 run), cross_logits="fp32" keeps the
+        # logits at fp32 accuracy: to_q with fp32 accumulation AND fp32 output, the key projection in fp32, and the
+        # split-precision kernel (agenda_attn_cross_fwd_heat_x3: Q_hi K_hi + Q_lo K_hi + Q_hi K_lo on bf16 tensor
+        # cores).  cross_logits="bf16" rounds Q and K to bf16 first (faster, heat maps to ~2e-3 only).
+        self.cross_logits = "bf16" if os.environ.get("AGENDA_CROSS_X3", "1") == "0" else cross_logits
         self._layer_sums = {}   # aggregate="daam": id(attn) -> [B',H,T,h,w] fp32 sum over denoising steps
+        self._layer_mods = {}   # id(attn) -> attn (held so that a freed module's id cannot be reused for another)
         # self-attention, bf16: to_q/to_k/to_v (hook.py:93,101-102) act on the same hidden_states, so they run as ONE
         # GEMM with the concatenated weights (hidden_states read once instead of three times) and the attention kernel
         # reads q/k/v as column slices of its output.  id(attn) -> (weight versions, fused [3C,C] weight)
@@ -124,47 +134,99 @@ class UNetCrossAttentionHooker:
         # d = 40 layers: scale * log2(e) is folded into the q rows (one rounding of the scaled fp32 weight to bf16), so the
         # attention kernel's scores are the base-2 exponents themselves (ABI: scale == 0)
         prescale = self.prescale_q and ws[0].shape[0] // attn.heads == 40
-        key = tuple((w.data_ptr(), w._version) for w in ws) + (prescale, float(attn.scale))
+        key = tuple((w.data_ptr(), 0 if w.is_inference() else w._version) for w in ws) + (prescale, float(attn.scale))
         hit = self._qkv_weights.get(id(attn))
         if hit is None or hit[0] != key:
             wq = ws[0].detach()
             if prescale:
                 wq = (wq.float() * (float(attn.scale) * 1.4426950408889634)).to(torch.bfloat16)
-            hit = (key, torch.cat([wq, ws[1].detach(), ws[2].detach()], 0).contiguous(), prescale)
+            # (the module is kept in the entry: a freed module's id() could otherwise be reused by another one)
+            hit = (key, torch.cat([wq, ws[1].detach(), ws[2].detach()], 0).contiguous(), prescale, attn)
             self._qkv_weights[id(attn)] = hit
         return hit[1], hit[2]
 
     @staticmethod
     def _kv_state(attn, ehs):
         wk, wv = attn.to_k.weight, attn.to_v.weight
-        return (ehs._version, tuple(ehs.shape), wk.data_ptr(), wk._version, wv.data_ptr(), wv._version)
+        # (inference tensors carry no version counter: they cannot be modified in place outside inference mode either)
+        ver = 0 if ehs.is_inference() else ehs._version
+        return (ver, tuple(ehs.shape), wk.data_ptr(), 0 if wk.is_inference() else wk._version, wv.data_ptr(),
+                0 if wv.is_inference() else wv._version)
 
-    def _context_kv(self, attn, ehs):
+    @staticmethod
+    def _full_weight(lin):
+        """fp32 weight of a projection; modules prepared by mixed.compensate_cross_projections carry the bf16 residual
+        `weight_lo` of their fp32 checkpoint value beside the bf16 `weight` (W = weight + weight_lo to 2^-17)."""
+        w = lin.weight.detach().float()
+        lo = getattr(lin, "weight_lo", None)
+        return w if lo is None else w + lo.float()
+
+    def _project_context(self, attn, ehs, split: bool):
+        """to_k / to_v of the prompt embedding (hook.py:101-102).  split=False: (K, V) in the modules' own precision.
+        split=True (cross_logits="fp32"): K in fp32 — from the fp32 weight, or weight + weight_lo — handed over as the
+        (K_hi, K_lo) bf16 pair the split-precision kernel takes, and V in bf16: (K_hi, K_lo, V)."""
+        if not split:
+            return attn.to_k(ehs), attn.to_v(ehs)
+        k32 = torch.nn.functional.linear(ehs.float(), self._full_weight(attn.to_k))
+        bias = getattr(attn.to_k, "bias", None)
+        if bias is not None:
+            k32 = k32 + bias.float()
+        k_hi, k_lo = ops.split_bf16(k32)
+        return k_hi, k_lo, attn.to_v(ehs).to(torch.bfloat16).contiguous()
+
+    def _context_kv(self, attn, ehs, split: bool = False):
+        if torch.is_grad_enabled() and (ehs.requires_grad or attn.to_k.weight.requires_grad
+                                        or attn.to_v.weight.requires_grad):
+            return self._project_context(attn, ehs, split)  # never cache tensors that carry an autograd graph
         ent = self._ctx_kv.get(id(attn))
-        state = self._kv_state(attn, ehs)
+        state = self._kv_state(attn, ehs) + (split,)
         if ent is not None and ent[0] is ehs and ent[1] == state:
-            return ent[2], ent[3]
-        key, value = attn.to_k(ehs), attn.to_v(ehs)
-        if torch.is_grad_enabled() and (key.requires_grad or value.requires_grad):
-            return key, value  # never cache tensors that carry an autograd graph
-        self._ctx_kv[id(attn)] = (ehs, state, key, value, attn)
-        return key, value
+            return ent[2]
+        tensors = self._project_context(attn, ehs, split)
+        self._ctx_kv[id(attn)] = (ehs, state, tensors, attn)
+        return tensors
 
     def refresh_context_kv(self, force: bool = False) -> None:
         """Recompute cached K / V IN PLACE from the tensor they were built from (only those whose source or weights
         changed, or all of them with `force`).  For callers that replay a captured CUDA graph of the processor calls
         after overwriting the prompt embedding in place (HeatmapPipeline): the graph reads the cached buffers, so they
         must be brought up to date outside the graph before the replays."""
-        for mod_id, (ehs, state, key, value, attn) in list(self._ctx_kv.items()):
-            new_state = self._kv_state(attn, ehs)
+        for mod_id, (ehs, state, tensors, attn) in list(self._ctx_kv.items()):
+            new_state = self._kv_state(attn, ehs) + (state[-1],)
             if new_state == state and not force:
                 continue
             if new_state[1] != state[1]:   # shape changed: rebuilt on the next call
                 del self._ctx_kv[mod_id]
                 continue
-            key.copy_(attn.to_k(ehs))
-            value.copy_(attn.to_v(ehs))
-            self._ctx_kv[mod_id] = (ehs, new_state, key, value, attn)
+            for dst, src in zip(tensors, self._project_context(attn, ehs, state[-1])):
+                dst.copy_(src)
+            self._ctx_kv[mod_id] = (ehs, new_state, tensors, attn)
+
+    @staticmethod
+    def _query_fp32(attn, hidden_states):
+        """to_q (hook.py:93) with an fp32 result.  fp32 activations: the module's own fp32 GEMM (what the reference
+        runs).  16-bit activations: one tensor-core GEMM with fp32 accumulation and fp32 OUTPUT (products of 16-bit
+        values are exact, so this is the fp32 projection of those activations and weights), plus the `weight_lo`
+        correction GEMM when the module carries its checkpoint's fp32 residual."""
+        lin = attn.to_q
+        w = getattr(lin, "weight", None)
+        if (hidden_states.dtype == torch.float32 or w is None or w.dtype != hidden_states.dtype
+                or type(lin) is not torch.nn.Linear):
+            return lin(hidden_states).float()
+        B, N, C = hidden_states.shape
+        x2 = hidden_states.reshape(B * N, C)
+        q = torch.mm(x2, w.t(), out_dtype=torch.float32)
+        lo = getattr(lin, "weight_lo", None)
+        if lo is not None:
+            q += torch.mm(x2, lo.to(x2.dtype).t(), out_dtype=torch.float32)
+        if lin.bias is not None:
+            q += lin.bias.float()
+        return q.view(B, N, -1)
+
+    def _use_x3(self, attn, query_dim: int, M: int) -> bool:
+        if self.precision != "bf16" or self.cross_logits != "fp32" or self.tokens is None or len(self.tokens) > 8:
+            return False
+        return M <= 80 and (query_dim // attn.heads) in (40, 64, 80, 160) and query_dim % attn.heads == 0
 
     def _accumulate(self, b_kept: int, n_tok: int, device) -> torch.Tensor:
         L = self.latent_hw
@@ -224,50 +286,68 @@ class UNetCrossAttentionHooker:
                 hidden_states = ops.attn_self_fused_qkv(qkv, attn.heads, scale=float(attn.scale), prescaled=prescaled)
                 hidden_states = attn.to_out[0](hidden_states)
                 return attn.to_out[1](hidden_states)
-        query = attn.to_q(hidden_states)
-
         is_cross_attn = encoder_hidden_states is not None
         if encoder_hidden_states is None:
             encoder_hidden_states = hidden_states
         elif attn.norm_cross is not None:
             encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
-
-        if is_cross_attn and self.cache_context_kv and attn.norm_cross is None:
-            key, value = self._context_kv(attn, encoder_hidden_states)
-        else:
-            key = attn.to_k(encoder_hidden_states)
-            value = attn.to_v(encoder_hidden_states)
         heads = attn.heads
         scale = float(attn.scale)
+        in_dtype = hidden_states.dtype
+
+        x3 = is_cross_attn and hidden_states.is_cuda and self._use_x3(attn, attn.to_q.weight.shape[0],
+                                                                       encoder_hidden_states.shape[1])
+        if x3:
+            query = self._query_fp32(attn, hidden_states)
+            if self.cache_context_kv and attn.norm_cross is None:
+                kv = self._context_kv(attn, encoder_hidden_states, split=True)
+            else:
+                kv = self._project_context(attn, encoder_hidden_states, True)
+            out_dtype = in_dtype if in_dtype in (torch.bfloat16, torch.float32) else torch.bfloat16
+
+            def cross(maps, accumulate, per_head=False):
+                o = ops.attn_cross_heat_x3(query, kv[0], kv[1], kv[2], heads, maps, self.tokens, b_first,
+                                           accumulate=accumulate, scale=scale, per_head=per_head, out_dtype=out_dtype)
+                return o if o.dtype == in_dtype else o.to(in_dtype)
+        else:
+            query = attn.to_q(hidden_states)
+            if is_cross_attn and self.cache_context_kv and attn.norm_cross is None:
+                key, value = self._context_kv(attn, encoder_hidden_states)
+            else:
+                key = attn.to_k(encoder_hidden_states)
+                value = attn.to_v(encoder_hidden_states)
+
+            def cross(maps, accumulate, per_head=False):
+                return ops.attn_cross_heat(query, key, value, heads, maps, self.tokens, b_first, accumulate=accumulate,
+                                           scale=scale, per_head=per_head)
 
         if is_cross_attn:
-            M = key.shape[1]
+            M = encoder_hidden_states.shape[1]
             n_tok = M if self.tokens is None else len(self.tokens)
             b_first = 0 if self.is_train else batch_size // 2  # hook.py:48-49: drop the unconditional half
             h = w = int(math.sqrt(sequence_length))
+            dev = hidden_states.device
             if self.aggregate == "daam":
                 if self.latent_hw // h == 8:  # daam drops the factor-8 maps
-                    hidden_states = ops.attn_cross_heat(query, key, value, heads, None, scale=scale)
+                    hidden_states = cross(None, False)
                 else:
                     buf = self._layer_sums.get(id(attn))
                     shape = (batch_size - b_first, heads, n_tok, h, w)
-                    if buf is None or tuple(buf.shape) != shape or buf.device != query.device:
-                        buf = torch.zeros(shape, dtype=torch.float32, device=query.device)
+                    if buf is None or tuple(buf.shape) != shape or buf.device != dev:
+                        buf = torch.zeros(shape, dtype=torch.float32, device=dev)
                         self._layer_sums[id(attn)] = buf
-                    hidden_states = ops.attn_cross_heat(query, key, value, heads, buf, self.tokens, b_first,
-                                                        accumulate=True, scale=scale, per_head=True)
+                        self._layer_mods[id(attn)] = attn   # keeps the module alive: its id() stays unique
+                    hidden_states = cross(buf, True, per_head=True)
                     self._count += 1
                 hidden_states = attn.to_out[0](hidden_states)
                 return attn.to_out[1](hidden_states)
-            acc = self._accumulate(batch_size - b_first, n_tok, query.device)
+            acc = self._accumulate(batch_size - b_first, n_tok, dev)
             if h == self.latent_hw and not self.record_maps:
                 # bicubic at scale 1 is the identity and probabilities are >= 0: accumulate from the epilogue
-                hidden_states = ops.attn_cross_heat(query, key, value, heads, acc, self.tokens, b_first,
-                                                    accumulate=True, scale=scale)
+                hidden_states = cross(acc, True)
             else:
-                maps = torch.empty((batch_size - b_first, n_tok, h, w), dtype=torch.float32, device=query.device)
-                hidden_states = ops.attn_cross_heat(query, key, value, heads, maps, self.tokens, b_first,
-                                                    accumulate=False, scale=scale)
+                maps = torch.empty((batch_size - b_first, n_tok, h, w), dtype=torch.float32, device=dev)
+                hidden_states = cross(maps, False)
                 ops.heat_upsample_accum(maps, acc)
                 if self.record_maps:
                     self.cross_attn_maps.append(maps)

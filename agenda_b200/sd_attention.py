@@ -123,6 +123,26 @@ class AttentionStack(nn.Module):
         ctx = torch.randn(batch, context_len, self.context_dim, generator=gen).to(device=device, dtype=dtype)
         return hs, ctx
 
+    def make_inputs_for_seeds(self, seeds, device, dtype, context_len: int = 77):
+        """Synthetic inputs of a batch of images, each a function of ITS OWN seed only (data_generation.py:56-59: an image
+        depends on (prompt, seed), never on which other seeds share its batch or rank).  UNet batch layout as under
+        classifier-free guidance: [uncond_0 .. uncond_{n-1}, cond_0 .. cond_{n-1}] (hook.py:48-49 keeps the second half)."""
+        shapes = []
+        for b in self.blocks:
+            if (b.hw, b.channels) not in shapes:
+                shapes.append((b.hw, b.channels))
+        per_image = []
+        for s in seeds:
+            gen = torch.Generator().manual_seed(100003 * int(s) + 17)
+            item = {k: torch.randn(2, k[0] * k[0], k[1], generator=gen) for k in shapes}
+            item["ctx"] = torch.randn(2, context_len, self.context_dim, generator=gen)
+            per_image.append(item)
+
+        def batch_of(key):
+            t = torch.cat([im[key][0:1] for im in per_image] + [im[key][1:2] for im in per_image], 0)
+            return t.to(device=device, dtype=dtype)
+        return {k: batch_of(k) for k in shapes}, batch_of("ctx")
+
     def forward(self, hidden_by_shape, context):
         """One UNet forward's worth of attention calls; returns the last output (keeps the work observable)."""
         out = None

@@ -99,6 +99,43 @@ def cpu_reference_sample(sample_steps: int = 6, seed: int = 0):
                                        f"extrapolated x{NUM_DENOISE_STEPS / sample_steps:g}"}
 
 
+def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
+    """max |heat - reference| over the first `n_check` images of the benchmarked batch.  Reference: the oracle port of
+    hook.py in fp32 on the CPU with the pipeline's FP32 checkpoint weights and the same synthetic activations (cross
+    attention only: the self-attention outputs do not feed the heat maps in this stack)."""
+    import numpy as np
+    import torch
+    from oracle import hook_oracle as O
+    pipe.use_cuda_graph = False
+    pipe.num_steps = 1
+    heat = pipe.run_device(hs_dev, ctx_dev)["heat"][:n_check].float().cpu().numpy()
+    rows = list(range(n_check)) + [n_img + i for i in range(n_check)]       # [uncond..., cond...] of the checked images
+    ref_stack = pipe.reference_stack()
+    ctx = ctx_dev[rows].float().cpu()
+    maps = []
+    with torch.no_grad():
+        for b, a2 in zip(pipe.blocks, ref_stack.attn2):
+            x = hs_dev[(b.hw, b.channels)][rows].float().cpu()
+            _, m = O.processor_call(x, ctx, a2.to_q.weight, a2.to_k.weight, a2.to_v.weight, a2.to_out[0].weight,
+                                    a2.to_out[0].bias, b.heads, False)
+            maps.append(m)
+    ref = O.global_heat_map(maps, pipe.latent_hw)[:, pipe.tokens]
+    n_px = n_diff = 0
+    box_changed = 0
+    for i in range(n_check):
+        for t in range(3):
+            a, r = O.heat_to_png_array(heat[i, t], pipe.image_size), O.heat_to_png_array(ref[i, t], pipe.image_size)
+            n_px += a.size
+            n_diff += int((a != r).sum())
+        ba, br = O.ccl_bbox(heat[i, 0], pipe.thr)[1], O.ccl_bbox(ref[i, 0], pipe.thr)[1]
+        box_changed += int(not (ba.shape == br.shape and np.array_equal(ba, br)))
+    return {"value": float(np.abs(heat - ref).max()), "tolerance": 1e-4, "images_checked": n_check,
+            "heat_max": float(ref.max()), "u8_pixels": n_px, "u8_pixels_differ": n_diff,
+            "maps_with_box_change": box_changed,
+            "against": "oracle (fp32 CPU restatement of hook.py:83-122,59-81) on the fp32 checkpoint weights, same "
+                       "synthetic activations"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,7 +176,9 @@ def workload_config(args, world):
                         f"batch {args.images_per_step} images per GPU (CFG => UNet batch {2 * args.images_per_step}), "
                         "heat maps for 3 tokens + u8 stacks (112^2) + CCL boxes; non-attention UNet layers replaced by "
                         "synthetic hidden states; to_k/to_v of the prompt embedding are projected once per image batch "
-                        "(loop-invariant over the denoising steps), everything else runs at every step",
+                        "(loop-invariant over the denoising steps), everything else runs at every step; bf16 "
+                        "activations, fp32 checkpoint weights (bf16 copies + bf16 residuals for cross to_q/to_k), "
+                        "cross-attention logits at fp32 accuracy (fp32-output to_q + split-precision tcgen05 kernel)",
             "images_per_step_per_gpu": args.images_per_step, "denoise_steps": NUM_DENOISE_STEPS, "tokens": len(TOKENS),
             "parallelism": f"dp{world} (seed-sharded, final NCCL all_gather of boxes+heat maps)",
             "l2": "per-step working set (hidden states 76 MB + Q/K/V/O activations > 300 MB) exceeds the 126 MB L2; "
@@ -299,7 +338,8 @@ def run_ours(args):
     # around every launch of the kernel on the launching stream.
     pipe_eager = pipe
     pipe_eager.use_cuda_graph = False
-    _lib.event_sink = {"agenda_attn_self_fwd": [], "agenda_attn_self_fwd_strided": [], "agenda_attn_cross_fwd_heat": []}
+    _lib.event_sink = {"agenda_attn_self_fwd": [], "agenda_attn_self_fwd_strided": [], "agenda_attn_cross_fwd_heat": [],
+                       "agenda_attn_cross_fwd_heat_x3": []}
     pipe_eager.num_steps = 5
     pipe_eager.run_device(hs_dev, ctx_dev)
     torch.cuda.synchronize()
@@ -364,20 +404,38 @@ def run_ours(args):
                                       "traffic = ncu dram bytes per map (the two-pass one-CTA kernel re-reads the map)"}}
 
     # cross-attention + heat epilogue (K2, HBM-bound): the same eager replay, in-pipeline cache state (Q was just
-    # written by the to_q GEMM).  args: q,k,v,out,dtype,B,H,N,M,d,scale,token_idx,T,b_first,maps,accumulate,stream
+    # written by the to_q GEMM).  The shipped path is the split-precision kernel (fp32 Q in, bf16 O out):
+    # args: q,k_hi,k_lo,v,out,out_dtype,B,H,N,M,d,scale,token_idx,T,b_first,per_head,maps,accumulate,stream
+    def cross_bytes_x3(a):
+        B_, H_, N_, M_, d_, T_, bf_ = a[6], a[7], a[8], a[9], a[10], a[13], a[14]
+        out_b = 4.0 if a[5] == 0 else 2.0
+        return B_ * N_ * H_ * d_ * (4.0 + out_b) + 3.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
+
+    # plain bf16 kernel (cross_logits="bf16"): q,k,v,out,dtype,B,H,N,M,d,scale,token_idx,T,b_first,maps,accumulate,stream
     def cross_bytes(a):
         B_, H_, N_, M_, d_, T_, bf_ = a[5], a[6], a[7], a[8], a[9], a[12], a[13]
         return 2.0 * B_ * N_ * H_ * d_ * 2 + 2.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
-    cross_calls = sink["agenda_attn_cross_fwd_heat"]
-    ms_x, bytes_x, n_x = summarize(cross_calls, lambda a: cross_bytes(a) if a[7] == big_n else None)
-    ms_x_all, _, _ = summarize(cross_calls, cross_bytes)
+    if sink["agenda_attn_cross_fwd_heat_x3"]:
+        cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat_x3"], cross_bytes_x3, 8, "attn_cross_sm100_x3_kernel"
+        note = "Q fp32 in + O bf16 out + K_hi,K_lo,V in + selected-token heat planes out"
+    else:
+        cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat"], cross_bytes, 7, "attn_cross_sm100_res_kernel"
+        note = "Q in + O out + K,V in + selected-token heat planes out (bf16)"
+    ms_x, bytes_x, n_x = summarize(cross_calls, lambda a: cb(a) if a[n_at] == big_n else None)
+    ms_x_all, _, _ = summarize(cross_calls, cb)
     if n_x:
         gbs = bytes_x / (ms_x / 1000.0) / 1e9
-        extra["cross_attention_heat"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
+        extra["cross_attention_heat"] = {"kernel": kern, "bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
                                          "frac": gbs / hbm_gbs, "avg_launch_ms": ms_x / n_x, "launches_timed": n_x,
                                          "ms_per_denoise_step_all_layers": ms_x_all / 5.0,
-                                         "note": "N=%d layers; algorithmic bytes = Q in + O out + K,V in + selected-"
-                                                 "token heat planes out" % big_n}
+                                         "share_of_step": (ms_x_all / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
+                                         "note": "N=%d layers; algorithmic bytes = %s" % (big_n, note)}
+
+    # ---- parity of THIS run's heat maps: images 0 and 1 of the benchmarked batch against the oracle's fp32 evaluation
+    #      of hook.py on the fp32 checkpoint weights (the checker; never on the product path) ----
+    parity = None
+    if not args.no_cpu_baseline:
+        parity = heat_parity(pipe, hs_dev, ctx_dev, n_img, min(2, n_img))
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -391,7 +449,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": pipe.h2d_bytes(hs_host, ctx_host),
                     "d2h_bytes_per_step": pipe.d2h_bytes(host_out)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": extra,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "heat_max_abs_err": parity}
     if graph_launch_note:
         line["gpu_launches_note"] = graph_launch_note
     print(json.dumps(line), file=_RESULT_OUT, flush=True)

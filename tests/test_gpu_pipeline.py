@@ -24,15 +24,35 @@ def _small_blocks():
             BlockSpec("up3", 16, 320, 8)]
 
 
+TOL_HEAT = 1e-4   # BASELINE.json north_star: heat maps max-abs 1e-4 against the fp32 reference
+
+
 def _oracle_heat(pipe, hs, ctx, steps, toks):
+    """hook.py semantics in fp32 on the CPU with the pipeline's FP32 checkpoint weights (not the bf16 copies the device
+    holds) and the same (bf16-valued) synthetic activations."""
     maps = []
-    for b, a2 in zip(pipe.blocks, pipe.stack.attn2):
+    ref = pipe.reference_stack()
+    for b, a2 in zip(pipe.blocks, ref.attn2):
         x = hs[(b.hw, b.channels)].float().cpu()
         w = [t.detach().float().cpu() for t in (a2.to_q.weight, a2.to_k.weight, a2.to_v.weight, a2.to_out[0].weight,
                                                 a2.to_out[0].bias)]
         _, m = O.processor_call(x, ctx.float().cpu(), *w, b.heads, is_train=False)
         maps.append(m)
     return O.global_heat_map(maps * steps, pipe.latent_hw)[:, toks]
+
+
+def _downstream_flips(heat, ref, size=112, thr=0.5):
+    """How far the byte / integer outputs move when OUR heat map replaces the reference's: u8 pixels that differ (and by
+    how much), and whether the CCL boxes differ.  heat / ref [n, T, L, L]."""
+    n_px = n_diff = max_step = box_maps = 0
+    for i in range(heat.shape[0]):
+        for t in range(heat.shape[1]):
+            a, b = O.heat_to_png_array(heat[i, t], size), O.heat_to_png_array(ref[i, t], size)
+            d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+            n_px += d.size; n_diff += int((d > 0).sum()); max_step = max(max_step, int(d.max()))
+        (_, ba), (_, bb) = O.ccl_bbox(heat[i, 0], thr), O.ccl_bbox(ref[i, 0], thr)
+        box_maps += int(not (ba.shape == bb.shape and np.array_equal(ba, bb)))
+    return {"u8_pixels": n_px, "u8_differ": n_diff, "u8_max_step": max_step, "maps_with_box_change": box_maps}
 
 
 @pytest.mark.parametrize("graph", [False, True])
@@ -43,11 +63,12 @@ def test_pipeline_matches_oracle(cuda_ok, graph):
                            use_cuda_graph=graph, max_boxes=32)
     hs, ctx = pipe.make_inputs(2, seed=3)  # 2 images -> UNet batch 4
     out = pipe.run_device(hs, ctx)
-    ref = _oracle_heat(pipe, hs, ctx, 3, toks)          # [2, 3, 16, 16]; the bf16 weights/inputs are shared
+    ref = _oracle_heat(pipe, hs, ctx, 3, toks)          # [2, 3, 16, 16]; fp32 checkpoint weights, fp32 math
     heat = out["heat"].cpu().numpy()
     assert heat.shape == ref.shape
-    # q/k are produced by bf16 cuBLAS GEMMs on the device vs fp32 on the CPU: compare at bf16-projection accuracy
-    assert np.abs(heat - ref).max() < 2e-3 * ref.max() + 1e-5
+    # the cross-attention logits keep fp32 accuracy on the tensor cores (fp32-output to_q with the weight_lo correction
+    # + the split-precision kernel): the stated 1e-4 holds against the fp32 reference on the fp32 weights
+    assert np.abs(heat - ref).max() < TOL_HEAT
     # everything downstream of the heat map is integer/byte work: bit-exact given OUR fp32 heat map
     for i in range(2):
         planes = [O.heat_to_png_array(heat[i, t], 112) for t in range(3)]
@@ -74,13 +95,57 @@ def test_pipeline_sd21_config4_shapes(cuda_ok):
     heat = out["heat"].cpu().numpy()
     ref = _oracle_heat(pipe, hs, ctx, 2, toks)
     assert heat.shape == ref.shape == (1, 4, 96, 96)
-    assert np.abs(heat - ref).max() < 2e-3 * ref.max() + 1e-5
+    assert np.abs(heat - ref).max() < TOL_HEAT
     planes = [O.heat_to_png_array(heat[0, t], 112) for t in range(3)]
     rs, ri = O.stack_heatmaps(*planes)
     assert np.array_equal(out["stack"][0].cpu().numpy(), rs) and np.array_equal(out["inv"][0].cpu().numpy(), ri)
     rl, rb = O.ccl_bbox(heat[0, 0], 0.5)
     assert out["counts"][0].item() == len(rb)
     assert np.array_equal(out["boxes"][0, :min(len(rb), 32)].cpu().numpy(), rb[:32])
+
+
+def test_pipeline_sd15_real_shapes_fp32_reference(cuda_ok):
+    """BASELINE configs[1] at its real layer shapes (SD-1.5, 64^2 latent: N = 4096 / 1024 / 256 / 64, d = 40 / 80 / 160,
+    16 blocks), the benchmarked bf16 pipeline, two images, two denoising steps: heat maps within 1e-4 max-abs of the
+    oracle's fp32 evaluation of hook.py on the FP32 checkpoint weights; and the damage downstream is counted: u8 pixels
+    that differ from the reference's, and maps whose boxes change."""
+    from agenda_b200.pipeline import sd15_pipeline
+    toks = [5, 6, 7]
+    pipe = sd15_pipeline(tokens=toks, num_steps=2, use_cuda_graph=True, max_boxes=64)
+    hs, ctx = pipe.make_inputs(2, seeds=[0, 1])
+    out = pipe.run_device(hs, ctx)
+    heat = out["heat"].cpu().numpy()
+    ref = _oracle_heat(pipe, hs, ctx, 2, toks)
+    assert heat.shape == ref.shape == (2, 3, 64, 64)
+    err = float(np.abs(heat - ref).max())
+    assert err < TOL_HEAT, err
+    flips = _downstream_flips(heat, ref)
+    print(f"sd15 real shapes: heat max-abs err {err:.2e} (max {ref.max():.3f}); downstream {flips}")
+    # a u8 level changes only where the normalised value sits within ~1e-4 * 255 of an integer: at most one level, rarely
+    assert flips["u8_max_step"] <= 1 and flips["u8_differ"] <= 0.02 * flips["u8_pixels"]
+    # the plain-bf16 logits path on the same inputs misses the tolerance (what round 1 shipped)
+    fast = sd15_pipeline(tokens=toks, num_steps=2, use_cuda_graph=False, max_boxes=64, cross_logits="bf16")
+    err_fast = float(np.abs(fast.run_device(hs, ctx)["heat"].cpu().numpy() - ref).max())
+    print(f"  cross_logits='bf16': heat max-abs err {err_fast:.2e}")
+    assert err_fast > 2 * err
+
+
+def test_pipeline_fp32_activations(cuda_ok):
+    """An fp32 pipeline (the reference's configuration, data_generation.py:30-31): fp32 modules and activations.  Cross
+    attention takes the modules' own fp32 projections into the split-precision tensor-core kernel, self-attention the
+    bf16 tensor-core kernel; heat maps within 1e-4, outputs fp32."""
+    from agenda_b200.pipeline import HeatmapPipeline
+    toks = [2, 5, 9]
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=toks, num_steps=2, latent_hw=16, dtype=torch.float32,
+                           use_cuda_graph=False, max_boxes=32)
+    hs, ctx = pipe.make_inputs(2, seeds=[4, 9])
+    assert ctx.dtype == torch.float32
+    out = pipe.run_device(hs, ctx)
+    ref = _oracle_heat(pipe, hs, ctx, 2, toks)
+    assert np.abs(out["heat"].cpu().numpy() - ref).max() < TOL_HEAT
+    with torch.no_grad():
+        y = pipe.stack(hs, ctx)
+    assert y.dtype == torch.float32
 
 
 def test_pipeline_host_api_equals_device_api(cuda_ok):
