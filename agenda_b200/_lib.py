@@ -38,9 +38,9 @@ _SIGNATURES = {
     "agenda_attn_cross_fwd_heat_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int,
                                        c_void_p],
-    "agenda_attn_cross_fwd_heat_x3": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                      c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int,
-                                      c_void_p],
+    "agenda_pack_context_kv": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "agenda_attn_cross_fwd_heat_x3": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                      ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "agenda_attn_cross_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int,
                               c_void_p],
@@ -55,7 +55,7 @@ _SIGNATURES = {
                                       c_void_p],
     "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
-EXPORTS = ["agenda_version", "agenda_last_error", "agenda_device_ok"] + list(_SIGNATURES)
+EXPORTS = ["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes"] + list(_SIGNATURES)
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_last_error.argtypes = []
     lib.agenda_device_ok.restype = c_int
     lib.agenda_device_ok.argtypes = []
+    lib.agenda_context_blob_bytes.restype = ctypes.c_longlong
+    lib.agenda_context_blob_bytes.argtypes = [c_int, c_int, c_int]
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

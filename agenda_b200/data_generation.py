@@ -1,9 +1,20 @@
 """CLI mirror of the reference's `data_generation/data_generation.py` (same flags, same output tree:
 `images/{seed}.png`, `daam_{word}_heatmaps/{seed}.png`), with the heat-map path on the B200 kernels:
 
-  * `daam.trace(pipeline)` (data_generation.py:57)            -> `agenda_b200.trace.trace(pipeline, tokens=...)`
+  * `daam.trace(pipeline)` (data_generation.py:57)            -> `agenda_b200.trace.trace(pipeline, tokens=..., mode="daam")`
   * `.compute_word_heat_map(word).heatmap` (:74-77)           -> same call on the shim
   * min-max -> u8 -> PIL resize (:78-85, numpy/PIL on the CPU) -> `agenda_heat_to_u8_image` on the GPU
+  * (not in the reference) threshold + connected components + boxes on the first word's heat map,
+    scaled to the image grid, the reference's fixed 42.36 px box rule (refine_label.py:58-113), one COCO json
+    (`annotations_coco_ccl.json`, [x, y, w, h] top-left, Data/README.md:7) for the whole run.
+
+Parity: the reference aggregates with the third-party `daam` package (un-vendored, un-pinned, requirements.txt:4), so
+`--trace-mode daam` (the default here, because it is what the reference calls) is PARITY UNPINNED: it follows daam's
+published algorithm as restated in oracle/hook_oracle.py.  `--trace-mode hook` aggregates with the in-tree hook.py
+semantics, which the golden vectors pin.  `--precision auto` (default) runs an fp32 pipeline — the reference's
+configuration, data_generation.py:30-31 — through the exact fp32 kernels, so that the image of a seed does not drift
+from the reference's; `--precision bf16` puts self-attention on the bf16 tensor cores (outputs to 1e-2) while the
+cross-attention logits behind the heat maps keep fp32 accuracy.
 
 Two modes:
   * real generation (needs `diffusers` + a checkpoint; neither exists in this offline image, so this branch is
@@ -52,6 +63,14 @@ def build_parser() -> argparse.ArgumentParser:
                         help="context rows of the words (when no tokenizer vocabulary is available)")
     parser.add_argument("--num-inference-steps", type=int, default=20)
     parser.add_argument("--batch-size", type=int, default=8, help="images per batch in --synthetic mode")
+    parser.add_argument("--trace-mode", choices=["daam", "hook"], default="daam",
+                        help="heat-map aggregation: daam = what the reference calls (parity unpinned: daam is not "
+                             "vendored), hook = the in-tree hook.py semantics (pinned)")
+    parser.add_argument("--precision", choices=["auto", "bf16", "fp32"], default="auto",
+                        help="auto: fp32 pipelines take the exact fp32 kernels (reference behaviour), 16-bit pipelines the "
+                             "tensor-core kernels; bf16: tensor-core self-attention, fp32-accurate heat-map logits")
+    parser.add_argument("--box-threshold", type=float, default=0.5, help="threshold on the min-max normalised heat map")
+    parser.add_argument("--no-boxes", action="store_true", help="do not run CCL / write annotations_coco_ccl.json")
     return parser
 
 
@@ -70,8 +89,24 @@ def save_word_heatmaps(save_dir, word, seeds, heat, image_size):
         Image.fromarray(u8[k]).save(os.path.join(out_dir, f"{seed}.png"))
 
 
+COCO_FILE = "annotations_coco_ccl.json"
+
+
+def _gather_box_records(records, world):
+    """rank-local [(seed, boxes [K,4] float64)] -> the same list for every seed on rank 0 (pickled gather: KBs)."""
+    if world == 1:
+        return records
+    import torch.distributed as dist
+    out = [None] * world if dist.get_rank() == 0 else None
+    dist.gather_object(records, out, dst=0)
+    if out is None:
+        return None
+    return sorted((r for part in out for r in part), key=lambda r: r[0])
+
+
 def run_synthetic(args):
     import torch.distributed as dist
+    from . import postprocess
     from .pipeline import sd15_pipeline
     from .sharding import shard_seeds
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -86,18 +121,34 @@ def run_synthetic(args):
         raise SystemExit("--token-indices must give one context row per word")
     while len(toks) < 3:
         toks = toks + [toks[-1] + 1]
-    pipe = sd15_pipeline(tokens=toks, num_steps=args.num_inference_steps, device=f"cuda:{local}")
+    pipe = sd15_pipeline(tokens=toks, num_steps=args.num_inference_steps, device=f"cuda:{local}", thr=args.box_threshold)
     seeds = shard_seeds(args.num_images, rank, world)
     os.makedirs(args.save_dir, exist_ok=True)
-    done = 0
-    for i in range(0, len(seeds), args.batch_size):
-        chunk = seeds[i:i + args.batch_size]
+    done, staging, box_records = 0, None, []
+    bs = args.batch_size
+    for i in range(0, len(seeds), bs):
+        chunk = seeds[i:i + bs]
         n = len(chunk)
-        hs, ctx = pipe.make_inputs(args.batch_size, seed=chunk[0])
-        out = pipe.run_device(hs, ctx)
+        # every image is a function of its own seed (data_generation.py:56-59), whatever batch or rank it lands in; a
+        # short last batch is padded with repeats so the staging buffers (and the captured CUDA graph) keep their shape
+        hs, ctx = pipe.make_inputs(bs, seeds=chunk + [chunk[-1]] * (bs - n), pinned_host=True)
+        if staging is None:
+            staging = pipe.make_staging(hs, ctx)
+        out = pipe.run_host(hs, ctx, staging)
+        dev = pipe.last_device_out
         for w, word in enumerate(words):
-            save_word_heatmaps(args.save_dir, word, chunk, out["heat"][:n, w], args.image_size)
+            save_word_heatmaps(args.save_dir, word, chunk, dev["heat"][:n, w], args.image_size)
+        if not args.no_boxes:
+            per_image = postprocess.ccl_boxes_to_coco_boxes(out["counts"][:n], out["boxes"][:n], pipe.latent_hw,
+                                                            args.image_size)
+            box_records += list(zip(chunk, per_image))
         done += n
+    if not args.no_boxes:
+        allrec = _gather_box_records(box_records, world)
+        if rank == 0:
+            coco = postprocess.coco_annotations([f"{s}.png" for s, _ in allrec], [b for _, b in allrec],
+                                                (args.image_size, args.image_size), image_ids=[s for s, _ in allrec])
+            postprocess.write_coco_json(os.path.join(args.save_dir, COCO_FILE), coco)
     if world > 1:
         dist.barrier()
     return done
@@ -124,31 +175,64 @@ def _install_learned_tokens(pipeline, args):
     return used, words
 
 
-def run_pipeline(args):
-    try:
-        from diffusers import StableDiffusionPipeline
-    except ImportError as e:  # pragma: no cover - not installable offline
-        raise SystemExit("diffusers is not installed: real generation needs the reference's environment "
-                         "(requirements.txt). Use --synthetic for the attention-stack workload.") from e
+def _pipeline_precision(pipeline, choice: str) -> str:
+    if choice != "auto":
+        return choice
+    unet = getattr(pipeline, "unet", pipeline)
+    p = next(iter(unet.parameters()), None)
+    return "fp32" if (p is None or p.dtype == torch.float32) else "bf16"
+
+
+def generate_with_pipeline(pipeline, args, used, words):
+    """data_generation.py:54-86 on an already-loaded pipeline (a diffusers StableDiffusionPipeline, or any object with
+    .unet / .tokenizer that is callable as pipeline(prompt, num_inference_steps=, generator=).images)."""
+    from . import postprocess
     from . import trace as trace_mod
-    pipeline = StableDiffusionPipeline.from_pretrained(args.pretrained_model_path).to("cuda")
-    used, words = _install_learned_tokens(pipeline, args)
     prompt = args.prompt.format(*used)
     image_dir = os.path.join(args.save_dir, "images")
     os.makedirs(image_dir, exist_ok=True)
+    precision = _pipeline_precision(pipeline, args.precision)
+    # the words' context rows are known before generation (daam resolves them afterwards, :74-77): tracing only those
+    # rows keeps the capture on the few-token kernels
+    word_rows = {w: trace_mod.word_token_indices(pipeline.tokenizer, prompt, w) for w in words}
+    tokens = sorted({i for rows in word_rows.values() for i in rows})
+    box_records, saved = [], 0
+    dev = next(iter(getattr(pipeline, "unet", pipeline).parameters())).device
     for seed in range(args.num_images):
-        rng = torch.Generator(device="cuda").manual_seed(seed)
-        with trace_mod.trace(pipeline, prompt=prompt) as tracer:          # daam.trace(pipeline), :57
+        rng = torch.Generator(device=dev).manual_seed(seed)
+        with trace_mod.trace(pipeline, tokens=tokens, prompt=prompt, mode=args.trace_mode,
+                             precision=precision) as tracer:              # daam.trace(pipeline), :57
             image = pipeline(prompt, num_inference_steps=args.num_inference_steps, generator=rng).images[0]
             image = image.resize((args.image_size, args.image_size))
             if np.asarray(image).max() < 1e-5:                            # all-black = filtered image, :61-62
                 continue
             heat = tracer.compute_global_heat_map()
         image.save(os.path.join(image_dir, f"{seed}.png"))
-        for word in words:
-            plane = heat.compute_word_heat_map(word).heatmap              # :74-77
+        for k, word in enumerate(words):
+            plane = heat.compute_word_heat_map(word, token_idx=word_rows[word]).heatmap   # :74-77
             save_word_heatmaps(args.save_dir, word, [seed], plane[None], args.image_size)
-    return args.num_images
+            if k == 0 and not args.no_boxes:
+                from . import ops
+                _, counts, boxes = ops.ccl_bbox(plane[None].contiguous(), args.box_threshold, 64, want_labels=False)
+                box_records.append((seed, postprocess.ccl_boxes_to_coco_boxes(counts, boxes, plane.shape[-1],
+                                                                              args.image_size)[0]))
+        saved += 1
+    if not args.no_boxes:
+        coco = postprocess.coco_annotations([f"{s}.png" for s, _ in box_records], [b for _, b in box_records],
+                                            (args.image_size, args.image_size), image_ids=[s for s, _ in box_records])
+        postprocess.write_coco_json(os.path.join(args.save_dir, COCO_FILE), coco)
+    return saved
+
+
+def run_pipeline(args):
+    try:
+        from diffusers import StableDiffusionPipeline
+    except ImportError as e:  # pragma: no cover - not installable offline
+        raise SystemExit("diffusers is not installed: real generation needs the reference's environment "
+                         "(requirements.txt). Use --synthetic for the attention-stack workload.") from e
+    pipeline = StableDiffusionPipeline.from_pretrained(args.pretrained_model_path).to("cuda")
+    used, words = _install_learned_tokens(pipeline, args)
+    return generate_with_pipeline(pipeline, args, used, words)
 
 
 def main(argv=None):

@@ -128,41 +128,67 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
 
 
 def split_bf16(x: torch.Tensor):
-    """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): x == hi + lo to 2^-17 relative.  The operand form
-    of the split-precision cross-attention kernel (agenda_attn_cross_fwd_heat_x3) for the key projection."""
+    """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): x == hi + lo to 2^-17 relative (the operand form
+    of the split-precision cross-attention kernel; pack_context_kv does the same on the device)."""
     x = x.float()
     hi = x.to(torch.bfloat16)
     lo = (x - hi.float()).to(torch.bfloat16)
     return hi.contiguous(), lo.contiguous()
 
 
-def attn_cross_heat_x3(q: torch.Tensor, k_hi: torch.Tensor, k_lo: torch.Tensor, v: torch.Tensor, heads: int,
-                       maps: Optional[torch.Tensor], token_idx: Optional[Sequence[int]] = None, b_first: int = 0,
-                       accumulate: bool = False, scale: Optional[float] = None, per_head: bool = False,
+class ContextKV:
+    """The prompt side of the split-precision cross-attention, packed for the tensor cores (agenda_pack_context_kv):
+    `blob` u8 [B, H, block] with K_hi | K_lo | V of every (batch, head) in the kernel's shared-memory layout."""
+
+    def __init__(self, blob: torch.Tensor, B: int, M: int, heads: int, d: int):
+        self.blob, self.B, self.M, self.heads, self.d = blob, B, M, heads, d
+
+
+def pack_context_kv(k32: torch.Tensor, v: torch.Tensor, heads: int, out: Optional[ContextKV] = None) -> ContextKV:
+    """k32 fp32 [B,M,H*d] (the key projection in fp32), v fp32 or bf16 [B,M,H*d] -> ContextKV.  Pass `out` to refill an
+    existing blob in place (same shapes): captured CUDA graphs keep reading the same buffer."""
+    k32 = _dev(k32, "k32", torch.float32)
+    v = _dev(v, "v")
+    if v.dtype not in (torch.float32, torch.bfloat16):
+        v = v.to(torch.bfloat16)
+    B, M, C = k32.shape
+    if tuple(v.shape) != (B, M, C) or C % heads:
+        raise ValueError(f"k32 / v must both be [B,M,H*d], got {tuple(k32.shape)} {tuple(v.shape)}, heads={heads}")
+    d = C // heads
+    nbytes = _lib.load().agenda_context_blob_bytes(B, heads, d)
+    if nbytes < 0:
+        raise _lib.AgendaError(int(nbytes), _lib.load().agenda_last_error().decode("utf-8", "replace"))
+    if out is None:
+        out = ContextKV(torch.empty((B, heads, nbytes // (B * heads)), dtype=torch.uint8, device=k32.device), B, M, heads, d)
+    elif (out.B, out.M, out.heads, out.d) != (B, M, heads, d) or out.blob.numel() != nbytes:
+        raise ValueError("pack_context_kv: `out` was built for a different shape")
+    _lib.call("agenda_pack_context_kv", k32.data_ptr(), v.data_ptr(), _dtype_code(v), out.blob.data_ptr(), B, heads, M, d,
+              _stream())
+    return out
+
+
+def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Tensor],
+                       token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
+                       scale: Optional[float] = None, per_head: bool = False,
                        out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """Cross-attention + heat epilogue with fp32-accurate logits on the bf16 tensor cores (hook.py:108-114 at the
     reference's fp32 precision; heat maps to ~1e-6 of an fp32 softmax).
 
-    q fp32 [B,N,H*d] (to_q output with fp32 accumulation); k_hi / k_lo = split_bf16(K) of the fp32 key projection
-    [B,M,H*d]; v bf16 [B,M,H*d].  maps / token_idx / b_first / accumulate / per_head as in attn_cross_heat (at most 8
-    tokens).  Returns out [B,N,H*d] in `out_dtype` (bf16 or fp32)."""
+    q fp32 [B,N,H*d] (to_q output with fp32 accumulation); ctx = pack_context_kv(K fp32, V).  maps / token_idx / b_first
+    / accumulate / per_head as in attn_cross_heat (token_idx None = all prompt tokens; per_head takes at most 8).
+    Returns out [B,N,H*d] in `out_dtype` (bf16 or fp32)."""
     q = _dev(q, "q", torch.float32)
-    k_hi, k_lo = _dev(k_hi, "k_hi", torch.bfloat16), _dev(k_lo, "k_lo", torch.bfloat16)
-    v = _dev(v, "v", torch.bfloat16)
     B, N, C = q.shape
-    M = k_hi.shape[1]
-    if k_lo.shape != k_hi.shape or v.shape != k_hi.shape or k_hi.shape[0] != B or k_hi.shape[2] != C:
-        raise ValueError(f"k_hi/k_lo/v must be [{B},M,{C}], got {tuple(k_hi.shape)} {tuple(k_lo.shape)} {tuple(v.shape)}")
-    d = C // heads
+    heads, M, d = ctx.heads, ctx.M, ctx.d
+    if ctx.B != B or heads * d != C or not ctx.blob.is_cuda:
+        raise ValueError(f"context was packed for B={ctx.B}, H*d={heads * d}; q is {tuple(q.shape)}")
     scale = float(d ** -0.5 if scale is None else scale)
     if out_dtype not in (torch.bfloat16, torch.float32):
         raise TypeError("out_dtype must be bfloat16 or float32")
     out = torch.empty((B, N, C), dtype=out_dtype, device=q.device)
     if maps is not None:
-        if token_idx is None:
-            raise ValueError("attn_cross_heat_x3 needs explicit token indices (at most 8)")
         maps = _dev(maps, "maps", torch.float32)
-        T = len(token_idx)
+        T = M if token_idx is None else len(token_idx)
         lead = (B - b_first, heads, T) if per_head else (B - b_first, T)
         n_lead = 1
         for x in lead:
@@ -172,12 +198,12 @@ def attn_cross_heat_x3(q: torch.Tensor, k_hi: torch.Tensor, k_lo: torch.Tensor, 
                              f"got {tuple(maps.shape)}")
         if not maps.is_contiguous():
             raise ValueError("maps must be contiguous (it is written in place)")
-        idx = (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
+        idx = None if token_idx is None else (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
         mp = maps.data_ptr()
     else:
         T, idx, mp = 0, None, None
-    _lib.call("agenda_attn_cross_fwd_heat_x3", q.data_ptr(), k_hi.data_ptr(), k_lo.data_ptr(), v.data_ptr(),
-              out.data_ptr(), _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32, B, heads, N, M, d, scale, idx, T,
+    _lib.call("agenda_attn_cross_fwd_heat_x3", q.data_ptr(), ctx.blob.data_ptr(), out.data_ptr(),
+              _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32, B, heads, N, M, d, scale, idx, T,
               int(b_first), int(bool(per_head)), mp, int(bool(accumulate)), _stream())
     return out
 

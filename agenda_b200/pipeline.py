@@ -57,12 +57,16 @@ class HeatmapPipeline:
         return AttentionStack(self.blocks, self.stack.context_dim, self._weight_seed)
 
     # ------------------------------------------------------------------------------------------------------
-    def make_inputs(self, n_images: int, seed: int = 0, pinned_host: bool = False, seeds: Optional[Sequence[int]] = None):
+    def make_inputs(self, n_images: int, seed: int = 0, pinned_host: bool = False, seeds: Optional[Sequence[int]] = None,
+                    on_device: bool = False):
         """Synthetic inputs for `n_images` (UNet batch = 2*n_images with classifier-free guidance).  With `seeds` (one
-        per image) every image's inputs depend on its own seed only, whatever batch or rank it lands in."""
+        per image) every image's inputs depend on its own seed only, whatever batch or rank it lands in; on_device=True
+        then draws them on the GPU (returns device tensors)."""
         if seeds is not None:
             if len(seeds) != n_images:
                 raise ValueError("need one seed per image")
+            if on_device:
+                return self.stack.make_inputs_for_seeds(seeds, self.device, self.dtype, on_device=True)
             hs, ctx = self.stack.make_inputs_for_seeds(seeds, "cpu", self.dtype)
         else:
             hs, ctx = self.stack.make_inputs(2 * n_images, "cpu", self.dtype, seed)
@@ -126,6 +130,35 @@ class HeatmapPipeline:
             host[name].copy_(out[name], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return host
+
+    @torch.no_grad()
+    def run_seeds(self, seeds: Sequence[int], batch_size: int = 8, staging: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
+        """The sharded-generation loop of one rank (data_generation.py:56-59 over this rank's seeds): batches of
+        `batch_size` images, inputs drawn on the device from each image's own seed, persistent staging buffers (one CUDA
+        graph for the whole run), a short last batch padded with repeats and trimmed.  Returns per-image records in
+        `seeds` order: heat [n,T,L,L] fp32, stack u8 [n,S,S,3], counts int32 [n], boxes int32 [n,max_boxes,5]."""
+        keep = ("heat", "stack", "counts", "boxes")
+        parts = {k: [] for k in keep}
+        seeds = list(seeds)
+        for i in range(0, len(seeds), batch_size):
+            chunk = seeds[i:i + batch_size]
+            n = len(chunk)
+            hs, ctx = self.make_inputs(batch_size, seeds=chunk + [chunk[-1]] * (batch_size - n), on_device=True)
+            if staging is None:
+                staging = {"hs": {k: torch.empty_like(v) for k, v in hs.items()}, "ctx": torch.empty_like(ctx)}
+            for k, v in hs.items():
+                staging["hs"][k].copy_(v)
+            staging["ctx"].copy_(ctx)
+            out = self.run_device(staging["hs"], staging["ctx"])
+            for k in keep:
+                parts[k].append(out[k][:n].clone())
+        self._seed_staging = staging
+        if not seeds:
+            L, S, T = self.latent_hw, self.image_size, len(self.tokens)
+            return {"heat": torch.empty((0, T, L, L), device=self.device), "stack": torch.empty((0, S, S, 3), dtype=torch.uint8, device=self.device),
+                    "counts": torch.empty((0,), dtype=torch.int32, device=self.device),
+                    "boxes": torch.empty((0, self.max_boxes, 5), dtype=torch.int32, device=self.device)}
+        return {k: torch.cat(v, 0) for k, v in parts.items()}
 
     def make_staging(self, hs_host: Dict, ctx_host: torch.Tensor) -> Dict:
         return {"hs": {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in hs_host.items()},

@@ -42,6 +42,26 @@ from . import autograd as _ag
 from . import ops
 
 
+_ADDMM_IN_PLACE = None   # does this torch build take addmm(out_dtype=fp32, out=input) on 16-bit operands?
+
+
+def _addmm_f32_(q: torch.Tensor, x2: torch.Tensor, w_t: torch.Tensor) -> torch.Tensor:
+    """q (fp32) += x2 @ w_t (16-bit operands, fp32 accumulation) — as ONE GEMM that accumulates into q when the
+    library allows it, else a second fp32-output GEMM and an add."""
+    global _ADDMM_IN_PLACE
+    if _ADDMM_IN_PLACE is not False:
+        try:
+            torch.addmm(q, x2, w_t, out_dtype=torch.float32, out=q)
+            _ADDMM_IN_PLACE = True
+            return q
+        except (RuntimeError, TypeError):
+            if _ADDMM_IN_PLACE:   # worked before: a real error
+                raise
+            _ADDMM_IN_PLACE = False
+    q += torch.mm(x2, w_t, out_dtype=torch.float32)
+    return q
+
+
 class UNetCrossAttentionHooker:
     def __init__(self, is_train: bool = True, latent_hw: int = 64, tokens: Optional[Sequence[int]] = None,
                  precision: str = "bf16", record_maps: bool = False, aggregate: str = "hook",
@@ -161,18 +181,18 @@ class UNetCrossAttentionHooker:
         lo = getattr(lin, "weight_lo", None)
         return w if lo is None else w + lo.float()
 
-    def _project_context(self, attn, ehs, split: bool):
+    def _project_context(self, attn, ehs, split: bool, into=None):
         """to_k / to_v of the prompt embedding (hook.py:101-102).  split=False: (K, V) in the modules' own precision.
-        split=True (cross_logits="fp32"): K in fp32 — from the fp32 weight, or weight + weight_lo — handed over as the
-        (K_hi, K_lo) bf16 pair the split-precision kernel takes, and V in bf16: (K_hi, K_lo, V)."""
+        split=True (cross_logits="fp32"): K in fp32 — from the fp32 weight, or weight + weight_lo — and V, packed into
+        the tensor-core operand blob of the split-precision kernel (ops.pack_context_kv): (ContextKV,).  `into` refills
+        an existing blob in place."""
         if not split:
             return attn.to_k(ehs), attn.to_v(ehs)
         k32 = torch.nn.functional.linear(ehs.float(), self._full_weight(attn.to_k))
         bias = getattr(attn.to_k, "bias", None)
         if bias is not None:
             k32 = k32 + bias.float()
-        k_hi, k_lo = ops.split_bf16(k32)
-        return k_hi, k_lo, attn.to_v(ehs).to(torch.bfloat16).contiguous()
+        return (ops.pack_context_kv(k32, attn.to_v(ehs), attn.heads, out=into),)
 
     def _context_kv(self, attn, ehs, split: bool = False):
         if torch.is_grad_enabled() and (ehs.requires_grad or attn.to_k.weight.requires_grad
@@ -198,8 +218,11 @@ class UNetCrossAttentionHooker:
             if new_state[1] != state[1]:   # shape changed: rebuilt on the next call
                 del self._ctx_kv[mod_id]
                 continue
-            for dst, src in zip(tensors, self._project_context(attn, ehs, state[-1])):
-                dst.copy_(src)
+            if state[-1]:
+                self._project_context(attn, ehs, True, into=tensors[0])
+            else:
+                for dst, src in zip(tensors, self._project_context(attn, ehs, False)):
+                    dst.copy_(src)
             self._ctx_kv[mod_id] = (ehs, new_state, tensors, attn)
 
     @staticmethod
@@ -218,13 +241,16 @@ class UNetCrossAttentionHooker:
         q = torch.mm(x2, w.t(), out_dtype=torch.float32)
         lo = getattr(lin, "weight_lo", None)
         if lo is not None:
-            q += torch.mm(x2, lo.to(x2.dtype).t(), out_dtype=torch.float32)
+            _addmm_f32_(q, x2, lo.to(x2.dtype).t())
         if lin.bias is not None:
             q += lin.bias.float()
         return q.view(B, N, -1)
 
     def _use_x3(self, attn, query_dim: int, M: int) -> bool:
-        if self.precision != "bf16" or self.cross_logits != "fp32" or self.tokens is None or len(self.tokens) > 8:
+        if self.precision != "bf16" or self.cross_logits != "fp32":
+            return False
+        n_tok = M if self.tokens is None else len(self.tokens)
+        if n_tok > 8 and self.aggregate == "daam":   # per-head planes: the kernel keeps at most 8 tokens apart
             return False
         return M <= 80 and (query_dim // attn.heads) in (40, 64, 80, 160) and query_dim % attn.heads == 0
 
@@ -306,8 +332,8 @@ class UNetCrossAttentionHooker:
             out_dtype = in_dtype if in_dtype in (torch.bfloat16, torch.float32) else torch.bfloat16
 
             def cross(maps, accumulate, per_head=False):
-                o = ops.attn_cross_heat_x3(query, kv[0], kv[1], kv[2], heads, maps, self.tokens, b_first,
-                                           accumulate=accumulate, scale=scale, per_head=per_head, out_dtype=out_dtype)
+                o = ops.attn_cross_heat_x3(query, kv[0], maps, self.tokens, b_first, accumulate=accumulate, scale=scale,
+                                           per_head=per_head, out_dtype=out_dtype)
                 return o if o.dtype == in_dtype else o.to(in_dtype)
         else:
             query = attn.to_q(hidden_states)

@@ -123,19 +123,22 @@ class AttentionStack(nn.Module):
         ctx = torch.randn(batch, context_len, self.context_dim, generator=gen).to(device=device, dtype=dtype)
         return hs, ctx
 
-    def make_inputs_for_seeds(self, seeds, device, dtype, context_len: int = 77):
+    def make_inputs_for_seeds(self, seeds, device, dtype, context_len: int = 77, on_device: bool = False):
         """Synthetic inputs of a batch of images, each a function of ITS OWN seed only (data_generation.py:56-59: an image
         depends on (prompt, seed), never on which other seeds share its batch or rank).  UNet batch layout as under
-        classifier-free guidance: [uncond_0 .. uncond_{n-1}, cond_0 .. cond_{n-1}] (hook.py:48-49 keeps the second half)."""
+        classifier-free guidance: [uncond_0 .. uncond_{n-1}, cond_0 .. cond_{n-1}] (hook.py:48-49 keeps the second half).
+        on_device=True draws the values with a per-image generator ON `device` (no host synthesis, no H2D copy; the
+        values differ from the CPU generator's, but are again a function of the seed alone)."""
         shapes = []
         for b in self.blocks:
             if (b.hw, b.channels) not in shapes:
                 shapes.append((b.hw, b.channels))
+        gdev = device if on_device else "cpu"
         per_image = []
         for s in seeds:
-            gen = torch.Generator().manual_seed(100003 * int(s) + 17)
-            item = {k: torch.randn(2, k[0] * k[0], k[1], generator=gen) for k in shapes}
-            item["ctx"] = torch.randn(2, context_len, self.context_dim, generator=gen)
+            gen = torch.Generator(device=gdev).manual_seed(100003 * int(s) + 17)
+            item = {k: torch.randn(2, k[0] * k[0], k[1], generator=gen, device=gdev) for k in shapes}
+            item["ctx"] = torch.randn(2, context_len, self.context_dim, generator=gen, device=gdev)
             per_image.append(item)
 
         def batch_of(key):

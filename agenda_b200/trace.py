@@ -26,6 +26,22 @@ import torch
 from .processor import UNetCrossAttentionHooker
 
 
+def word_token_indices(tokenizer, prompt: str, word: str) -> List[int]:
+    """daam.utils.compute_token_merge_indices: positions (BOS offset +1) of the word's sub-token sequence in the
+    lower-cased prompt (convention also at data_generation/dataset.py:93)."""
+    if tokenizer is None:
+        raise ValueError("no tokenizer: pass explicit token indices (compute_word_heat_map(word, token_idx=...))")
+    split = tokenizer.tokenize if hasattr(tokenizer, "tokenize") else (lambda s: s.split())
+    prompt_ids, word_ids = split(prompt.lower()), split(word.lower())
+    hits = []
+    for i in range(len(prompt_ids) - len(word_ids) + 1):
+        if prompt_ids[i:i + len(word_ids)] == word_ids:
+            hits += [i + 1 + k for k in range(len(word_ids))]
+    if not hits:
+        raise ValueError(f"Search word {word} not found in prompt!")
+    return hits
+
+
 class WordHeatMap:
     def __init__(self, heatmap: torch.Tensor, word: str):
         self.heatmap = heatmap  # [L, L] fp32 on the device, what data_generation.py:77-79 reads
@@ -44,20 +60,7 @@ class GlobalHeatMap:
         self.prompt = prompt
 
     def token_indices(self, word: str) -> List[int]:
-        """daam.utils.compute_token_merge_indices: positions (BOS offset +1) of the word's sub-token sequence in
-        the lower-cased prompt (convention also at data_generation/dataset.py:93)."""
-        if self.tokenizer is None:
-            raise ValueError("no tokenizer: pass explicit token indices (compute_word_heat_map(word, token_idx=...))")
-        tok = self.tokenizer
-        prompt_ids = tok.tokenize(self.prompt.lower()) if hasattr(tok, "tokenize") else self.prompt.lower().split()
-        word_ids = tok.tokenize(word.lower()) if hasattr(tok, "tokenize") else word.lower().split()
-        hits = []
-        for i in range(len(prompt_ids) - len(word_ids) + 1):
-            if prompt_ids[i:i + len(word_ids)] == word_ids:
-                hits += [i + 1 + k for k in range(len(word_ids))]
-        if not hits:
-            raise ValueError(f"Search word {word} not found in prompt!")
-        return hits
+        return word_token_indices(self.tokenizer, self.prompt, word)
 
     def compute_word_heat_map(self, word: str, token_idx: Optional[Sequence[int]] = None) -> WordHeatMap:
         idx = list(token_idx) if token_idx is not None else self.token_indices(word)
@@ -82,7 +85,7 @@ class trace:
         if latent_hw is None:  # daam: 64 for 512/1024-px pipelines, else 96
             cfg = getattr(self.unet, "config", None)
             sample = getattr(cfg, "sample_size", 64) if cfg is not None else 64
-            latent_hw = sample if sample in (64, 96, 128) else 64
+            latent_hw = int(sample) if isinstance(sample, int) and sample > 0 else 64
         self.mode = mode
         self.prompt = prompt
         self.tokens = None if tokens is None else list(tokens)

@@ -44,9 +44,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-step", type=int, default=None, help="default 8 (sd15) / 16 (sd21)")
-    ap.add_argument("--workload", default="sd15", choices=["sd15", "sd21"],
+    ap.add_argument("--workload", default="sd15", choices=["sd15", "sd21", "config3"],
                     help="sd15 = BASELINE configs[1] (the headline metric); sd21 = configs[3] (SD-2.1 768^2, 96^2 latent, "
-                         "batch 16, 4 tokens) — informational")
+                         "batch 16, 4 tokens) — informational; config3 = configs[2]: --num-images seeds sharded over the "
+                         "ranks (strong scaling), final NCCL gather of heat maps + boxes, determinism check")
+    ap.add_argument("--num-images", type=int, default=4096, help="config3: seeds 0..num_images-1 over all ranks")
+    ap.add_argument("--denoise-steps", type=int, default=NUM_DENOISE_STEPS, help="config3: denoising steps per image")
+    ap.add_argument("--dump", default=None, help="config3: rank 0 writes the gathered records to this .npz")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ccl-maps", type=int, default=2048, help="512^2 maps for the post-process roofline probe")
@@ -457,9 +461,95 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config3(args):
+    """BASELINE configs[2]: `--num-images` (prompt embedding, seed) pairs, rank r takes the seeds i = r (mod W)
+    (SURVEY.md §8e), batches of --images-per-step, one final gather of fixed-size records over NCCL
+    (agenda_b200.sharding.gather_records).  Strong scaling: the job is the same at every N.  One "step" = the whole job."""
+    import torch
+    import torch.distributed as dist
+    from agenda_b200 import _lib
+    from agenda_b200.pipeline import sd15_pipeline
+    from agenda_b200.sharding import gather_records, shard_seeds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    bs, n_total = args.images_per_step, args.num_images
+    pipe = sd15_pipeline(tokens=TOKENS, num_steps=args.denoise_steps, device=dev, use_cuda_graph=not args.no_graph)
+    seeds = shard_seeds(n_total, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job():
+        local_rec = pipe.run_seeds(seeds, bs, getattr(pipe, "_seed_staging", None))
+        return gather_records(local_rec, seeds, n_total)          # NCCL all_gather, seed-major re-order
+
+    for _ in range(max(args.warmup, 1)):                             # warm-up: graph capture + a few batches
+        pipe.run_seeds(seeds[:2 * bs], bs, getattr(pipe, "_seed_staging", None))
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        merged = job()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = _lib.launches - l0
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        # determinism across rank / batch composition: recompute seeds that (mostly) ran on OTHER ranks, in batches of a
+        # different composition, on this GPU, and compare bit for bit with the gathered records
+        picks = sorted({(i * (n_total // 16 or 1) + i % max(world, 1)) % n_total for i in range(16)})
+        again = pipe.run_seeds(picks, bs, getattr(pipe, "_seed_staging", None))
+        same = all(torch.equal(again[k], merged[k][picks]) for k in ("heat", "stack", "counts", "boxes"))
+        if args.dump:
+            import numpy as np
+            np.savez(args.dump, **{k: v.cpu().numpy() for k, v in merged.items()})
+        n_boxes = int(merged["counts"].sum().item())
+        line = {"metric": METRIC, "value": n_total * args.steps / (ms / 1000.0), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[2]: SD-1.5 attention stack, {args.denoise_steps} denoising steps, "
+                                       f"{n_total} synthetic (prompt embedding, seed) pairs, rank r takes seeds i = r mod "
+                                       f"{world}, batches of {bs} images (inputs drawn on the device from each image's own "
+                                       "seed), heat maps for 3 tokens + u8 stacks + CCL boxes, final NCCL all_gather of the "
+                                       "records re-ordered by seed on every rank",
+                           "num_images": n_total, "images_per_step_per_gpu": bs, "denoise_steps": args.denoise_steps,
+                           "parallelism": f"dp{world} (seed-sharded, final NCCL all_gather)",
+                           "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"},
+                "gpu_launches": launches, "clocks": clocks,
+                "gathered": {"images": int(merged["heat"].shape[0]), "boxes": n_boxes,
+                             "bytes": int(sum(v.numel() * v.element_size() for v in merged.values()))},
+                "determinism_check": {"seeds_recomputed_on_rank0": len(picks), "bit_identical": bool(same),
+                                      "what": "heat, u8 stack, counts, boxes of seeds spread over all ranks' shards, recomputed "
+                                              "in differently composed batches on rank 0's GPU"}}
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
+        if not same:
+            raise SystemExit("config3: gathered records differ from a recomputation on rank 0")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "config3":
+        run_config3(a)
     else:
         run_ours(a)

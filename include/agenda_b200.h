@@ -102,20 +102,32 @@ int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v
                                      const int32_t* token_idx, int T, int b_first,
                                      float* maps, int accumulate, void* stream);
 
+/* ---- prompt side of the split-precision cross-attention: pack K / V once per prompt --------------------------------
+ * to_k / to_v of the prompt embedding (hook.py:101-102) do not depend on the latent.  agenda_pack_context_kv turns the
+ * fp32 key projection k32 [B,M,H*d] and the value projection v [B,M,H*d] (v_dtype AGENDA_F32 or AGENDA_BF16) into
+ * `blob`: for every (batch, head) the exact shared-memory image agenda_attn_cross_fwd_heat_x3 feeds to the tensor
+ * cores — K_hi = bf16(K) chunks | K_lo = bf16(K - K_hi) chunks | V (bf16) chunks, 80-row x 128-byte tiles in the
+ * 128B-swizzled UMMA layout, zero padded — so that a head's K and V each arrive with one bulk copy.
+ * agenda_context_blob_bytes gives the size of `blob` in bytes (negative error code for an unsupported d).
+ * M <= 80; d in {40,64,80,160}; pointers 16-byte aligned. */
+long long agenda_context_blob_bytes(int B, int H, int d);
+int agenda_pack_context_kv(const float* k32, const void* v, int v_dtype, void* blob, int B, int H, int M, int d,
+                           void* stream);
+
 /* Cross-attention with fp32-accurate logits on the bf16 tensor cores ("bf16 x 3" split): the path that holds the heat
  * maps to the 1e-4 tolerance against the reference's fp32 baddbmm + softmax (hook.py:108; the reference pipeline is
- * fp32, data_generation.py:30-31).  q is FP32 [B,N,H*d] (a to_q output with fp32 accumulation); k_hi / k_lo are bf16
- * [B,M,H*d] with k_hi = bf16(K), k_lo = bf16(K - k_hi) for the fp32 key projection K (computed once per prompt by the
- * caller); v bf16 [B,M,H*d].  The kernel splits every Q tile into hi / lo on chip and accumulates
- * Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T in fp32 (products of bf16 values are exact; the dropped lo*lo term is 2^-18
- * relative).  Softmax, head mean and maps are fp32 as in agenda_attn_cross_fwd_heat; P V runs with bf16 P.
- * out [B,N,H*d] in out_dtype (AGENDA_BF16 or AGENDA_F32).  maps: per_head == 0 -> [B-b_first, T, N] (mean over heads),
- * per_head != 0 -> [B-b_first, H, T, N] (no mean, DAAM-style); T <= 8 selected tokens (token_idx HOST int32[T], not
- * NULL when maps is given); maps NULL skips the epilogue.  M <= 80; d in {40,64,80,160}; all pointers 16-byte aligned. */
-int agenda_attn_cross_fwd_heat_x3(const float* q, const void* k_hi, const void* k_lo, const void* v, void* out,
-                                  int out_dtype, int B, int H, int N, int M, int d, float scale,
-                                  const int32_t* token_idx, int T, int b_first, int per_head,
-                                  float* maps, int accumulate, void* stream);
+ * fp32, data_generation.py:30-31).  q is FP32 [B,N,H*d] (a to_q output with fp32 accumulation); kv_blob is the packed
+ * prompt side from agenda_pack_context_kv (same B, H, M, d).  The kernel splits every Q tile into hi / lo bf16 on chip
+ * and accumulates Q_hi K_hi^T + Q_lo K_hi^T + Q_hi K_lo^T in fp32 (products of bf16 values are exact; the dropped
+ * lo*lo term is 2^-18 relative).  Softmax, head mean and maps are fp32 as in agenda_attn_cross_fwd_heat; P V runs with
+ * bf16 P and V.  out [B,N,H*d] in out_dtype (AGENDA_BF16 or AGENDA_F32).
+ * maps: per_head == 0 -> [B-b_first, T, N] (mean over heads; token_idx HOST int32[T], or NULL with T == M for all
+ * prompt tokens in order, the reference's behaviour); per_head != 0 -> [B-b_first, H, T, N] (no mean, DAAM-style,
+ * T <= 8).  maps NULL skips the epilogue.  T <= 8 takes the two-warpgroup kernel, larger T the all-token form.
+ * M <= 80; d in {40,64,80,160}; q / kv_blob / out 16-byte aligned. */
+int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob, void* out, int out_dtype, int B, int H, int N,
+                                  int M, int d, float scale, const int32_t* token_idx, int T, int b_first,
+                                  int per_head, float* maps, int accumulate, void* stream);
 
 /* Backward of agenda_attn_cross_fwd_heat (training mode, SURVEY.md §8 f N3: autograd of hook.py:104-115 and of
  * _unravel_attn hook.py:28-56 as exercised by finetune_sd_token.py:1043-1069).  Given d_out [B,N,H*d] (same dtype as

@@ -326,3 +326,48 @@ def synthetic_heatmaps(n: int, size: int = 512, seed: int = 0) -> np.ndarray:
                                                / (2 * sig * sig))).astype(np.float32)
         out[i] = img
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# N2: the reference's fixed-size box rule  (data_annotation/refine_label.py:17-18,58-113), one box, Python floats
+# --------------------------------------------------------------------------------------------------------------
+
+
+def fixed_size_box_rule(l, t, r, b, bboxes_size_px=42.36, image_size=(112, 112)):
+    """refine_label.py:58-113 restated for one detection (l, t, r, b); rgb_image.size == image_size.  Returns the COCO
+    box (x, y, w, h) the reference appends at refine_label.py:126-135.  (The reference hard-codes 42.36 in the
+    edge-completion branch, :78-100, and uses bboxes_size_px for the final square, :105-109.)"""
+    margin_px = bboxes_size_px / 2 - 1
+    x_c_bbox = (l + r) / 2
+    y_c_bbox = (t + b) / 2
+    v = 'left' if x_c_bbox < margin_px else ('right' if x_c_bbox > image_size[0] - margin_px else None)
+    h = 'top' if y_c_bbox < margin_px else ('bottom' if y_c_bbox > image_size[1] - margin_px else None)
+    if v == 'left':
+        r_full, l_full = r, r - 42.36
+    elif v == 'right':
+        l_full, r_full = l, l + 42.36
+    else:
+        l_full, r_full = l, r
+    if h == 'top':
+        b_full, t_full = b, b - 42.36
+    elif h == 'bottom':
+        t_full, b_full = t, t + 42.36
+    else:
+        t_full, b_full = t, b
+    xc, yc = (l_full + r_full) / 2, (t_full + b_full) / 2
+    l2 = max(0, xc - bboxes_size_px / 2)
+    t2 = max(0, yc - bboxes_size_px / 2)
+    r2 = min(xc + bboxes_size_px / 2, image_size[0] - 1)
+    b2 = min(yc + bboxes_size_px / 2, image_size[1] - 1)
+    return l2, t2, r2 - l2, b2 - t2
+
+
+def coco_boxes_from_heat(heat: np.ndarray, thr: float = 0.5, image_size: int = 112):
+    """a9 boxes of one fp32 heat map [L, L] -> the annotation boxes the generation driver writes: CCL boxes scaled from
+    the map grid to the image grid (x S/L), then the fixed-size rule.  List of (x, y, w, h) float tuples."""
+    _, boxes = ccl_bbox(heat, thr)
+    s = image_size / heat.shape[-1]
+    out = []
+    for x, y, w, h, _ in boxes.tolist():
+        out.append(fixed_size_box_rule(x * s, y * s, x * s + w * s, y * s + h * s, image_size=(image_size, image_size)))
+    return out

@@ -216,12 +216,15 @@ def test_processor_matches_reference_hook_golden(ops, golden_dir, mode, precisio
             o_cross = a_cross(hs, encoder_hidden_states=ctx).cpu().numpy()
         tol_self = TOL_F32_OUT * 5 if precision == "fp32" else TOL_BF16_OUT * 3  # x |to_out| gain
         assert np.abs(o_self - g[f"{name}_self_out"]).max() < tol_self, name
-        assert np.abs(o_cross - g[f"{name}_cross_out"]).max() < TOL_F32_OUT * 5, name
+        # precision="bf16": the cross-attention call runs on the tensor cores too (split-precision kernel, all 77 token
+        # maps): outputs to the bf16 tolerance (P V with bf16 P and V), maps far inside the 1e-4 heat tolerance
+        tol_cross = TOL_F32_OUT * 5 if precision == "fp32" else TOL_BF16_OUT * 3
+        assert np.abs(o_cross - g[f"{name}_cross_out"]).max() < tol_cross, name
         got = proc.cross_attn_maps[-1].cpu().numpy()
         assert got.shape == g[f"{name}_maps"].shape
-        assert np.abs(got - g[f"{name}_maps"]).max() < 1e-6, name
+        assert np.abs(got - g[f"{name}_maps"]).max() < (1e-6 if precision == "fp32" else 3e-5), name
     heat = proc.compute_global_heat_map().cpu().numpy()
-    assert np.abs(heat - g["global"]).max() < 1e-5
+    assert np.abs(heat - g["global"]).max() < (1e-5 if precision == "fp32" else 3e-5)
     proc.clear()
     assert proc.num_maps == 0 and proc.cross_attn_maps == []
 

@@ -32,13 +32,17 @@ def _qkv(B, N, M, H, d, seed, gain=1.0):
     return q, k, v
 
 
-def _run(ops, q, k, v, H, T, b_first, per_head=False, out_dtype=torch.bfloat16, accumulate=False, maps=None):
+def _run(ops, q, k, v, H, T, b_first, per_head=False, out_dtype=torch.bfloat16, accumulate=False, maps=None,
+         heat=True):
+    """T: list of token rows, or None for all M prompt tokens; heat=False skips the epilogue."""
     B, N, _ = q.shape
-    k_hi, k_lo = ops.split_bf16(k.cuda())
-    if maps is None and T is not None:
-        lead = (B - b_first, H, len(T)) if per_head else (B - b_first, len(T))
+    M = k.shape[1]
+    ctx = ops.pack_context_kv(k.cuda(), v.cuda().bfloat16(), H)
+    if maps is None and heat:
+        n_tok = M if T is None else len(T)
+        lead = (B - b_first, H, n_tok) if per_head else (B - b_first, n_tok)
         maps = torch.full(lead + (N,), 7.0, device="cuda")
-    out = ops.attn_cross_heat_x3(q.cuda(), k_hi, k_lo, v.cuda().bfloat16(), H, maps, T, b_first, accumulate=accumulate,
+    out = ops.attn_cross_heat_x3(q.cuda(), ctx, maps if heat else None, T, b_first, accumulate=accumulate,
                                  per_head=per_head, out_dtype=out_dtype)
     return out, maps
 
@@ -66,7 +70,7 @@ def test_x3_matches_fp32_reference(ops, B, N, H, d, T, is_train):
     _run(ops, q, k, v, H, T, b_first, accumulate=True, maps=maps)
     assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 2 * TIGHT_HEAT
     # fp32 output, no heat requested
-    out32, _ = _run(ops, q, k, v, H, None, b_first, out_dtype=torch.float32)
+    out32, _ = _run(ops, q, k, v, H, None, b_first, out_dtype=torch.float32, heat=False)
     assert out32.dtype == torch.float32
     assert (out32.cpu() - ref).abs().max().item() < TOL_OUT
     assert (out32.cpu() - out.float().cpu()).abs().max().item() < 4e-2 * ref.abs().max().item() + 1e-3
@@ -122,15 +126,64 @@ def test_x3_deterministic(ops):
     assert torch.equal(o1, o2) and torch.equal(m1, m2)
 
 
+@pytest.mark.parametrize("B,N,H,d,M", [(2, 256, 8, 40, 77), (2, 1024, 8, 80, 77), (2, 64, 8, 160, 77), (4, 4096, 8, 40, 77),
+                                        (2, 576, 5, 64, 77), (2, 300, 3, 40, 30), (3, 200, 2, 64, 80)])
+@pytest.mark.parametrize("is_train", [False, True])
+def test_x3_all_tokens(ops, B, N, H, d, M, is_train):
+    """token_idx None: heat maps for ALL prompt tokens, the reference's own behaviour (hook.py:28-56 keeps 77 maps) —
+    the one-warpgroup form with register accumulators.  Also an explicit list of more than 8 tokens."""
+    q, k, v = _qkv(B, N, M, H, d, seed=N * 11 + d, gain=1.5)
+    ref, p = O.attention_core(q, k, v.bfloat16().float(), H)
+    b_first = 0 if is_train else B // 2
+    ref_maps = p.reshape(B, H, N, M)[b_first:].mean(1).permute(0, 2, 1)      # [B', M, N]
+    out, maps = _run(ops, q, k, v, H, None, b_first)
+    assert maps.shape == (B - b_first, M, N)
+    assert (out.float().cpu() - ref).abs().max().item() < TOL_OUT
+    assert (maps.cpu() - ref_maps).abs().max().item() < TIGHT_HEAT
+    _run(ops, q, k, v, H, None, b_first, accumulate=True, maps=maps)
+    assert (maps.cpu() - 2 * ref_maps).abs().max().item() < 2 * TIGHT_HEAT
+    toks = [M - 1, 0, 3, 3, 7, 8, 9, 10, 11, 12, 5]
+    _, maps_t = _run(ops, q, k, v, H, toks, b_first)
+    assert (maps_t.cpu() - ref_maps[:, toks]).abs().max().item() < TIGHT_HEAT
+    # the few-token kernel and the all-token kernel agree on the attention output bit for bit
+    out_few, _ = _run(ops, q, k, v, H, [0], b_first)
+    assert torch.equal(out_few, out)
+
+
+def test_pack_context_kv_layout(ops):
+    """The packed prompt block is what the kernel's descriptors expect: K_hi | K_lo | V tiles of 80 rows x 128 bytes,
+    16-byte piece p of row r stored at piece p ^ (r & 7), zero padding beyond M rows and beyond the chunk's columns."""
+    B, H, d, M = 2, 3, 40, 77
+    g = torch.Generator().manual_seed(2)
+    k = torch.randn(B, M, H * d, generator=g)
+    v = torch.randn(B, M, H * d, generator=g)
+    ctx = ops.pack_context_kv(k.cuda(), v.cuda(), H)
+    blob = ctx.blob.cpu().numpy().view(np.uint16).reshape(B, H, 3, 80, 8, 8)   # tiles: K_hi, K_lo, V
+    k_hi = k.bfloat16()
+    k_lo = (k - k_hi.float()).bfloat16()
+    planes = [k_hi, k_lo, v.bfloat16()]
+    for t, src in enumerate(planes):
+        want = np.zeros((B, H, 80, 8, 8), np.uint16)
+        s16 = src.view(torch.int16).numpy().view(np.uint16).reshape(B, M, H, d)
+        for r in range(M):
+            for p in range(5):
+                want[:, :, r, p ^ (r & 7), :] = s16[:, r, :, p * 8:(p + 1) * 8]
+        assert np.array_equal(blob[:, :, t], want), t
+    # refill in place
+    ctx2 = ops.pack_context_kv((k * 2).cuda(), v.cuda(), H, out=ctx)
+    assert ctx2 is ctx and not np.array_equal(ctx.blob.cpu().numpy().view(np.uint16).reshape(B, H, 3, 80, 8, 8), blob)
+
+
 def test_x3_argument_errors(ops):
     from agenda_b200 import _lib
     q, k, v = _qkv(2, 64, 77, 2, 40, seed=1)
-    k_hi, k_lo = ops.split_bf16(k.cuda())
+    ctx = ops.pack_context_kv(k.cuda(), v.cuda(), 2)
     with pytest.raises(TypeError):
-        ops.attn_cross_heat_x3(q.cuda().bfloat16(), k_hi, k_lo, v.cuda().bfloat16(), 2, None)
-    maps = torch.zeros(2, 9, 64, device="cuda")
-    with pytest.raises(_lib.AgendaError):   # more than 8 heat tokens
-        ops.attn_cross_heat_x3(q.cuda(), k_hi, k_lo, v.cuda().bfloat16(), 2, maps, list(range(9)), 0)
+        ops.attn_cross_heat_x3(q.cuda().bfloat16(), ctx, None)
+    maps = torch.zeros(2, 2, 9, 64, device="cuda")
+    with pytest.raises(_lib.AgendaError):   # per-head planes for more than 8 heat tokens
+        ops.attn_cross_heat_x3(q.cuda(), ctx, maps, list(range(9)), 0, per_head=True)
     with pytest.raises(_lib.AgendaError):   # unsupported head dim
-        ops.attn_cross_heat_x3(q.cuda()[..., :48].contiguous(), k_hi[..., :48].contiguous(), k_lo[..., :48].contiguous(),
-                               v.cuda().bfloat16()[..., :48].contiguous(), 2, None)
+        ops.pack_context_kv(k.cuda()[..., :48].contiguous(), v.cuda()[..., :48].contiguous(), 2)
+    with pytest.raises(ValueError):         # context packed for another batch size
+        ops.attn_cross_heat_x3(q.cuda()[:1].contiguous(), ctx, None)

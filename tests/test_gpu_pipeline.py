@@ -456,15 +456,142 @@ def test_cli_postprocess_heatmap(cuda_ok, tmp_path):
 
 
 def test_cli_data_generation_synthetic(cuda_ok, tmp_path):
+    """--synthetic: heat-map PNGs per word and seed, plus the COCO json of the CCL boxes (fixed 42.36 px rule), read
+    back and checked against the oracle's boxes on the heat maps of the same seeds (every image is a function of its own
+    seed: the CLI ran batches of 2, the check runs one batch of 3)."""
+    import json
     from PIL import Image
     from agenda_b200 import data_generation
+    from agenda_b200.pipeline import sd15_pipeline
     n = data_generation.main(["--synthetic", "--save-dir", str(tmp_path), "--num-images", "3", "--batch-size", "2",
                               "--num-inference-steps", "1", "--word_token_heatmaps", "cars", "fg", "bg",
                               "--token-indices", "5", "6", "7", "--image-size", "112"])
     assert n == 3
-    for word in ("cars", "fg", "bg"):
+    pipe = sd15_pipeline(tokens=[5, 6, 7], num_steps=1, use_cuda_graph=False)
+    # same batch size as the CLI's (the last CLI batch was padded to 2): bit-identical heat maps, hence identical bytes
+    heats = []
+    for chunk in ([0, 1], [2, 2]):
+        hs, ctx = pipe.make_inputs(2, seeds=chunk)
+        heats.append(pipe.run_device(hs, ctx)["heat"].cpu().numpy())
+    heat = np.concatenate([heats[0], heats[1][:1]], 0)
+    for w, word in enumerate(("cars", "fg", "bg")):
         for seed in range(3):
             im = Image.open(tmp_path / f"daam_{word}_heatmaps" / f"{seed}.png")
             assert im.size == (112, 112) and im.mode == "L"
-            a = np.asarray(im)
-            assert a.max() > 200 and a.min() < 50  # min-max normalised
+            assert np.array_equal(np.asarray(im), O.heat_to_png_array(heat[seed, w], 112))
+    coco = json.load(open(tmp_path / data_generation.COCO_FILE))
+    assert coco["categories"] == [{"id": 1, "name": "small"}]
+    assert [im["id"] for im in coco["images"]] == [0, 1, 2]
+    assert [im["file_name"] for im in coco["images"]] == ["0.png", "1.png", "2.png"]
+    for seed in range(3):
+        want = O.coco_boxes_from_heat(heat[seed, 0], 0.5, 112)[:pipe.max_boxes]   # (the pipeline keeps the first max_boxes)
+        got = [tuple(a["bbox"]) for a in coco["annotations"] if a["image_id"] == seed]
+        assert got == want, seed
+    assert all(a["area"] == a["bbox"][2] * a["bbox"][3] and a["category_id"] == 1 for a in coco["annotations"])
+    assert len(coco["annotations"]) > 0
+
+
+class _FakeTokenizer:
+    def tokenize(self, text):
+        return text.split()
+
+
+class _FakePipeline:
+    """What generate_with_pipeline touches on a diffusers StableDiffusionPipeline: .unet (modules with set_processor),
+    .tokenizer, and pipeline(prompt, num_inference_steps=, generator=).images — here the attention stack on synthetic
+    hidden states drawn from the generator, and a noise image instead of a VAE decode."""
+
+    def __init__(self, stack, black_seeds=()):
+        self.unet = stack
+        self.tokenizer = _FakeTokenizer()
+        self.black = set(black_seeds)
+        self.inputs = {}
+
+    def __call__(self, prompt, num_inference_steps=20, generator=None):
+        from PIL import Image
+        seed = generator.initial_seed()
+        dt = next(self.unet.parameters()).dtype
+        hs, ctx = self.unet.make_inputs(2, "cuda", dt, seed=seed)
+        self.inputs[seed] = (hs, ctx)
+        with torch.no_grad():
+            for _ in range(num_inference_steps):
+                self.unet(hs, ctx)
+        rgb = np.zeros((64, 64, 3), np.uint8) if seed in self.black else \
+            np.random.default_rng(seed).integers(1, 255, (64, 64, 3), dtype=np.uint8)
+
+        class R:
+            images = [Image.fromarray(rgb)]
+        return R()
+
+
+@pytest.mark.parametrize("mode", ["daam", "hook"])
+def test_generation_loop_on_a_pipeline_object(cuda_ok, tmp_path, mode):
+    """The non-synthetic branch of the data_generation.py mirror (generate_with_pipeline == data_generation.py:54-86),
+    on a stand-in pipeline object: the reference's defaults (daam aggregation, precision from the pipeline dtype = fp32
+    kernels for fp32 weights), word -> context rows through the tokenizer, black-image skip, PNG tree, COCO json."""
+    import json
+    from PIL import Image
+    from agenda_b200 import UNetCrossAttentionHooker, data_generation
+    from agenda_b200.sd_attention import AttentionStack, BlockSpec
+    blocks = [BlockSpec("down0", 16, 320, 8), BlockSpec("down1", 8, 640, 8), BlockSpec("down2", 2, 1280, 8),
+              BlockSpec("mid", 4, 1280, 8), BlockSpec("up3", 16, 320, 8)]
+    stack = AttentionStack(blocks, 768, seed=4).cuda()               # fp32 weights, as the reference loads them
+    stack.unet_config_sample_size = 16
+    stack.set_attn_processor(UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=[1], precision="fp32"))
+    pipe = _FakePipeline(stack, black_seeds=[1])
+    args = data_generation.parse_args(["--save-dir", str(tmp_path), "--num-images", "3", "--num-inference-steps", "2",
+                                       "--prompt", "an aerial view image with {} cars in {} utah",
+                                       "--word_token_heatmaps", "cars", "utah", "--trace-mode", mode])
+    assert args.trace_mode == mode and args.precision == "auto"
+    stack.config = type("Cfg", (), {"sample_size": 16})()
+    saved = data_generation.generate_with_pipeline(pipe, args, used=["<v0>", "<v1>"], words=["cars", "utah", "<v0>"])
+    assert saved == 2                                                  # seed 1 produced a black image: skipped (:61-62)
+    assert sorted(os.listdir(tmp_path / "images")) == ["0.png", "2.png"]
+    prompt = "an aerial view image with <v0> cars in <v1> utah".split()
+    rows = {w: prompt.index(w) + 1 for w in ("cars", "utah", "<v0>")}  # BOS offset (dataset.py:93)
+    for seed in (0, 2):
+        hs, ctx = pipe.inputs[seed]
+        if mode == "daam":
+            sums = []
+            for b, a2 in zip(blocks, stack.attn2):
+                if b.name == "mid" or 16 // b.hw == 8:
+                    continue
+                x = hs[(b.hw, b.channels)].float().cpu()
+                q = O.head_to_batch_dim(x @ a2.to_q.weight.detach().float().cpu().T, b.heads)
+                k = O.head_to_batch_dim(ctx.float().cpu() @ a2.to_k.weight.detach().float().cpu().T, b.heads)
+                p = O.attention_probs(q, k, b.dim_head ** -0.5)[b.heads:]
+                toks = sorted(rows.values())
+                sums.append(p[:, :, toks].permute(0, 2, 1).reshape(b.heads, len(toks), b.hw, b.hw).numpy() * np.float32(2))
+            ref = O.daam_global_heat_map(sums, 16)                      # rows in sorted-token order
+        else:
+            maps = []
+            for b, a2 in zip(blocks, stack.attn2):
+                w = [t.detach().float().cpu() for t in (a2.to_q.weight, a2.to_k.weight, a2.to_v.weight,
+                                                        a2.to_out[0].weight, a2.to_out[0].bias)]
+                maps.append(O.processor_call(hs[(b.hw, b.channels)].float().cpu(), ctx.float().cpu(), *w, b.heads, False)[1])
+            ref = O.global_heat_map(maps * 2, 16)[0, sorted(rows.values())]
+        order = {t: i for i, t in enumerate(sorted(rows.values()))}
+        for word, row in rows.items():
+            got = np.asarray(Image.open(tmp_path / f"daam_{word}_heatmaps" / f"{seed}.png")).astype(np.int32)
+            want = O.heat_to_png_array(ref[order[row]], 112).astype(np.int32)
+            d = np.abs(got - want)
+            assert d.max() <= 1 and (d > 0).mean() < 0.02, (word, seed, d.max(), (d > 0).mean())
+    coco = json.load(open(tmp_path / data_generation.COCO_FILE))
+    assert [im["id"] for im in coco["images"]] == [0, 2] and coco["categories"][0]["name"] == "small"
+
+
+def test_run_seeds_is_independent_of_batch_composition(cuda_ok):
+    """Sharded generation: an image's records depend on its seed only — not on its neighbours in the
+    batch, its position in it, or the padding of a short last batch."""
+    from agenda_b200.pipeline import HeatmapPipeline
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=[2, 5, 9], num_steps=2, latent_hw=16, use_cuda_graph=True,
+                           max_boxes=16)
+    a = pipe.run_seeds([0, 1, 2, 3, 4, 5, 6], 4)            # 4 + 3 (padded)
+    b = pipe.run_seeds([6, 3, 11, 0, 5], 4)                 # other neighbours, other positions
+    for k in ("heat", "stack", "counts", "boxes"):
+        assert a[k].shape[0] == 7 and b[k].shape[0] == 5
+        for ia, ib in ((6, 0), (3, 1), (0, 3), (5, 4)):
+            assert torch.equal(a[k][ia], b[k][ib]), (k, ia, ib)
+    assert not torch.equal(a["heat"][0], a["heat"][1])
+    empty = pipe.run_seeds([], 4)
+    assert empty["heat"].shape[0] == 0 and empty["boxes"].shape == (0, 16, 5)

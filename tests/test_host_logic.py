@@ -10,6 +10,11 @@ import numpy as np
 import pytest
 import torch
 
+ROOT_ = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT_ not in sys.path:
+    sys.path.insert(0, ROOT_)
+from oracle import hook_oracle as O  # noqa: E402
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -66,33 +71,6 @@ def test_gather_records_single_process():
         gather_records({"x": torch.arange(4)}, seeds, 5)
 
 
-def _reference_box_rule(l, t, r, b, bboxes_size_px=42.36, image_size=(112, 112)):
-    """refine_label.py:58-113 restated (oracle for fixed_size_boxes; rgb_image.size == image_size)."""
-    margin_px = bboxes_size_px / 2 - 1
-    x_c_bbox = (l + r) / 2
-    y_c_bbox = (t + b) / 2
-    v = 'left' if x_c_bbox < margin_px else ('right' if x_c_bbox > image_size[0] - margin_px else None)
-    h = 'top' if y_c_bbox < margin_px else ('bottom' if y_c_bbox > image_size[1] - margin_px else None)
-    if v == 'left':
-        r_full, l_full = r, r - 42.36
-    elif v == 'right':
-        l_full, r_full = l, l + 42.36
-    else:
-        l_full, r_full = l, r
-    if h == 'top':
-        b_full, t_full = b, b - 42.36
-    elif h == 'bottom':
-        t_full, b_full = t, t + 42.36
-    else:
-        t_full, b_full = t, b
-    xc, yc = (l_full + r_full) / 2, (t_full + b_full) / 2
-    l2 = max(0, xc - bboxes_size_px / 2)
-    t2 = max(0, yc - bboxes_size_px / 2)
-    r2 = min(xc + bboxes_size_px / 2, image_size[0] - 1)
-    b2 = min(yc + bboxes_size_px / 2, image_size[1] - 1)
-    return l2, t2, r2 - l2, b2 - t2
-
-
 def test_fixed_size_boxes_matches_reference_rule():
     from agenda_b200.postprocess import fixed_size_boxes
     rng = np.random.default_rng(0)
@@ -101,9 +79,36 @@ def test_fixed_size_boxes_matches_reference_rule():
     xywh[:, 3] = np.minimum(xywh[:, 3], 112 - xywh[:, 1])
     got = fixed_size_boxes(xywh)
     for i, (x, y, w, h) in enumerate(xywh):
-        assert tuple(got[i]) == _reference_box_rule(x, y, x + w, y + h), i
+        assert tuple(got[i]) == O.fixed_size_box_rule(x, y, x + w, y + h), i
     centre = fixed_size_boxes(np.array([[50, 50, 10, 10, 100]]))[0]
     assert np.allclose(centre, [55 - 21.18, 55 - 21.18, 42.36, 42.36])
+    assert fixed_size_boxes(np.zeros((0, 5))).shape == (0, 4)
+    assert fixed_size_boxes(np.array([1.0, 2.0, 3.0, 4.0])).shape == (1, 4)
+
+
+def test_ccl_boxes_to_coco_json(tmp_path):
+    """CCL output (counts, padded int boxes on the L x L map) -> image-grid fixed-size boxes -> COCO dict in the
+    reference's layout (refine_label.py:28-48,126-135; [x, y, w, h] top-left, Data/README.md:7) -> json round trip."""
+    import json
+    from agenda_b200 import postprocess
+    counts = np.array([2, 0, 1], dtype=np.int32)
+    boxes = np.zeros((3, 4, 5), dtype=np.int32)
+    boxes[0, 0] = (10, 12, 6, 4, 20); boxes[0, 1] = (0, 60, 3, 4, 9); boxes[2, 0] = (60, 1, 4, 2, 8)
+    per = postprocess.ccl_boxes_to_coco_boxes(counts, boxes, map_size=64, image_size=112)
+    assert [p.shape for p in per] == [(2, 4), (0, 4), (1, 4)]
+    s = 112 / 64
+    for got, raw in ((per[0][0], boxes[0, 0]), (per[0][1], boxes[0, 1]), (per[2][0], boxes[2, 0])):
+        x, y, w, h = (float(v) * s for v in raw[:4])
+        assert tuple(got) == O.fixed_size_box_rule(x, y, x + w, y + h)
+    coco = postprocess.coco_annotations(["7.png", "8.png", "9.png"], per, (112, 112), image_ids=[7, 8, 9])
+    assert coco["categories"] == [{"id": 1, "name": "small"}]
+    assert [im["id"] for im in coco["images"]] == [7, 8, 9] and coco["images"][0]["width"] == 112
+    assert [a["image_id"] for a in coco["annotations"]] == [7, 7, 9]
+    a0 = coco["annotations"][0]
+    assert a0["iscrowd"] == 0 and a0["category_id"] == 1 and a0["area"] == a0["bbox"][2] * a0["bbox"][3]
+    path = tmp_path / "ann.json"
+    postprocess.write_coco_json(str(path), coco)
+    assert json.load(open(path)) == coco
 
 
 def _flags(src):
