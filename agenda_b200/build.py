@@ -30,13 +30,21 @@ def _stale() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def _variants_wanted() -> bool:
+    return os.environ.get("AGENDA_BUILD_VARIANTS", "0") == "1"
+
+
+def build(force: bool = False, verbose: bool = False, variants=None) -> str:
+    """variants=True (or AGENDA_BUILD_VARIANTS=1) adds -DAGENDA_VARIANTS: the measurement / test variants of the
+    self-attention kernel (agenda_attn_self_fwd_variant 10..58).  The product library does not carry them."""
+    variants = _variants_wanted() if variants is None else variants
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libagenda_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    cmd = ([nvcc] + NVCC_FLAGS + (["-DAGENDA_VARIANTS"] if variants else []) + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", LIB] + sources())
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
@@ -46,4 +54,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variants=True if "--variants" in sys.argv else None))

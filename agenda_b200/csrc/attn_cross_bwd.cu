@@ -218,7 +218,7 @@ int launch_bwd(const void* q, const void* k, const void* v, const void* d_out, c
   if (smem > 200 * 1024)
     return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross_bwd: M=%d, d=%d needs %zu B of shared memory (> 200 KB)", M, d, smem);
   auto kern = attn_cross_bwd_kernel<T>;
-  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(kern, smem);
   dim3 grid((N + kBwdRows - 1) / kBwdRows, B * H);
   kern<<<grid, kBwdThreads, smem, stream>>>(static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v),
                                             static_cast<const T*>(d_out), d_maps, static_cast<T*>(dq), dk, dv, tl, H, N,

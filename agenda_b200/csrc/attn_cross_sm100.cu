@@ -369,7 +369,7 @@ static int launch_cross_t(const void* q, const void* k, const void* v, void* out
   if ((rc = make_head_map(&mv, v, B, H, M, D, sm100::kXMPad)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::x_smem_bytes<D>();
   auto kern = sm100::attn_cross_sm100_kernel<D, kFew>;
-  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(kern, smem);
   dim3 grid((N + sm100::kXBlockM - 1) / sm100::kXBlockM, B);
   // few (batch, query tile) pairs: split the heads over a cluster along z while the grid still fits one wave
   int hs = 1;
@@ -378,7 +378,7 @@ static int launch_cross_t(const void* q, const void* k, const void* v, void* out
                                 cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
     // (measured on B200, tools/bench_cross.py: N = 256 26.7 -> 13.1 us and N = 64 19.3 -> 9.7 us at 4; 8 is slower)
     while (hs < 4 && H % (hs * 2) == 0 && static_cast<long long>(grid.x) * grid.y * hs * 2 <= sms) hs *= 2;
-    if (const char* e = getenv("AGENDA_XSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && H % v == 0) hs = v; }
+    if (const char* e = knob("AGENDA_XSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 8 && H % v == 0) hs = v; }
   }
   grid.z = hs;
   const float scale_log2 = scale * 1.4426950408889634f;
@@ -421,12 +421,12 @@ int attn_cross_sm100(const void* q, const void* k, const void* v, void* out, int
   // Q ring.  QT query tiles per CTA: the smallest count that puts the whole launch into one wave of CTAs.
   {
     bool use_res = (d == 40 || d == 64) && H <= 8 && (maps == nullptr || tl.n <= sm100::kXFewTokens);
-    if (const char* e = getenv("AGENDA_XRES")) use_res = use_res && atoi(e) != 0;
+    if (const char* e = knob("AGENDA_XRES")) use_res = use_res && atoi(e) != 0;
     if (use_res) {
       const int n_tiles = (N + sm100::kXBlockM - 1) / sm100::kXBlockM, sms = num_sms();
       int QT = 1;
       while (QT < 32 && ((n_tiles + QT - 1) / QT) * B > sms) ++QT;
-      if (const char* e = getenv("AGENDA_XRES_QT")) { const int t = atoi(e); if (t >= 1 && t <= 64) QT = t; }
+      if (const char* e = knob("AGENDA_XRES_QT")) { const int t = atoi(e); if (t >= 1 && t <= 64) QT = t; }
       // one CTA per SM: pays off once every CTA amortises its K/V block over several query tiles (B = 16, N = 4096:
       // 49 vs 55 us); small launches (QT = 1) keep the two-CTAs-per-SM kernel below
       if (QT >= 2)

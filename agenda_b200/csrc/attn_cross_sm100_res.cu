@@ -393,12 +393,12 @@ static int launch_cross_res(const void* q, const void* k, const void* v, void* o
   if ((rc = make_head_map(&mv, v, B, H, M, D, sm100::kRMPad)) != AGENDA_OK) return rc;
   const size_t smem = sm100::r_smem_bytes(H);
   auto kern = sm100::attn_cross_sm100_res_kernel<D>;
-  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(kern, smem);
   const int n_tiles = (N + 127) / 128;
   dim3 grid((n_tiles + QT - 1) / QT, B);
   kern<<<grid, sm100::kRThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), maps, tl, H, N, M, QT,
                                                  b_first, accumulate, scale * 1.4426950408889634f,
-                                                 getenv("AGENDA_XRES_PF") ? atoi(getenv("AGENDA_XRES_PF")) : 0);
+                                                 knob("AGENDA_XRES_PF") ? atoi(knob("AGENDA_XRES_PF")) : 0);
   AGENDA_LAUNCH_CHECK("attn_cross_sm100_res_kernel");
   return AGENDA_OK;
 }

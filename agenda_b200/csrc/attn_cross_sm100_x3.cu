@@ -676,11 +676,7 @@ static int launch_cross_x3(const float* q, const void* kv_blob, void* out, int B
   const size_t smem = 1024 + C::kFixedBytes + static_cast<size_t>(n_stages) * C::kQ32Bytes +
                       static_cast<size_t>(2) * QT * n_heat * 128 * 4 + sizeof(sm100::TBarriers) + 64;
   auto kern = sm100::attn_cross_sm100_x3_kernel<D, OutT, kAll>;
-  static bool attr_set = false;  // (per template instantiation)
-  if (!attr_set) {
-    AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sm100::kTSmemMax));
-    attr_set = true;
-  }
+  AGENDA_DYN_SMEM(kern, sm100::kTSmemMax);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kAll ? 256 : 384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -191,8 +191,8 @@ template <typename T, bool CROSS>
 static int launch_attn_f32(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
                            float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream) {
   const size_t smem = attn_f32_smem(d, CROSS ? tl.n : 0);
-  AGENDA_CUDA(cudaFuncSetAttribute(attn_f32_kernel<T, CROSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+  auto kern = attn_f32_kernel<T, CROSS>;
+  AGENDA_DYN_SMEM(kern, smem);
   dim3 grid((N + kTQ - 1) / kTQ, CROSS ? B : B * H);
   attn_f32_kernel<T, CROSS><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v), static_cast<T*>(out), B, H, N, M,

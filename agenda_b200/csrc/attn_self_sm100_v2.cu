@@ -657,22 +657,22 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 
 template <int D, int kEmu, int NT, int BN, int KS = 1, bool kFast = false, bool kUnit = false>
 static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, long long ld) {
   using C = sm100::V2Cfg<D, NT, BN, KS>;
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
-  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
-  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, 128, ld)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN, ld)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN, ld)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::v2_smem_bytes<C>();
   auto kern = sm100::attn_self_sm100_v2_kernel<D, kEmu, NT, BN, KS, kFast, kUnit>;
-  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(kern, smem);
   dim3 grid(static_cast<unsigned>(((N + 128 * NT - 1) / (128 * NT)) * B * H));
   // measured on B200 (tools/bench_attn.py): one MMA warp per query tile (2) wins except where P aliases S (d = 80)
   int issue_order = C::kAliasP ? 0 : 2;
-  if (const char* e = getenv("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only (+4: exp-pass ping-pong)
+  if (const char* e = knob("AGENDA_V2_ORDER")) issue_order = atoi(e);  // experiments only (+4: exp-pass ping-pong)
   int stagger = (NT == 2 && !C::kAliasP) ? 800 : 0;  // cycles; measured on B200 (tools/bench_attn.py)
-  if (const char* e = getenv("AGENDA_V2_SKEW")) stagger = atoi(e);
+  if (const char* e = knob("AGENDA_V2_SKEW")) stagger = atoi(e);
   issue_order |= stagger << 8;
   kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
                                             kUnit ? 1.0f : scale * 1.4426950408889634f, issue_order);
@@ -684,28 +684,35 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
 // tiles: 2 = two 128-query tiles per CTA with 128-key tiles (64 for d = 160); 3 = three query tiles with 64-key
 // tiles (d = 40 / 64 only); 4 = two query tiles, each served by two warpgroups owning half a row (d = 40 / 64).
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, int tiles, void* stream) {
+                       int emu, int tiles, void* stream, long long ld) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tiles >= 100) {  // fast first pass, instantiated for the shipped defaults (+ two emulation shares for measurements)
-    if (d == 40 && tiles == 203 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 40 && tiles == 103 && emu == 2) return launch_v2<40, 2, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 40 && tiles == 103 && emu == 4) return launch_v2<40, 4, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 64 && tiles == 102 && emu == 4) return launch_v2<64, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 64 && tiles == 102 && emu == 3) return launch_v2<64, 3, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 64 && tiles == 102 && emu == 2) return launch_v2<64, 2, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 80 && tiles == 102 && emu == 4) return launch_v2<80, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 80 && tiles == 105 && emu == 4) return launch_v2<80, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
-    if (d == 160 && tiles == 102 && emu == 4) return launch_v2<160, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st);
+  // ---- shipped configurations (what agenda_attn_self_fwd / _strided dispatch to) ----
+  if (d == 40 && tiles == 203 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true, true>(q, k, v, out, B, H, N, scale, st, ld);
+  if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+  if (d == 64 && tiles == 102 && emu == 4) return launch_v2<64, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+  if (d == 80 && tiles == 105 && emu == 4) return launch_v2<80, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+  if (d == 160 && tiles == 2 && emu == 4) return launch_v2<160, 4, 2, 64, 1>(q, k, v, out, B, H, N, scale, st, ld);
+#ifndef AGENDA_VARIANTS
+  return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: kernel variant (d=%d, tiles=%d, emu=%d) exists only in builds with "
+              "-DAGENDA_VARIANTS (tests / measurements)", d, tiles, emu);
+#else
+  // ---- measurement / test variants (python -m agenda_b200.build --variants) ----
+  if (tiles >= 100) {  // fast first pass with other emulation shares / tile shapes
+    if (d == 40 && tiles == 103 && emu == 2) return launch_v2<40, 2, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+    if (d == 40 && tiles == 103 && emu == 4) return launch_v2<40, 4, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+    if (d == 64 && tiles == 102 && emu == 3) return launch_v2<64, 3, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+    if (d == 64 && tiles == 102 && emu == 2) return launch_v2<64, 2, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+    if (d == 80 && tiles == 102 && emu == 4) return launch_v2<80, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
+    if (d == 160 && tiles == 102 && emu == 4) return launch_v2<160, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
     tiles -= 100;
   }
 #define AGENDA_V2_EMU(DD, NT, BN, KS)                                                   \
     switch (emu) {                                                                      \
-      case 0: return launch_v2<DD, 0, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
-      case 2: return launch_v2<DD, 2, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
-      case 3: return launch_v2<DD, 3, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
-      case 8: return launch_v2<DD, 8, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);    \
-      default: return launch_v2<DD, 4, NT, BN, KS>(q, k, v, out, B, H, N, scale, st);   \
+      case 0: return launch_v2<DD, 0, NT, BN, KS>(q, k, v, out, B, H, N, scale, st, ld);    \
+      case 2: return launch_v2<DD, 2, NT, BN, KS>(q, k, v, out, B, H, N, scale, st, ld);    \
+      case 3: return launch_v2<DD, 3, NT, BN, KS>(q, k, v, out, B, H, N, scale, st, ld);    \
+      case 8: return launch_v2<DD, 8, NT, BN, KS>(q, k, v, out, B, H, N, scale, st, ld);    \
+      default: return launch_v2<DD, 4, NT, BN, KS>(q, k, v, out, B, H, N, scale, st, ld);   \
     }
   if (tiles == 3) {
     switch (d) {
@@ -741,6 +748,7 @@ int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, i
     default: return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: head dim %d not in {40,64,80,160}", d);
   }
 #undef AGENDA_V2_EMU
+#endif  // AGENDA_VARIANTS
 }
 
 #ifdef AGENDA_V2_TRACE

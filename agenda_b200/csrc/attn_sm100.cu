@@ -296,17 +296,10 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [B, N, H*d] bf16 viewed as (d, H, N, B); box (64, 1, rows, 1), 128-byte swizzle, zero fill out of bounds.
-// Row stride (elements) of the NEXT tensor maps built on this thread; 0 = packed rows of H*d.  Set only for the duration
-// of agenda_attn_self_fwd_strided (q/k/v as column slices of one fused-projection output) — thread-local call scratch,
-// not library state.
-static thread_local long long g_row_stride = 0;
-// Same lifetime: q of the current agenda_attn_self_fwd_strided call already carries scale * log2(e) (its scale == 0).
-static thread_local bool g_q_prescaled = false;
-
-int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows) {
+int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows, long long row_stride) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t C = g_row_stride ? static_cast<cuuint64_t>(g_row_stride) : static_cast<cuuint64_t>(H) * d;
+  const cuuint64_t C = row_stride ? static_cast<cuuint64_t>(row_stride) : static_cast<cuuint64_t>(H) * d;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N),
                         static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(d) * 2, C * 2, static_cast<cuuint64_t>(N) * C * 2};
@@ -321,16 +314,16 @@ int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d
 
 template <int D, bool kPTmem>
 static int launch_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, long long ld) {
   using C = sm100::Cfg<D>;
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_head_map(&mq, q, B, H, N, D, sm100::kBlockM)) != AGENDA_OK) return rc;
-  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
-  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, sm100::kBlockM, ld)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, N, D, C::kBlockN, ld)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, N, D, C::kBlockN, ld)) != AGENDA_OK) return rc;
   constexpr size_t smem = sm100::smem_bytes<D, kPTmem>();
   auto kern = sm100::attn_self_sm100_kernel<D, kPTmem>;
-  AGENDA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(kern, smem);
   dim3 grid((N + sm100::kBlockM - 1) / sm100::kBlockM, B * H);
   kern<<<grid, sm100::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
                                                 scale * 1.4426950408889634f);
@@ -342,12 +335,13 @@ int attn_common_checks(const char* who, const void* q, const void* k, const void
                        int H, int N, int M, int d);
 
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, int tiles, void* stream);
+                       int emu, int tiles, void* stream, long long ld);
 
 // variant: 0 = two query tiles per CTA, ping-pong softmax warpgroups (v2; falls back to variant 1 when N <= 128),
 //          1 = one query tile per CTA, P through TMEM (TS-form PV MMA), 2 = same with P through shared memory (SS)
+// ld: row stride of q/k/v in elements (0 = packed H*d); q_prescaled: q already carries scale * log2(e) (ABI: scale == 0)
 int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                    int variant, void* stream) {
+                    int variant, void* stream, long long ld = 0, bool q_prescaled = false) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
@@ -361,37 +355,41 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   // (62 / 63 / 64: the same with 50 / 37.5 / 25 % emulated exponentials where instantiated: d = 40, 64)
   if (variant >= 60) {
     const int e = variant - 60;
-    if (d == 80 && e == 5) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream);  // 64-key tiles
-    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, e ? e : 3, 103, stream)
-                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, e ? e : 4, 102, stream);
+    if (d == 80 && e == 5) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream, ld);  // 64-key tiles
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, e ? e : 3, 103, stream, ld)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, e ? e : 4, 102, stream, ld);
   }
-  if (variant >= 50) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 50, 6, stream);
-  if (variant >= 40) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 40, 5, stream);
-  if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream);
-  if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream);
-  if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream);
+  if (variant >= 50) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 50, 6, stream, ld);
+  if (variant >= 40) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 40, 5, stream, ld);
+  if (variant >= 30) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 30, 4, stream, ld);
+  if (variant >= 20) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 20, 3, stream, ld);
+  if (variant >= 10) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, variant - 10, 2, stream, ld);
   // defaults measured on B200 (tools/bench_attn.py): d = 40: three query tiles with 64-key tiles, 37.5 % of the
   // exponentials on the FMA pipe; otherwise two query tiles with 128-key tiles (64 at d = 160), 25 %
   // and the fast first pass (first-tile maximum + row-sum check, exact second pass for the CTAs that need it);
   // AGENDA_V2_FAST=0 keeps the running maximum in a single pass (measurements)
   // agenda_attn_self_fwd_strided with scale == 0: q already carries scale * log2(e)
-  if (g_q_prescaled) {
+  // AGENDA_V2_FAST=0 (variant builds only) keeps the running maximum in a single pass (measurements)
+#ifdef AGENDA_VARIANTS
+  static const int fast = [] { const char* e = knob("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 100; }();
+#else
+  constexpr int fast = 100;
+#endif
+  if (q_prescaled) {
     scale = 0.6931471805599453f;  // kernels without the unit-scale form: scale * log2(e) = 1
-    static const int fast0 = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 1; }();
-    if (variant == 0 && N > 128 && d == 40 && fast0) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 203, stream);
+    if (variant == 0 && N > 128 && d == 40 && fast) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 203, stream, ld);
   }
   if (variant == 0 && N > 128) {
-    static const int fast = [] { const char* e = getenv("AGENDA_V2_FAST"); return (e && atoi(e) == 0) ? 0 : 100; }();
     // (d = 160 only occurs at N <= 256 in the SD UNets: four key tiles do not amortise the fast pass's epilogue)
     // d = 80: 64-key tiles so that P gets its own TMEM columns (0.071 vs 0.076 ms with P aliased onto S at N = 1024)
-    if (d == 80 && fast) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream);
-    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3 + fast, stream)
-                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2 + (d == 160 ? 0 : fast), stream);
+    if (d == 80 && fast) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream, ld);
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3 + fast, stream, ld)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2 + (d == 160 ? 0 : fast), stream, ld);
   }
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
-    return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st)                        \
-                        : launch_sm100<DD, false>(q, k, v, out, B, H, N, scale, st);
+    return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st, ld)                        \
+                        : launch_sm100<DD, false>(q, k, v, out, B, H, N, scale, st, ld);
   switch (d) {
     AGENDA_DISPATCH(40)
     AGENDA_DISPATCH(64)
@@ -422,12 +420,7 @@ extern "C" int agenda_attn_self_fwd_strided(const void* q, const void* k, const 
   if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_strided: bf16 only (dtype=1)");
   if (ld < static_cast<long long>(H) * d || (ld & 7))
     return fail(AGENDA_ERR_BAD_SHAPE, "attn_self_fwd_strided: ld=%lld must be >= H*d=%d and a multiple of 8", ld, H * d);
-  g_row_stride = ld;
-  g_q_prescaled = (scale == 0.0f);
-  rc = attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
-  g_row_stride = 0;
-  g_q_prescaled = false;
-  return rc;
+  return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream, ld, scale == 0.0f);
 }
 
 // Test hook: same contract, explicit kernel variant (see attn_self_sm100).

@@ -882,7 +882,7 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   // Shared-memory budget per CTA.  100 KB lets two CTAs (of different clusters) share an SM, so one cluster's
   // barrier waits are covered by another's work; AGENDA_CCL_SMEM_KB overrides it for experiments.
   size_t budget = 100 * 1024;
-  if (const char* e = getenv("AGENDA_CCL_SMEM_KB")) { const long kb = atol(e); if (kb >= 8 && kb <= 220) budget = static_cast<size_t>(kb) * 1024; }
+  if (const char* e = knob("AGENDA_CCL_SMEM_KB")) { const long kb = atol(e); if (kb >= 8 && kb <= 220) budget = static_cast<size_t>(kb) * 1024; }
   const size_t map_bytes = static_cast<size_t>(H) * W * 4;
   const int wpr = (W + 31) / 32;
   // per strip of R rows: fp32 strip R*W*4 (re-used for the union-find slots: R*wpr*64 B) + bit mask R*wpr*4
@@ -902,7 +902,7 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
   const int strip_px = R * W;
   // measured on 512x512 maps (16 strips of 32 rows): 256 threads 2.86 ms / 512: 3.36 / 1024: 6.0 per 2048 maps
   int threads = strip_px >= 65536 ? 1024 : (strip_px >= 32768 ? 512 : 256);
-  if (const char* e = getenv("AGENDA_CCL_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 1024 && t % 32 == 0) threads = t; }
+  if (const char* e = knob("AGENDA_CCL_THREADS")) { const int t = atoi(e); if (t >= 64 && t <= 1024 && t % 32 == 0) threads = t; }
   const int use_bulk = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(heat) & 15) == 0);
 
   // ---- one CTA per map when the bit mask fits (see ccl_bbox_cta_kernel); the cluster kernel then only redoes flagged maps ----
@@ -912,11 +912,11 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
     const long long n_words = n_px / 32;
     bool use_cta = counts != nullptr && (W & 31) == 0 && n_words <= 12288 && (reinterpret_cast<uintptr_t>(heat) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(labels) & 15) == 0;
-    if (const char* e = getenv("AGENDA_CCL_CTA")) use_cta = use_cta && atoi(e) != 0;
+    if (const char* e = knob("AGENDA_CCL_CTA")) use_cta = use_cta && atoi(e) != 0;
     if (use_cta) {
       const size_t fixed = static_cast<size_t>(n_words) * 6;  // mask words (4 B) + first piece id per word (2 B)
       size_t target = std::max<size_t>(72 * 1024, fixed + 16 * 1024);  // 72 KB: three CTAs per SM
-      if (const char* e = getenv("AGENDA_CCL_CTA_SMEM_KB")) { const long kb = atol(e); if (kb >= 4 && kb <= 200) target = static_cast<size_t>(kb) * 1024; }
+      if (const char* e = knob("AGENDA_CCL_CTA_SMEM_KB")) { const long kb = atol(e); if (kb >= 4 && kb <= 200) target = static_cast<size_t>(kb) * 1024; }
       long long cap = std::min<long long>({16 * n_words, 65535ll, static_cast<long long>((target - std::min(target, fixed)) / 4)});
       cap &= ~1ll;  // keeps the u16 table 4-byte aligned behind the slots
       if (cap >= 64 || cap >= 16 * n_words - 1) {
@@ -960,12 +960,12 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
     }                                                                                                                  \
   } while (0)
         int cta_cluster = 1;  // 4: split the two streaming passes of a map over a 4-CTA cluster
-        if (const char* e = getenv("AGENDA_CCL_CTA_CLUSTER")) { const int c = atoi(e); cta_cluster = (c == 4 || c == 2) ? c : 1; }
+        if (const char* e = knob("AGENDA_CCL_CTA_CLUSTER")) { const int c = atoi(e); cta_cluster = (c == 4 || c == 2) ? c : 1; }
         if (n_words < 64) cta_cluster = 1;
         int hints = 1;  // measured: +1-2 % (pass 2 still misses L2: ~300 MB of maps are in flight, L2 is 126 MB)
-        if (const char* e = getenv("AGENDA_CCL_HINTS")) hints = atoi(e);
+        if (const char* e = knob("AGENDA_CCL_HINTS")) hints = atoi(e);
         int cta_threads = n_px >= 65536 ? 1024 : (n_px >= 16384 ? 256 : 128);
-        if (const char* e = getenv("AGENDA_CCL_CTA_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) cta_threads = t; }
+        if (const char* e = knob("AGENDA_CCL_CTA_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) cta_threads = t; }
         if (cta_threads == 1024) AGENDA_CCL_CTA(1024);
         else if (cta_threads == 512) AGENDA_CCL_CTA(512);
         else if (cta_threads == 256) AGENDA_CCL_CTA(256);

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/agenda_b200.h"
 
@@ -36,6 +37,28 @@ inline int num_sms() {
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   return n > 0 ? n : 148;
 }
+
+// Test / measurement switches.  They are consulted only when AGENDA_KNOBS=1 was in the environment when
+// the library was first used (tests/conftest.py sets it): the production hot path makes no getenv call at all.
+inline const char* knob(const char* name) {
+  static const bool on = [] { const char* e = getenv("AGENDA_KNOBS"); return e != nullptr && atoi(e) != 0; }();
+  return on ? getenv(name) : nullptr;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (launch site, device) instead of once per launch: the
+// attribute sticks to the function in the device's context.  `bytes` may vary per call: it is raised when a larger
+// value comes along.  (A benign race between host threads at worst repeats the call.)
+#define AGENDA_DYN_SMEM(kernel, bytes)                                                                              \
+  do {                                                                                                              \
+    static int _agenda_set[64] = {0};                                                                               \
+    int _dev = 0;                                                                                                   \
+    cudaGetDevice(&_dev);                                                                                           \
+    const int _need = static_cast<int>(bytes);                                                                      \
+    if (_agenda_set[_dev & 63] < _need) {                                                                           \
+      AGENDA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _need));                \
+      _agenda_set[_dev & 63] = _need;                                                                               \
+    }                                                                                                               \
+  } while (0)
 
 constexpr int kMaxTokens = 128;
 // heat-map token selection, passed to kernels by value

@@ -198,8 +198,7 @@ static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes,
     const int threads_t = L * (256 / L);  // a multiple of L: each thread keeps one output column in pass 1
     const size_t smem = sizeof(float) * (((static_cast<size_t>(h) * w + 3) & ~size_t(3)) + static_cast<size_t>(h) * L +
                                          4 * L) + sizeof(int) * 4 * L;
-    AGENDA_CUDA(cudaFuncSetAttribute(heat_upsample_accum_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
+    AGENDA_DYN_SMEM(heat_upsample_accum_tiled_kernel, smem);
     // small source planes: several planes per CTA (the tap tables are built once); larger ones: one CTA per plane
     const int grid_t = (h * w <= 256) ? std::min(n_planes, num_sms() * 8) : n_planes;
     heat_upsample_accum_tiled_kernel<<<grid_t, threads_t, smem, static_cast<cudaStream_t>(stream)>>>(maps, acc, n_planes,

@@ -310,7 +310,7 @@ static int launch_resize(const char* who, const void* in, uint8_t* out, int n, i
   int rc = resize_shape_check(who, n, Hi, Wi, Ho, Wo, 1, &smem);
   if (rc != AGENDA_OK) return rc;
   if (n == 0) return AGENDA_OK;
-  AGENDA_CUDA(cudaFuncSetAttribute(resize_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(resize_kernel<MODE>, smem);
   resize_kernel<MODE><<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(in, out, Hi, Wi, Ho, Wo);
   AGENDA_LAUNCH_CHECK(who);
   return AGENDA_OK;
@@ -355,8 +355,7 @@ extern "C" int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes,
   int rc = resize_shape_check("heat_postprocess_stack", n, Hi, Wi, Ho, Wo, 3, &smem);
   if (rc != AGENDA_OK) return rc;
   if (n == 0) return AGENDA_OK;
-  AGENDA_CUDA(cudaFuncSetAttribute(postprocess_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+  AGENDA_DYN_SMEM(postprocess_stack_kernel, smem);
   postprocess_stack_kernel<<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(heat, planes, stack, inv, Hi,
                                                                                         Wi, Ho, Wo);
   AGENDA_LAUNCH_CHECK("postprocess_stack_kernel");

@@ -140,6 +140,83 @@ def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
                        "synthetic activations"}
 
 
+# ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the probes below (profiles/r02_*_key_metrics.txt);
+# None = not captured for that shape
+NCU_TRAFFIC = {}
+
+
+def _time_launches(fn, reps, graph=False):
+    import torch
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    if graph:   # kernels shorter than a ctypes call: replay the launches from a CUDA graph so the device is timed
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if graph:
+        g.replay()
+    else:
+        for _ in range(reps):
+            fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def probe_hbm_kernels(dev, hbm_gbs):
+    """Standalone probes of the remaining HBM-bound kernels, inputs larger than L2: K3 (bicubic upsample + clamp +
+    accumulate, hook.py:70-79), K4/K5 (normalise -> u8 -> PIL-bicubic resize -> stack, data_generation.py:82-85 +
+    postprocess_heatmap.py:44-46) and K7 (cross-attention backward, training mode)."""
+    import torch
+    from agenda_b200 import ops
+    out = {}
+    # K3: 32 -> 64 on 19712 planes (0.7 GB of accumulator): read h*w*4 + read-modify-write L*L*8 per plane
+    n_pl, h, L = 256 * 77, 32, 64
+    acc = torch.zeros((n_pl, L, L), device=dev)
+    m = torch.rand((n_pl, h, h), device=dev)
+    ms = _time_launches(lambda: ops.heat_upsample_accum(m, acc), 5)
+    by = n_pl * (h * h * 4 + L * L * 8)
+    out["heat_upsample_accum_32to64"] = {"kernel": "heat_upsample_accum_tiled_kernel", "bound": "hbm", "achieved": by / ms / 1e6,
+                                         "peak": hbm_gbs, "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms,
+                                         "planes": n_pl, "traffic": NCU_TRAFFIC.get("heat_upsample_accum_32to64"),
+                                         "note": "algorithmic bytes per plane = h*w*4 read + L*L*(4 read + 4 written)"}
+    del acc, m
+    # K4/K5: 8192 images, three 64x64 fp32 planes each -> planes u8 [3,112,112] + stack [112,112,3] + inverted bg [112,112]
+    n_img, S = 8192, 112
+    heat = torch.rand((n_img, 3, L, L), device=dev)
+    ms = _time_launches(lambda: ops.heat_postprocess_stack(heat, S), 5)
+    by = n_img * (3 * L * L * 4 + S * S * 7)
+    out["heat_postprocess_stack_64to112"] = {"kernel": "postprocess_stack_kernel", "bound": "hbm", "achieved": by / ms / 1e6,
+                                             "peak": hbm_gbs, "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms,
+                                             "images": n_img, "traffic": NCU_TRAFFIC.get("heat_postprocess_stack_64to112"),
+                                             "note": "algorithmic bytes per image = 3*L*L*4 read + S*S*(3+3+1) written; bound "
+                                                     "by PIL's exact two-pass 8-bit fixed-point filter arithmetic, not by HBM"}
+    del heat
+    # K7: cross-attention backward at the 64x64 layer shape of one training sample pair (B = 2)
+    B, N, H, d, T = 2, 4096, 8, 40, 3
+    q = torch.randn(B, N, H * d, device=dev).bfloat16()
+    k = torch.randn(B, 77, H * d, device=dev).bfloat16()
+    v = torch.randn(B, 77, H * d, device=dev).bfloat16()
+    go = torch.randn_like(q)
+    gm = torch.randn(B, T, N, device=dev)
+    toks = list(range(5, 5 + T))
+    ms = _time_launches(lambda: ops.attn_cross_bwd(q, k, v, go, gm, H, toks, 0), 20, graph=True)
+    by = 3 * B * N * H * d * 2 + 2 * B * 77 * H * d * 2 + 2 * B * 77 * H * d * 4 + gm.numel() * 4
+    fl = 10.0 * B * H * N * 77 * d
+    out["cross_attention_backward"] = {"kernel": "attn_cross_bwd_kernel", "bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm_gbs,
+                                       "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms, "fp32_tflops": fl / ms / 1e9,
+                                       "traffic": NCU_TRAFFIC.get("cross_attention_backward"),
+                                       "note": "B=2, N=4096, d=40, T=3 (includes the memsets / casts of dK, dV); far from both "
+                                               "roofs: fp32 CUDA-core kernel, shared-memory and atomics bound"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -409,10 +486,10 @@ def run_ours(args):
 
     # cross-attention + heat epilogue (K2, HBM-bound): the same eager replay, in-pipeline cache state (Q was just
     # written by the to_q GEMM).  The shipped path is the split-precision kernel (fp32 Q in, bf16 O out):
-    # args: q,k_hi,k_lo,v,out,out_dtype,B,H,N,M,d,scale,token_idx,T,b_first,per_head,maps,accumulate,stream
+    # args: q,kv_blob,out,out_dtype,B,H,N,M,d,scale,token_idx,T,b_first,per_head,maps,accumulate,stream
     def cross_bytes_x3(a):
-        B_, H_, N_, M_, d_, T_, bf_ = a[6], a[7], a[8], a[9], a[10], a[13], a[14]
-        out_b = 4.0 if a[5] == 0 else 2.0
+        B_, H_, N_, M_, d_, T_, bf_ = a[4], a[5], a[6], a[7], a[8], a[11], a[12]
+        out_b = 4.0 if a[3] == 0 else 2.0
         return B_ * N_ * H_ * d_ * (4.0 + out_b) + 3.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
 
     # plain bf16 kernel (cross_logits="bf16"): q,k,v,out,dtype,B,H,N,M,d,scale,token_idx,T,b_first,maps,accumulate,stream
@@ -420,7 +497,7 @@ def run_ours(args):
         B_, H_, N_, M_, d_, T_, bf_ = a[5], a[6], a[7], a[8], a[9], a[12], a[13]
         return 2.0 * B_ * N_ * H_ * d_ * 2 + 2.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
     if sink["agenda_attn_cross_fwd_heat_x3"]:
-        cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat_x3"], cross_bytes_x3, 8, "attn_cross_sm100_x3_kernel"
+        cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat_x3"], cross_bytes_x3, 6, "attn_cross_sm100_x3_kernel"
         note = "Q fp32 in + O bf16 out + K_hi,K_lo,V in + selected-token heat planes out"
     else:
         cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat"], cross_bytes, 7, "attn_cross_sm100_res_kernel"
@@ -434,6 +511,8 @@ def run_ours(args):
                                          "ms_per_denoise_step_all_layers": ms_x_all / 5.0,
                                          "share_of_step": (ms_x_all / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
                                          "note": "N=%d layers; algorithmic bytes = %s" % (big_n, note)}
+
+    extra.update(probe_hbm_kernels(dev, hbm_gbs))
 
     # ---- parity of THIS run's heat maps: images 0 and 1 of the benchmarked batch against the oracle's fp32 evaluation
     #      of hook.py on the fp32 checkpoint weights (the checker; never on the product path) ----

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# the library consults its test / measurement switches (AGENDA_XRES, AGENDA_XSPLIT, ...) only when this was set before
+# its first use; production runs (bench.py, the CLIs) never call getenv on the launch path
+os.environ.setdefault("AGENDA_KNOBS", "1")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")

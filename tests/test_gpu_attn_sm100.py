@@ -23,8 +23,13 @@ def _run(lib, q, k, v, H, variant):
     d = C // H
     qd, kd, vd = (t.cuda().contiguous() for t in (q, k, v))
     out = torch.full_like(qd, float("nan"))
-    lib.call("agenda_attn_self_fwd_variant", qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), B, H, N, d,
-             float(d ** -0.5), variant, torch.cuda.current_stream().cuda_stream)
+    try:
+        lib.call("agenda_attn_self_fwd_variant", qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), B, H, N, d,
+                 float(d ** -0.5), variant, torch.cuda.current_stream().cuda_stream)
+    except lib.AgendaError as e:
+        if "AGENDA_VARIANTS" in str(e):   # measurement variants are not in the product library
+            pytest.skip("kernel variant only in builds with -DAGENDA_VARIANTS (python -m agenda_b200.build --variants)")
+        raise
     torch.cuda.synchronize()
     return out.float().cpu()
 
