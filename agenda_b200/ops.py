@@ -46,6 +46,13 @@ def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     B, N, C = q.shape
     d = C // heads
     scale = float(d ** -0.5 if scale is None else scale)
+    if precision == "bf16" and d not in (40, 64, 80, 160):
+        # head dims the tensor-core kernels are not instantiated for: the exact fp32 kernel (any d <= 160), same contract
+        odt = q.dtype
+        if odt not in (torch.float32, torch.bfloat16):
+            q, k, v = (t.to(torch.bfloat16) for t in (q, k, v))
+        out = attn_self(q, k, v, heads, scale, precision="fp32")
+        return out if out.dtype == odt else out.to(odt)
     if precision == "bf16":
         odt = q.dtype
         qb, kb, vb = (_dev(t, n).to(torch.bfloat16) for t, n in ((q, "q"), (k, "k"), (v, "v")))

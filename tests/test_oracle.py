@@ -103,6 +103,25 @@ def test_ccl_oracle_spec():
     assert labels[4, 4] == 0
 
 
+def test_ccl_oracle_agrees_with_opencv():
+    """Second, independent pin for the a9 spec (absent from the reference): OpenCV's
+    connectedComponentsWithStats at 4-connectivity numbers components in the same raster order as scipy.ndimage.label
+     and reports the same (x, y, w, h, area) — on config-5 style maps, salt-and-pepper noise and edge cases."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    maps = [m for m in O.synthetic_heatmaps(6, 256, seed=9)] + [rng.random((96, 160), dtype=np.float32) for _ in range(3)]
+    maps += [np.zeros((40, 64), np.float32), np.ones((40, 64), np.float32), np.eye(48, dtype=np.float32)]
+    for h in maps:
+        for thr in (0.5, 0.2, 0.8):
+            labels, boxes = O.ccl_bbox(h, thr)
+            mn, mx = h.min(), h.max()
+            mask = ((h - mn) / ((mx - mn) + np.float32(1e-8)) > np.float32(thr)).astype(np.uint8)
+            n, lab, stats, _ = cv2.connectedComponentsWithStats(mask, connectivity=4, ltype=cv2.CV_32S)
+            assert n - 1 == len(boxes)
+            assert np.array_equal(lab, labels)
+            assert np.array_equal(stats[1:].astype(np.int64), boxes.astype(np.int64))   # [x, y, w, h, area]
+
+
 def test_synthetic_heatmaps_deterministic():
     from agenda_b200.synthetic import synthetic_heatmaps
     a = O.synthetic_heatmaps(2, 64, seed=0)
