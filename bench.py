@@ -548,6 +548,7 @@ def run_ours(args):
     # ---- the same metric with the REST of the denoising step around the attention calls (SURVEY.md §8 f N4): SD-1.x
     #      UNet skeleton (convolutions / linears / norms on cuDNN / cuBLAS), CFG, DDIM, one CUDA graph per step ----
     full_step = None
+    h2d_b, d2h_b = pipe.h2d_bytes(hs_host, ctx_host), pipe.d2h_bytes(host_out)
     if not args.no_unet and not sd21:
         del pipe, pipe_eager, hs_dev, ctx_dev, staging
         torch.cuda.empty_cache()
@@ -562,8 +563,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": pipe.h2d_bytes(hs_host, ctx_host),
-                    "d2h_bytes_per_step": pipe.d2h_bytes(host_out)},
+                    "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": extra,
             "cpu_baseline": cpu, "heat_max_abs_err": parity, "full_unet_step": full_step}
     if graph_launch_note:

@@ -46,10 +46,11 @@ def test_unet_pipeline_graph_equals_eager_and_is_deterministic(cuda_ok):
     b = _pipe(num_steps=3, use_cuda_graph=False)
     out3 = b.run(lat, ctx)
     assert (out3["heat"] - out1["heat"]).abs().max().item() < 1e-6
-    # an image's result does not depend on its batch neighbours
+    # an image's result does not depend on its batch neighbours — up to the bf16 rounding of the library kernels, whose
+    # algorithm choice (cuDNN / cuBLAS) changes with the batch size
     lat1, ctx1 = a.make_inputs([8])
     single = b.run(lat1, ctx1)
-    assert (single["heat"][0] - out3["heat"][1]).abs().max().item() < 2e-5
+    assert (single["heat"][0] - out3["heat"][1]).abs().max().item() < 2e-4
     # downstream of the heat map everything is byte / integer work: bit-exact given OUR heat map
     heat = out1["heat"].cpu().numpy()
     for i in range(2):
