@@ -44,6 +44,8 @@ _SIGNATURES = {
     "agenda_attn_cross_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int,
                               c_void_p],
+    "agenda_attn_self_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_int, c_int, c_int, c_float, c_void_p],
     "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_heat_upsample_accum_heads": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_heat_finalize": [c_void_p, c_void_p, c_int64, c_int, c_void_p],
@@ -55,7 +57,8 @@ _SIGNATURES = {
                                       c_void_p],
     "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
-EXPORTS = ["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes"] + list(_SIGNATURES)
+EXPORTS = (["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes",
+            "agenda_attn_self_bwd_workspace_bytes"] + list(_SIGNATURES))
 
 _lib = None
 
@@ -78,6 +81,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_device_ok.argtypes = []
     lib.agenda_context_blob_bytes.restype = ctypes.c_longlong
     lib.agenda_context_blob_bytes.argtypes = [c_int, c_int, c_int]
+    lib.agenda_attn_self_bwd_workspace_bytes.restype = ctypes.c_longlong
+    lib.agenda_attn_self_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

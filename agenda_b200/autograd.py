@@ -3,11 +3,10 @@
 through the selected-token probabilities into Q and K of every cross-attention layer, and from there through every
 self-attention layer of the UNet into the learned token embeddings.
 
-FIRST CORRECT VERSION.  The forward passes are the sm_100a kernels behind the C ABI (same entry points as inference).
-Cross-attention backward (where the heat-map gradient enters) is `agenda_attn_cross_bwd`, an exact fp32 CUDA-core
-kernel (csrc/attn_cross_bwd.cu).  Self-attention backward is NOT a hand-written kernel yet: it recomputes through
-`F.scaled_dot_product_attention` and uses that library's backward, in the dtype of the inputs.  A fused tcgen05
-backward (dQ/dK/dV with recomputed P) is the next step for this row.
+The forward passes are the sm_100a kernels behind the C ABI (same entry points as inference).  Cross-attention backward
+(where the heat-map gradient enters) is `agenda_attn_cross_bwd`, an exact fp32 CUDA-core kernel
+(csrc/attn_cross_bwd.cu).  Self-attention backward is `agenda_attn_self_bwd` (csrc/attn_self_bwd_sm100.cu): tcgen05
+kernels that recompute P from a log-sum-exp pass and form dQ, dK and dV with their accumulators in TMEM.
 
 Gradient formulas (per batch element b and head h; P = softmax(scale * Q K^T), O = P V):
     dV = P^T dO
@@ -37,23 +36,40 @@ def _merge_heads(x: torch.Tensor) -> torch.Tensor:
 
 
 class SelfAttentionFn(torch.autograd.Function):
-    """out = softmax(scale q k^T) v per head; q/k/v [B,N,H*d] (hook.py:104-115 with encoder_hidden_states None)."""
+    """out = softmax(scale q k^T) v per head; q/k/v [B,N,H*d] (hook.py:104-115 with encoder_hidden_states None).
+
+    Backward: precision="bf16" at the SD head dims -> the tcgen05 backward kernels (agenda_attn_self_bwd: log-sum-exp
+    pass, then dQ / dK / dV with P recomputed on chip).  precision="fp32" (the exact-parity path) and other head dims ->
+    the same formulas with fp32 GEMMs, one head at a time so that the [N, N] probability block stays bounded."""
 
     @staticmethod
     def forward(ctx, q, k, v, heads: int, scale: float, precision: str):
         out = ops.attn_self(q, k, v, heads, scale=scale, precision=precision)
-        ctx.save_for_backward(q, k, v)
-        ctx.heads, ctx.scale = heads, scale
+        ctx.save_for_backward(q, k, v, out)
+        ctx.heads, ctx.scale, ctx.precision = heads, scale, precision
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        q, k, v = ctx.saved_tensors
-        with torch.enable_grad():
-            qh, kh, vh = (_split_heads(t.detach(), ctx.heads).requires_grad_(True) for t in (q, k, v))
-            o = F.scaled_dot_product_attention(qh, kh, vh, scale=ctx.scale)
-        dq, dk, dv = torch.autograd.grad(o, (qh, kh, vh), _split_heads(d_out.to(o.dtype).contiguous(), ctx.heads))
-        return _merge_heads(dq), _merge_heads(dk), _merge_heads(dv), None, None, None
+        q, k, v, out = ctx.saved_tensors
+        d = q.shape[-1] // ctx.heads
+        if ctx.precision == "bf16" and d in ops.SELF_BWD_HEAD_DIMS:
+            dq, dk, dv = ops.attn_self_bwd(q, k, v, out, d_out, ctx.heads, scale=ctx.scale)
+            return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
+        return SelfAttentionFn._backward_fp32(q, k, v, d_out, ctx.heads, ctx.scale) + (None, None, None)
+
+    @staticmethod
+    def _backward_fp32(q, k, v, d_out, heads, scale):
+        qf, kf, vf, gf = (_split_heads(t.float().contiguous(), heads) for t in (q, k, v, d_out))   # [B,H,N,d]
+        dq, dk, dv = torch.empty_like(qf), torch.empty_like(kf), torch.empty_like(vf)
+        for h in range(heads):   # one head at a time: [B, N, N] fp32 blocks
+            p = torch.softmax(torch.matmul(qf[:, h], kf[:, h].transpose(-1, -2)) * scale, dim=-1)
+            dv[:, h] = torch.matmul(p.transpose(-1, -2), gf[:, h])
+            dp = torch.matmul(gf[:, h], vf[:, h].transpose(-1, -2))
+            ds = p * (dp - (p * dp).sum(dim=-1, keepdim=True))
+            dq[:, h] = torch.matmul(ds, kf[:, h]) * scale
+            dk[:, h] = torch.matmul(ds.transpose(-1, -2), qf[:, h]) * scale
+        return _merge_heads(dq).to(q.dtype), _merge_heads(dk).to(k.dtype), _merge_heads(dv).to(v.dtype)
 
 
 class CrossAttentionHeatFn(torch.autograd.Function):

@@ -622,6 +622,7 @@ typedef CUresult (*EncodeTiledFnX3)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 // fp32 [B, rows, H*d] viewed as (d, H, rows, B); box (box_cols, 1, box_rows, 1), dense rows (no swizzle), zero fill
 static int make_head_map_f32(CUtensorMap* map, const void* base, int B, int H, int rows, int d, int box_cols, int box_rows) {
+  bind_primary_context();
   static EncodeTiledFnX3 enc = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;

@@ -1,0 +1,381 @@
+// Self-attention backward on the tcgen05 tensor cores (training mode, SURVEY.md §8 f N3): autograd of hook.py:104-115
+// with encoder_hidden_states None, as exercised by finetune_sd_token.py:1043-1069,1089.
+//
+//   P = softmax(scale Q K^T), O = P V;   dV = P^T dO;   dP = dO V^T;   dS = P o (dP - Delta),  Delta_i = sum_c dO_ic O_ic;
+//   dQ = scale dS K;   dK = scale dS^T Q.
+//
+// P is never stored by the forward kernel, so it is recomputed from the log-sum-exp of every row.  One kernel template,
+// four modes, one 128-row tile of one (batch, head) per CTA and a loop over the 128-row tiles of the other operand:
+//
+//   LSE  rows = queries i, stream K_j:            T1 = Q_i K_j^T;  online max / sum  ->  lse2[i] = log2 sum_j 2^(c T1)
+//   DQ   rows = queries i, stream K_j, V_j:       T1 = Q_i K_j^T, T2 = dO_i V_j^T;  G = E (T2 - Delta_i) scale;  dQ_i += G K_j
+//   DK   rows = keys j,    stream Q_i, dO_i:      T1 = K_j Q_i^T, T2 = V_j dO_i^T;  G = E (T2 - Delta_i) scale;  dK_j += G Q_i
+//   DV   rows = keys j,    stream Q_i, dO_i:      T1 = K_j Q_i^T;                    G = E;                       dV_j += G dO_i
+//   with E = 2^(c T1 - lse2[query]), c = scale log2(e).
+//
+// DK / DV work on the TRANSPOSED score tile (rows = keys), so that every MMA uses an operand form the forward kernels
+// already use: T1 / T2 are SS-form MMAs of two K-major tiles (contraction over the head dim), G goes back to the
+// tensor core through TMEM as packed bf16 (TS form, like P in the forward pass) and the streamed tile is read a second
+// time as an MN-major B operand (contraction over its 128 rows), exactly like V in the forward PV product.
+// The price is recomputation: S is formed in three kernels and dP in two (9 GEMM units instead of 5), in exchange for
+// one accumulator per kernel (TMEM: T1 128 + T2 128 + G 64 + accumulator <= 160 columns), no atomics and no dQ
+// round trips through global memory.
+//
+// Warps: 0-3 row threads (thread == row of the tile == TMEM lane), 4 TMA producer, 5 TMEM allocator + MMA issuer.
+#include <cstdlib>
+
+#include "sm100_common.cuh"
+
+namespace agenda {
+namespace sm100 {
+
+constexpr int kBwdThreads = 192;
+constexpr int kBwdLSE = 0, kBwdDQ = 1, kBwdDK = 2, kBwdDV = 3;
+
+template <int D>
+struct BCfg {
+  static constexpr int kDP = (D + 15) / 16 * 16;
+  static constexpr int kChunks = (D + 63) / 64;
+  static constexpr int kTileBytes = kChunks * 128 * 128;   // 128 rows, 64-column swizzle chunks
+  static constexpr int kStages = (kChunks <= 2) ? 2 : 1;
+  static constexpr int kColT1 = 0, kColT2 = 128, kColG = 256, kColAcc = 320;
+  static_assert(kColAcc + kDP <= 512, "TMEM overflow");
+};
+
+struct BBarriers {
+  float vec[2][128];   // DK / DV: lse2 / Delta of the streamed query tile (column vectors)
+  uint64_t fixed_full;
+  uint64_t st_full[2], st_empty[2];
+  uint64_t t_full, t_free, g_full, g_done;
+  uint32_t tmem_base;
+};
+
+template <int D>
+constexpr size_t b_smem_bytes() {
+  return 1024 + (2 + 2 * BCfg<D>::kStages) * BCfg<D>::kTileBytes + sizeof(BBarriers) + 64;
+}
+
+// map_r1 / map_r2: the tensors the fixed row tiles come from; map_c1 / map_c2: the streamed ones (see the mode table).
+template <int D, int MODE>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_constant__ CUtensorMap map_r2,
+                     const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2,
+                     float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ out, int H,
+                     int N, float scale) {
+  using C = BCfg<D>;
+  constexpr bool kT2 = (MODE == kBwdDQ || MODE == kBwdDK);
+  constexpr bool kAcc = (MODE != kBwdLSE);
+  constexpr bool kColVec = (MODE == kBwdDK || MODE == kBwdDV);  // lse2 / Delta indexed by the streamed (query) tile
+  constexpr int ST = C::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sR1 = smem;
+  unsigned char* sR2 = sR1 + C::kTileBytes;
+  unsigned char* sC = sR2 + C::kTileBytes;   // ST stages x (C1 tile, C2 tile)
+  BBarriers* bars = reinterpret_cast<BBarriers*>(sC + 2 * ST * C::kTileBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (N + 127) / 128;
+  const int bh = blockIdx.x / n_tiles, rt = blockIdx.x - bh * n_tiles;
+  const int b = bh / H, h = bh - b * H;
+  const int r0 = rt * 128;
+  const float c_log2 = scale * 1.4426950408889634f;
+
+  if (tid == 4 * 32) {
+    tma_prefetch_desc(&map_r1); tma_prefetch_desc(&map_c1);
+    if (kT2) tma_prefetch_desc(&map_r2);
+    if (MODE != kBwdLSE) tma_prefetch_desc(&map_c2);
+    mbar_init(&bars->fixed_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars->st_full[s], 1); mbar_init(&bars->st_empty[s], 1); }
+    mbar_init(&bars->t_full, 1); mbar_init(&bars->t_free, 128);
+    mbar_init(&bars->g_full, 128); mbar_init(&bars->g_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  // which streamed tile feeds the accumulating MMA: DQ -> K_j = C1, DK -> Q_i = C1, DV -> dO_i = C2
+  constexpr bool kAccFromC2 = (MODE == kBwdDV);
+  constexpr bool kLoadC2 = kT2 || kAccFromC2;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (elect_one()) {
+      mbar_expect_tx(&bars->fixed_full, (kT2 ? 2 : 1) * C::kTileBytes);
+      for (int c = 0; c < C::kChunks; ++c) {
+        tma_load_4d(&map_r1, &bars->fixed_full, sR1 + c * 128 * 128, c * 64, h, r0, b);
+        if (kT2) tma_load_4d(&map_r2, &bars->fixed_full, sR2 + c * 128 * 128, c * 64, h, r0, b);
+      }
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(&bars->st_empty[s], ph ^ 1);
+      if (elect_one()) {
+        unsigned char* c1 = sC + (2 * s) * C::kTileBytes;
+        unsigned char* c2 = c1 + C::kTileBytes;
+        mbar_expect_tx(&bars->st_full[s], (kLoadC2 ? 2 : 1) * C::kTileBytes);
+        for (int c = 0; c < C::kChunks; ++c) {
+          tma_load_4d(&map_c1, &bars->st_full[s], c1 + c * 128 * 128, c * 64, h, it * 128, b);
+          if (kLoadC2) tma_load_4d(&map_c2, &bars->st_full[s], c2 + c * 128 * 128, c * 64, h, it * 128, b);
+        }
+      }
+      __syncwarp();
+      if (++s == ST) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_t = make_idesc(128, 128, 0);
+    constexpr uint32_t idesc_acc = make_idesc(128, C::kDP, 1);
+    const uint64_t r1_desc = make_sdesc(smem_u32(sR1), 16, 1024);
+    const uint64_t r2_desc = make_sdesc(smem_u32(sR2), 16, 1024);
+    const uint64_t c_desc = make_sdesc(smem_u32(sC), 16, 1024);
+    const uint64_t cacc_desc = make_sdesc(smem_u32(sC), 128 * 128, 1024);   // MN-major view: LBO = chunk stride
+    mbar_wait(&bars->fixed_full, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < n_tiles; ++it) {
+      mbar_wait(&bars->st_full[s], ph);
+      if (it > 0) mbar_wait(&bars->t_free, (it - 1) & 1);   // T1 / T2 of the previous tile are in registers
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t c1_off = (2 * s) * C::kTileBytes, c2_off = c1_off + C::kTileBytes;
+#pragma unroll
+        for (int kk = 0; kk < C::kDP / 16; ++kk) {
+          const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
+          umma_ss(tmem + C::kColT1, r1_desc + static_cast<uint64_t>(ko >> 4), c_desc + static_cast<uint64_t>((c1_off + ko) >> 4),
+                  idesc_t, kk != 0);
+        }
+        if (kT2) {
+#pragma unroll
+          for (int kk = 0; kk < C::kDP / 16; ++kk) {
+            const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
+            umma_ss(tmem + C::kColT2, r2_desc + static_cast<uint64_t>(ko >> 4), c_desc + static_cast<uint64_t>((c2_off + ko) >> 4),
+                    idesc_t, kk != 0);
+          }
+        }
+        umma_commit(&bars->t_full);
+        if (!kAcc) umma_commit(&bars->st_empty[s]);
+      }
+      __syncwarp();
+      if (kAcc) {
+        mbar_wait(&bars->g_full, it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t acc_off = (2 * s + (kAccFromC2 ? 1 : 0)) * C::kTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // contraction over the 128 rows of the streamed tile, 16 per MMA
+            umma_ts(tmem + C::kColAcc, tmem + C::kColG + kk * 8, cacc_desc + static_cast<uint64_t>((acc_off + kk * 2048) >> 4),
+                    idesc_acc, !(it == 0 && kk == 0));
+          umma_commit(&bars->g_done);
+          umma_commit(&bars->st_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (++s == ST) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ============================== row threads (thread == row of this CTA's tile) ==============================
+    const int row = tid;
+    const int n_row = r0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const long long vec_base = static_cast<long long>(bh) * N;
+    float lse_r = 0.f, delta_r = 0.f;
+    if (!kColVec && MODE != kBwdLSE) {
+      lse_r = (n_row < N) ? lse2[vec_base + n_row] : 0.f;
+      if (kT2) delta_r = (n_row < N) ? delta[vec_base + n_row] : 0.f;
+    }
+    float m_run = -INFINITY, l_run = 0.f;   // LSE mode
+    for (int it = 0; it < n_tiles; ++it) {
+      const int c0 = it * 128;   // first row of the streamed tile == first column of T1 / T2
+      if (kColVec) {
+        // lse2 / Delta of the streamed query tile: one element per thread into shared memory, read back as broadcasts.
+        // Out-of-range queries get lse2 = +inf, i.e. E = 0.
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers are done
+        bars->vec[0][row] = (c0 + row < N) ? lse2[vec_base + c0 + row] : INFINITY;
+        if (kT2) bars->vec[1][row] = (c0 + row < N) ? delta[vec_base + c0 + row] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&bars->t_full, it & 1);
+      tc_fence_after();
+      if (kAcc && it > 0) {   // the accumulating MMA of the previous tile has finished reading G
+        mbar_wait(&bars->g_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+      float tile_max = -INFINITY;
+      if (MODE == kBwdLSE) {
+        // pass A over the 128 columns: the tile's row maximum (columns beyond N masked)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float t1[32];
+          tmem_ld32(tmem + lane_base + C::kColT1 + c * 32, t1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) tile_max = fmaxf(tile_max, (c0 + c * 32 + i < N) ? t1[i] : -INFINITY);
+        }
+        const float m_new = fmaxf(m_run, tile_max * c_log2);
+        l_run *= ex2(m_run - m_new);   // (first tile: 2^-inf = 0)
+        m_run = m_new;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t1[32], t2[32];
+        tmem_ld32(tmem + lane_base + C::kColT1 + c * 32, t1);
+        if (kT2) tmem_ld32(tmem + lane_base + C::kColT2 + c * 32, t2);
+        tmem_wait_ld();
+        if (MODE == kBwdLSE) {
+          float sum = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum += (c0 + c * 32 + i < N) ? ex2(fmaf(t1[i], c_log2, -m_run)) : 0.f;
+          l_run += sum;
+        } else {
+          uint32_t u[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float g[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = c * 32 + i + e;
+              float lse_x, delta_x;
+              if (kColVec) { lse_x = bars->vec[0][col]; delta_x = kT2 ? bars->vec[1][col] : 0.f; }
+              else { lse_x = lse_r; delta_x = delta_r; }
+              float p = ex2(fmaf(t1[i + e], c_log2, -lse_x));
+              if (!kColVec && c0 + col >= N) p = 0.f;   // keys beyond the sequence (DQ); DK / DV: lse2 = +inf did it
+              g[e] = kT2 ? p * (t2[i + e] - delta_x) * scale : p;
+            }
+            u[i >> 1] = pack_bf16(g[0], g[1]);
+          }
+          tmem_st16(tmem + lane_base + C::kColG + c * 16, u);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->t_free);   // T1 / T2 may be overwritten
+      if (kAcc) {
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->g_full);
+      }
+    }
+    // ---- epilogue ----
+    if (MODE == kBwdLSE) {
+      if (n_row < N) lse2[vec_base + n_row] = m_run + log2f(l_run);
+    } else {
+      mbar_wait(&bars->g_done, (n_tiles - 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
+#pragma unroll
+      for (int c = 0; c < C::kDP / 16; ++c) {
+        float o[16];
+        tmem_ld16(tmem + lane_base + C::kColAcc + c * 16, o);
+        tmem_wait_ld();
+        if (n_row < N) {
+          uint4 lo, hi;
+          lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
+          hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
+          if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+          if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// Delta[b, h, n] = sum_c dO[b, n, h*d + c] * O[b, n, h*d + c]  (fp32): one warp per (b, n), lanes over the row
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                      float* __restrict__ delta, int B, int H, int N, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= static_cast<long long>(B) * N) return;
+  const int b = static_cast<int>(wid / N), n = static_cast<int>(wid - static_cast<long long>(b) * N);
+  const __nv_bfloat16* po = o + wid * (H * d);
+  const __nv_bfloat16* pd = d_o + wid * (H * d);
+  for (int h = 0; h < H; ++h) {
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc += __bfloat162float(po[h * d + c]) * __bfloat162float(pd[h * d + c]);
+    acc = warp_sum(acc);
+    if (lane == 0) delta[(static_cast<long long>(b) * H + h) * N + n] = acc;
+  }
+}
+
+}  // namespace sm100
+
+template <int D, int MODE>
+static int launch_bwd_mode(const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& c1, const CUtensorMap& c2,
+                           float* lse2, const float* delta, void* out, int B, int H, int N, float scale, cudaStream_t st) {
+  constexpr size_t smem = sm100::b_smem_bytes<D>();
+  auto kern = sm100::attn_self_bwd_kernel<D, MODE>;
+  AGENDA_DYN_SMEM(kern, smem);
+  const int n_tiles = (N + 127) / 128;
+  kern<<<static_cast<unsigned>(n_tiles) * B * H, sm100::kBwdThreads, smem, st>>>(r1, r2, c1, c2, lse2, delta,
+                                                                               static_cast<__nv_bfloat16*>(out), H, N, scale);
+  AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel");
+  return AGENDA_OK;
+}
+
+template <int D>
+static int attn_self_bwd_d(const void* q, const void* k, const void* v, const void* o, const void* d_o, float* ws, void* dq,
+                           void* dk, void* dv, int B, int H, int N, float scale, cudaStream_t st) {
+  CUtensorMap mq, mk, mv, mdo;
+  int rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mdo, d_o, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  float* lse2 = ws;
+  float* delta = ws + static_cast<long long>(B) * H * N;
+  {
+    const long long warps = static_cast<long long>(B) * N;
+    const int threads = 256;
+    const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
+    sm100::attn_bwd_delta_kernel<<<blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(o),
+                                                             static_cast<const __nv_bfloat16*>(d_o), delta, B, H, N, D);
+    AGENDA_LAUNCH_CHECK("attn_bwd_delta_kernel");
+  }
+  if ((rc = launch_bwd_mode<D, sm100::kBwdLSE>(mq, mq, mk, mk, lse2, delta, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  if ((rc = launch_bwd_mode<D, sm100::kBwdDQ>(mq, mdo, mk, mv, lse2, delta, dq, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  if ((rc = launch_bwd_mode<D, sm100::kBwdDK>(mk, mv, mq, mdo, lse2, delta, dk, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  return launch_bwd_mode<D, sm100::kBwdDV>(mk, mk, mq, mdo, lse2, delta, dv, B, H, N, scale, st);
+}
+
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" long long agenda_attn_self_bwd_workspace_bytes(int B, int H, int N) {
+  if (B <= 0 || H <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "attn_self_bwd_workspace_bytes: B=%d H=%d N=%d", B, H, N);
+  return 2ll * B * H * N * 4;
+}
+
+extern "C" int agenda_attn_self_bwd(const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                                    void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N, int d,
+                                    float scale, void* stream) {
+  const char* who = "attn_self_bwd";
+  if (!q || !k || !v || !out || !d_out || !workspace || !dq || !dk || !dv)
+    return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "%s: bf16 only (dtype=1)", who);
+  if (B <= 0 || H <= 0 || N <= 0 || d <= 0 || static_cast<long long>(B) * H > 65535)
+    return fail(AGENDA_ERR_BAD_SHAPE, "%s: B=%d H=%d N=%d d=%d", who, B, H, N, d);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(dq) |
+                       reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv) | reinterpret_cast<uintptr_t>(workspace);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: all pointers must be 16-byte aligned", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  switch (d) {
+    case 40: return attn_self_bwd_d<40>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
+    case 64: return attn_self_bwd_d<64>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
+    case 80: return attn_self_bwd_d<80>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
+    case 160: return attn_self_bwd_d<160>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
+    default: return fail(AGENDA_ERR_UNSUPPORTED, "%s: head dim %d not in {40,64,80,160}", who, d);
+  }
+}

@@ -296,7 +296,18 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [B, N, H*d] bf16 viewed as (d, H, N, B); box (64, 1, rows, 1), 128-byte swizzle, zero fill out of bounds.
+// cuTensorMapEncodeTiled is a DRIVER entry point: it needs the primary context current on the calling thread.  A thread
+// that has made no runtime call yet (PyTorch's autograd worker on its first backward kernel) has none bound.
+void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows, long long row_stride) {
+  bind_primary_context();
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t C = row_stride ? static_cast<cuuint64_t>(row_stride) : static_cast<cuuint64_t>(H) * d;

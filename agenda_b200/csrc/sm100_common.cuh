@@ -221,6 +221,7 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
 }  // namespace sm100
 
 // [B, rows, H*d] bf16 viewed as (d, H, rows, B); box (64, 1, box_rows, 1), 128-byte swizzle, zero fill out of bounds.
+void bind_primary_context();
 // row_stride (elements) = distance between consecutive rows; 0 = packed rows of H*d (q/k/v as column slices of one
 // fused-projection output pass the row length of that output).
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int rows, int d, int box_rows, long long row_stride = 0);

@@ -134,6 +134,29 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
     return out
 
 
+SELF_BWD_HEAD_DIMS = (40, 64, 80, 160)
+
+
+def attn_self_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, heads: int,
+                  scale: Optional[float] = None):
+    """Backward of attn_self on the tensor cores (agenda_attn_self_bwd): q/k/v/out/d_out [B,N,H*d] -> (dq, dk, dv) in
+    the dtype of q.  Inputs are taken as bf16 (cast if needed); P is recomputed from a log-sum-exp pass."""
+    q = _dev(q, "q")
+    odt = q.dtype
+    qb, kb, vb, ob, gb = (_dev(t, n).to(torch.bfloat16).contiguous()
+                          for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out"), (d_out, "d_out")))
+    B, N, C = qb.shape
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    ws = torch.empty(_lib.load().agenda_attn_self_bwd_workspace_bytes(B, heads, N) // 4, dtype=torch.float32, device=q.device)
+    dq, dk, dv = torch.empty_like(qb), torch.empty_like(qb), torch.empty_like(qb)
+    _lib.call("agenda_attn_self_bwd", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), ob.data_ptr(), gb.data_ptr(),
+              ws.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _lib.BF16, B, heads, N, d, scale, _stream())
+    if odt != torch.bfloat16:
+        dq, dk, dv = dq.to(odt), dk.to(odt), dv.to(odt)
+    return dq, dk, dv
+
+
 def split_bf16(x: torch.Tensor):
     """x (fp32) -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): x == hi + lo to 2^-17 relative (the operand form
     of the split-precision cross-attention kernel; pack_context_kv does the same on the device)."""
@@ -221,6 +244,11 @@ def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: tor
     """Backward of attn_cross_heat (training mode): returns (dq, dk, dv) in the dtypes of q / k / v.  d_maps is the
     gradient of the head-mean maps, fp32 [B-b_first, T, N] (or any trailing shape of N elements), or None."""
     q = _dev(q, "q")
+    if q.dtype == torch.float16:
+        # fp16 training (accelerate mixed_precision=fp16, finetune_sd_token.py): the kernel computes in fp32 anyway, so the
+        # fp16 tensors go in as fp32 (exact) and the gradients come back in fp16, like the forward pass handles fp16
+        dq, dk, dv = attn_cross_bwd(q.float(), k.float(), v.float(), d_out.float(), d_maps, heads, token_idx, b_first, scale)
+        return dq.to(torch.float16), dk.to(torch.float16), dv.to(torch.float16)
     k, v, d_out = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype), _dev(d_out, "d_out", q.dtype)
     B, N, C = q.shape
     M = k.shape[1]

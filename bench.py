@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images-per-step", type=int, default=None, help="default 8 (sd15) / 16 (sd21)")
-    ap.add_argument("--workload", default="sd15", choices=["sd15", "sd21", "config3"],
+    ap.add_argument("--workload", default="sd15", choices=["sd15", "sd21", "config3", "train"],
                     help="sd15 = BASELINE configs[1] (the headline metric); sd21 = configs[3] (SD-2.1 768^2, 96^2 latent, "
                          "batch 16, 4 tokens) — informational; config3 = configs[2]: --num-images seeds sharded over the "
                          "ranks (strong scaling), final NCCL gather of heat maps + boxes, determinism check")
@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--ccl-maps", type=int, default=2048, help="512^2 maps for the post-process roofline probe")
     a = ap.parse_args()
     if a.images_per_step is None:
-        a.images_per_step = 16 if a.workload == "sd21" else 8
+        a.images_per_step = 16 if a.workload == "sd21" else (2 if a.workload == "train" else 8)
     return a
 
 
@@ -657,10 +657,83 @@ def run_config3(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Training-mode processor (SURVEY.md §8 f N3; finetune_sd_token.py:1043-1069,1089): forward + backward of the SD-1.5
+    attention stack — per block self -> cross -> self, UNet weights frozen, the prompt embedding carries the graph, loss =
+    output term + L1 on the aggregated heat map of three tokens.  One "step" = one such train step at --images-per-step
+    samples (is_train=True: no CFG pair).  Metric: train samples/s; roofline: the self-attention backward at N = 4096."""
+    import torch
+    from agenda_b200 import UNetCrossAttentionHooker, _lib, ops
+    from agenda_b200.sd_attention import AttentionStack, sd15_blocks
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.images_per_step
+    stack = AttentionStack(sd15_blocks(), 768, seed=0).to(dev).to(torch.bfloat16)
+    for p_ in stack.parameters():
+        p_.requires_grad_(False)
+    hs, ctx0 = stack.make_inputs(B, dev, torch.bfloat16)
+    tgt = torch.rand(B, len(TOKENS), 64, 64, device=dev)
+    proc = UNetCrossAttentionHooker(is_train=True, latent_hw=64, tokens=list(TOKENS), precision="bf16")
+
+    def step():
+        proc.clear()
+        ctx = ctx0.clone().requires_grad_(True)
+        loss = 0.0
+        for b, a1, a2 in zip(stack.blocks, stack.attn1, stack.attn2):
+            x = hs[(b.hw, b.channels)]
+            y = proc(a2, proc(a1, x) + x, ctx)
+            y = proc(a1, y)                  # activations now carry the graph: the self-attention backward runs
+            loss = loss + y.float().pow(2).mean()
+        loss = loss + 50.0 * (proc.compute_global_heat_map() - tgt).abs().mean()
+        loss.backward()
+        return loss.detach()
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    l0 = _lib.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.launches - l0
+    clocks = sampler.stop()
+    _, _, tf_sust, peak_src = measured_peaks()
+    # self-attention backward alone at the 64x64 layer shape
+    N, H, d = 4096, 8, 40
+    g = torch.Generator(device=dev).manual_seed(0)
+    q, k, v, go = (torch.randn(B, N, H * d, device=dev, generator=g).bfloat16() for _ in range(4))
+    o = ops.attn_self(q, k, v, H)
+    ms_b = _time_launches(lambda: ops.attn_self_bwd(q, k, v, o, go, H), 10)
+    flops = 10.0 * B * H * N * N * d
+    line = {"metric": "train_samples_per_s", "value": B / (ms / 1000.0), "unit": "samples/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "training-mode processor: SD-1.5 attention stack, 48 processor calls forward + backward "
+                                   f"(self -> cross -> self per block), batch {B}, frozen weights, prompt embedding with grad, "
+                                   "output + heat-map L1 loss; forward = the inference kernels, backward = agenda_attn_self_bwd "
+                                   "(tcgen05) + agenda_attn_cross_bwd (fp32 CUDA cores)", "samples_per_step": B},
+            "gpu_launches": launches, "clocks": clocks, "loss": float(loss),
+            "roofline": {"kernel": "attn_self_bwd_kernel<40, LSE|DQ|DK|DV> (N=4096, B*H=%d)" % (B * H), "bound": "tensor",
+                         "achieved": flops / ms_b / 1e9, "peak": tf_sust, "unit": "TFLOP/s", "frac": flops / ms_b / 1e9 / tf_sust,
+                         "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained", "avg_launch_ms": ms_b,
+                         "how": "CUDA events around 10 calls (5 launches each: Delta, LSE, dQ, dK, dV); useful FLOPs "
+                                "10*B*H*N*N*d (five GEMMs); the kernels execute 9 GEMM units (S recomputed three times, dP twice)"}}
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "train":
+        run_train(a)
     elif a.workload == "config3":
         run_config3(a)
     else:

@@ -139,6 +139,17 @@ int agenda_attn_cross_bwd(const void* q, const void* k, const void* v, const voi
                           void* dq, float* dk, float* dv, int dtype, int B, int H, int N, int M, int d, float scale,
                           const int32_t* token_idx, int T, int b_first, void* stream);
 
+/* Backward of agenda_attn_self_fwd (training mode, SURVEY.md §8 f N3: autograd of hook.py:104-115 with
+ * encoder_hidden_states None, as exercised by finetune_sd_token.py:1043-1069,1089) on the tcgen05 tensor cores.
+ * q, k, v, out (the forward result), d_out and the gradients dq, dk, dv are bf16 [B,N,H*d].  P is recomputed from a
+ * log-sum-exp pass (the forward kernel stores no statistics): five launches — Delta = rowsum(dO o O), LSE, dQ, dK, dV —
+ * all enqueued on `stream`.  workspace: agenda_attn_self_bwd_workspace_bytes(B, H, N) bytes of device memory (fp32
+ * [2,B,H,N]: log2-domain LSE and Delta).  d in {40,64,80,160}; all pointers 16-byte aligned. */
+long long agenda_attn_self_bwd_workspace_bytes(int B, int H, int N);
+int agenda_attn_self_bwd(const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                         void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N, int d,
+                         float scale, void* stream);
+
 /* Test hook: same contract, forcing the exact fp32 CUDA-core kernel (bf16 inputs otherwise take the tcgen05
  * tensor-core kernel; fp32 inputs always take the fp32 kernel). */
 int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, void* out, int dtype,
