@@ -1,0 +1,246 @@
+// to_q for the cross-attention heat path (hook.py:93) with an fp32 result, as ONE tcgen05 GEMM:
+//
+//     out[M, N] (fp32) = x[M, K] (bf16) * (W_hi + W_lo)[N, K]^T          W_hi = bf16(W), W_lo = bf16(W - W_hi)
+//
+// The heat-map logits need the checkpoint's fp32 projection weights (agenda_b200/mixed.py), i.e. two bf16 products per
+// activation.  With library GEMMs that is an fp32-output GEMM plus an accumulating second GEMM that reads and rewrites
+// the whole fp32 output (65 us against 27 us for one GEMM at M = 65536, K = N = 320, profiles/r02_to_q_gemm_forms.txt).
+// Here both weight halves are B operands of the same accumulator: the activation tile is read once, the output is
+// written once, and the correction costs only tensor-pipe time the kernel does not need (it is bound by the fp32 store
+// stream and the L2 weight stream).  w_lo == NULL gives the plain fp32-output GEMM.
+//
+// Persistent, warp-specialised (the canonical sm_100 GEMM shape): CTA tile 128 x 160, K in blocks of 64 (128-byte
+// swizzled rows) through a 3-stage TMA ring; accumulators double-buffered in TMEM (2 x 160 columns) so the epilogue of
+// tile i overlaps the MMAs of tile i + 1; epilogue warps stage 32-column fp32 sub-tiles in the 128B-swizzled layout
+// (conflict-free stores) and write them with TMA tensor stores (full 128-byte lines, rows clipped by the hardware).
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue (TMEM lane quadrant = warp % 4)
+#include <cstdlib>
+
+#include "sm100_common.cuh"
+
+namespace agenda {
+namespace sm100 {
+
+constexpr int kLThreads = 192;
+constexpr int kLBM = 128, kLBN = 160, kLBK = 64;
+constexpr int kLStages = 3;
+constexpr int kLABytes = kLBM * 128;              // 128 rows x 64 bf16
+constexpr int kLBBytes = kLBN * 128;              // 160 rows x 64 bf16
+constexpr int kLStageBytes = kLABytes + 2 * kLBBytes;
+constexpr int kLSubBytes = 128 * 128;             // one fp32 output sub-tile: 128 rows x 32 columns
+constexpr int kLStaging = 3;                      // sub-tiles staged at a time (160 columns = 3 + 2 sub-tiles)
+
+struct LBarriers {
+  uint64_t full[kLStages], empty[kLStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+constexpr size_t l_smem_bytes() { return 1024 + kLStages * kLStageBytes + kLStaging * kLSubBytes + sizeof(LBarriers) + 64; }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_f4(void* p, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool kLo>
+__global__ void __launch_bounds__(kLThreads, 1)
+linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+                    const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out, int M, int K,
+                    int N) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sStage = smem;
+  unsigned char* sOut = sStage + kLStages * kLStageBytes;
+  LBarriers* bars = reinterpret_cast<LBarriers*>(sOut + kLStaging * kLSubBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_m = (M + kLBM - 1) / kLBM, tiles_n = N / kLBN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int n_kb = K / kLBK;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_out);
+    if (kLo) tma_prefetch_desc(&map_wlo);
+    for (int s = 0; s < kLStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;   // n fastest: the CTAs that share an activation tile run together
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&bars->empty[s], ph ^ 1);
+        if (elect_one()) {
+          unsigned char* a = sStage + s * kLStageBytes;
+          mbar_expect_tx(&bars->full[s], kLABytes + (kLo ? 2 : 1) * kLBBytes);
+          tma_load_2d(&map_x, &bars->full[s], a, kb * kLBK, tm * kLBM);
+          tma_load_2d(&map_whi, &bars->full[s], a + kLABytes, kb * kLBK, tn * kLBN);
+          if (kLo) tma_load_2d(&map_wlo, &bars->full[s], a + kLABytes + kLBBytes, kb * kLBK, tn * kLBN);
+        }
+        __syncwarp();
+        if (++s == kLStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc = make_idesc(kLBM, kLBN, 0);
+    const uint64_t desc0 = make_sdesc(smem_u32(sStage), 16, 1024);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int ab = it & 1;
+      mbar_wait(&bars->acc_empty[ab], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator (two tiles ago)
+      tc_fence_after();
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&bars->full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_off = s * kLStageBytes, bh_off = a_off + kLABytes, bl_off = bh_off + kLBBytes;
+#pragma unroll
+          for (int kk = 0; kk < kLBK / 16; ++kk) {
+            const uint64_t ad = desc0 + static_cast<uint64_t>((a_off + kk * 32) >> 4);
+            umma_ss(tmem + ab * kLBN, ad, desc0 + static_cast<uint64_t>((bh_off + kk * 32) >> 4), idesc, !(kb == 0 && kk == 0));
+            if (kLo) umma_ss(tmem + ab * kLBN, ad, desc0 + static_cast<uint64_t>((bl_off + kk * 32) >> 4), idesc, 1);
+          }
+          umma_commit(&bars->empty[s]);
+          if (kb == n_kb - 1) umma_commit(&bars->acc_full[ab]);
+        }
+        __syncwarp();
+        if (++s == kLStages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue: TMEM -> swizzled fp32 sub-tiles -> TMA store ==============================
+    const int et = tid - 64;                                   // 0..127
+    const int quad = warp & 3;                                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + (tid & 31);                    // row of the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int ab = it & 1;
+      mbar_wait(&bars->acc_full[ab], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int sub = 0; sub < kLBN / 32; ++sub) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + ab * kLBN + sub * 32, v);
+        tmem_wait_ld();
+        const int slot = sub % kLStaging;
+        if (slot == 0) {
+          // the TMA stores that read the staging buffers have finished reading (issued by thread et == 0)
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        unsigned char* dst = sOut + slot * kLSubBytes + row * 128;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          st_shared_f4(dst + ((p ^ (row & 7)) << 4), v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+        if (slot == kLStaging - 1 || sub == kLBN / 32 - 1) {
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            const int first = sub - slot;
+            for (int q = first; q <= sub; ++q)
+              tma_store_2d(&map_out, sOut + (q % kLStaging) * kLSubBytes, tn * kLBN + q * 32, tm * kLBM);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_empty[ab]);
+    }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace sm100
+
+typedef CUresult (*EncodeTiledFnL)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// row-major [rows, cols] matrix viewed as (cols, rows); box (box_cols, box_rows), 128-byte swizzle
+static int make_matrix_map(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem, long long rows, long long cols,
+                           int box_cols, int box_rows) {
+  bind_primary_context();
+  static EncodeTiledFnL enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFnL>(p);
+  }();
+  if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled (matrix) failed (CUresult %d)", static_cast<int>(r));
+  return AGENDA_OK;
+}
+
+}  // namespace agenda
+
+using namespace agenda;
+
+extern "C" int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                                       void* stream) {
+  const char* who = "linear_split_f32";
+  if (!x || !w_hi || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (M <= 0 || K <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "%s: M=%d K=%d N=%d", who, M, K, N);
+  if (K % sm100::kLBK || N % sm100::kLBN)
+    return fail(AGENDA_ERR_UNSUPPORTED, "%s: K=%d must be a multiple of %d and N=%d a multiple of %d", who, K, sm100::kLBK, N,
+                sm100::kLBN);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) |
+                       reinterpret_cast<uintptr_t>(out);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: x / w_hi / w_lo / out must be 16-byte aligned", who);
+  CUtensorMap mx, mh, ml, mo;
+  int rc;
+  if ((rc = make_matrix_map(&mx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, sm100::kLBK, sm100::kLBM)) != AGENDA_OK) return rc;
+  if ((rc = make_matrix_map(&mh, w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
+  if ((rc = make_matrix_map(&ml, w_lo ? w_lo : w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
+  if ((rc = make_matrix_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, 32, sm100::kLBM)) != AGENDA_OK) return rc;
+  const int n_tiles = ((M + sm100::kLBM - 1) / sm100::kLBM) * (N / sm100::kLBN);
+  const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
+  constexpr size_t smem = sm100::l_smem_bytes();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (w_lo) {
+    auto kern = sm100::linear_split_kernel<true>;
+    AGENDA_DYN_SMEM(kern, smem);
+    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N);
+  } else {
+    auto kern = sm100::linear_split_kernel<false>;
+    AGENDA_DYN_SMEM(kern, smem);
+    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N);
+  }
+  AGENDA_LAUNCH_CHECK("linear_split_kernel");
+  return AGENDA_OK;
+}

@@ -166,6 +166,30 @@ def split_bf16(x: torch.Tensor):
     return hi.contiguous(), lo.contiguous()
 
 
+def linear_split_f32_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.dim() == 2
+            and w.shape[1] % 64 == 0 and w.shape[0] % 160 == 0 and x.shape[-1] == w.shape[1])
+
+
+def linear_split_f32(x: torch.Tensor, w_hi: torch.Tensor, w_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [..., K] @ (w_hi + w_lo)[N, K]^T -> fp32 [..., N] in one tcgen05 GEMM (agenda_linear_split_f32): fp32
+    accumulation AND fp32 output, both weight halves into the same accumulator.  w_lo None: plain fp32-output GEMM."""
+    x = _dev(x, "x", torch.bfloat16)
+    w_hi = _dev(w_hi, "w_hi", torch.bfloat16)
+    if w_lo is not None:
+        w_lo = _dev(w_lo, "w_lo", torch.bfloat16)
+        if w_lo.shape != w_hi.shape:
+            raise ValueError("w_lo must have the shape of w_hi")
+    N, K = w_hi.shape
+    if x.shape[-1] != K:
+        raise ValueError(f"x [..., {x.shape[-1]}] does not match the weight [{N}, {K}]")
+    M = x.numel() // K
+    out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+    _lib.call("agenda_linear_split_f32", x.data_ptr(), w_hi.data_ptr(), None if w_lo is None else w_lo.data_ptr(),
+              out.data_ptr(), M, K, N, _stream())
+    return out
+
+
 class ContextKV:
     """The prompt side of the split-precision cross-attention, packed for the tensor cores (agenda_pack_context_kv):
     `blob` u8 [B, H, block] with K_hi | K_lo | V of every (batch, head) in the kernel's shared-memory layout."""

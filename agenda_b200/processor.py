@@ -228,18 +228,22 @@ class UNetCrossAttentionHooker:
     @staticmethod
     def _query_fp32(attn, hidden_states):
         """to_q (hook.py:93) with an fp32 result.  fp32 activations: the module's own fp32 GEMM (what the reference
-        runs).  16-bit activations: one tensor-core GEMM with fp32 accumulation and fp32 OUTPUT (products of 16-bit
-        values are exact, so this is the fp32 projection of those activations and weights), plus the `weight_lo`
-        correction GEMM when the module carries its checkpoint's fp32 residual."""
+        runs).  bf16 activations: agenda_linear_split_f32 — one tcgen05 GEMM with fp32 accumulation and fp32 OUTPUT
+        (products of 16-bit values are exact, so this is the fp32 projection of those activations and weights) that
+        also takes the `weight_lo` residual of the checkpoint's fp32 weight as a second B operand of the same
+        accumulator.  Other 16-bit cases (fp16, odd shapes): library GEMMs with out_dtype=float32 (+ a correction GEMM)."""
         lin = attn.to_q
         w = getattr(lin, "weight", None)
         if (hidden_states.dtype == torch.float32 or w is None or w.dtype != hidden_states.dtype
                 or type(lin) is not torch.nn.Linear):
             return lin(hidden_states).float()
         B, N, C = hidden_states.shape
+        lo = getattr(lin, "weight_lo", None)
+        if lin.bias is None and ops.linear_split_f32_supported(hidden_states, w) and (lo is None or lo.dtype == w.dtype):
+            # one tcgen05 GEMM: both weight halves into the same fp32 accumulator, activations read once, fp32 written once
+            return ops.linear_split_f32(hidden_states, w.detach(), None if lo is None else lo)
         x2 = hidden_states.reshape(B * N, C)
         q = torch.mm(x2, w.t(), out_dtype=torch.float32)
-        lo = getattr(lin, "weight_lo", None)
         if lo is not None:
             _addmm_f32_(q, x2, lo.to(x2.dtype).t())
         if lin.bias is not None:

@@ -102,6 +102,15 @@ int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v
                                      const int32_t* token_idx, int T, int b_first,
                                      float* maps, int accumulate, void* stream);
 
+/* ---- to_q of the cross-attention heat path (hook.py:93) with an fp32 result, one tcgen05 GEMM ---------------------------
+ * out[M,N] (fp32, row-major) = x[M,K] (bf16, row-major) * (w_hi + w_lo)[N,K]^T, w_hi / w_lo bf16 row-major in the
+ * nn.Linear layout; w_lo may be NULL (plain fp32-output GEMM).  w_hi = bf16(W), w_lo = bf16(W - w_hi) of an fp32
+ * checkpoint weight W (agenda_b200/mixed.py) reproduce the fp32 projection to 2^-17: products of bf16 values are exact
+ * in the fp32 accumulator, and both halves accumulate into the same TMEM tile, so x is read once and out written once.
+ * K % 64 == 0, N % 160 == 0 (320 / 640 / 1280 in the SD UNets); pointers 16-byte aligned; no bias. */
+int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                            void* stream);
+
 /* ---- prompt side of the split-precision cross-attention: pack K / V once per prompt --------------------------------
  * to_k / to_v of the prompt embedding (hook.py:101-102) do not depend on the latent.  agenda_pack_context_kv turns the
  * fp32 key projection k32 [B,M,H*d] and the value projection v [B,M,H*d] (v_dtype AGENDA_F32 or AGENDA_BF16) into

@@ -1,0 +1,49 @@
+"""GPU parity of agenda_linear_split_f32 (to_q with an fp32 result: one tcgen05 GEMM over bf16 activations and the
+hi / lo halves of an fp32 weight) against an fp64 matmul of the same values."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from agenda_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 320, 320), (4096, 320, 320), (1000, 640, 640), (333, 1280, 1280), (65536, 320, 320),
+                                    (64, 1280, 1280), (20000, 64, 160)])
+@pytest.mark.parametrize("with_lo", [True, False])
+def test_linear_split_f32(ops, M, K, N, with_lo):
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    w_hi, w_lo = ops.split_bf16(w.cuda())
+    out = ops.linear_split_f32(x.cuda(), w_hi, w_lo if with_lo else None)
+    assert out.dtype == torch.float32 and out.shape == (M, N)
+    w_eff = (w_hi.double() + (w_lo.double() if with_lo else 0)).cpu()
+    rows = torch.randperm(M, generator=g)[:min(M, 512)]
+    ref = x[rows].double() @ w_eff.t()
+    err = (out[rows.cuda()].double().cpu() - ref).abs().max().item()
+    assert err < 2e-5 * ref.abs().max().item() + 1e-6, err          # fp32 accumulation of exact products
+    if with_lo:   # and that IS the fp32 checkpoint's projection (to 2^-17)
+        ref32 = x[rows].double() @ w.double().t()
+        assert (out[rows.cuda()].double().cpu() - ref32).abs().max().item() < 3e-5 * ref32.abs().max().item() + 1e-6
+    # batched leading dims, determinism
+    x3 = x.cuda().view(1, M, K)
+    out2 = ops.linear_split_f32(x3, w_hi, w_lo if with_lo else None)
+    assert out2.shape == (1, M, N) and torch.equal(out2[0], out)
+
+
+def test_linear_split_f32_argument_errors(ops):
+    from agenda_b200 import _lib
+    x = torch.zeros(128, 320, device="cuda").bfloat16()
+    with pytest.raises(_lib.AgendaError):   # N not a multiple of 160
+        ops.linear_split_f32(x, torch.zeros(128, 320, device="cuda").bfloat16())
+    with pytest.raises(TypeError):
+        ops.linear_split_f32(x.float(), torch.zeros(320, 320, device="cuda").bfloat16())
+    assert not ops.linear_split_f32_supported(x, torch.zeros(128, 320, device="cuda").bfloat16())
+    assert ops.linear_split_f32_supported(x, torch.zeros(320, 320, device="cuda").bfloat16())
