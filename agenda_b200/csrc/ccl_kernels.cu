@@ -577,7 +577,11 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
 
   // ---- pass 1: min / max / NaN ----
   const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-  auto ld1 = [&](int i) { return hints ? ldg_hint(src4 + i, pol_keep) : __ldg(src4 + i); };
+  // hints >= 2: only the LAST (hints) percent of this CTA's range — read last in pass 1 and first in pass 2 — is marked
+  // evict_last; the rest streams with evict_first.  With ~300 maps in flight only a fraction of each can stay in the
+  // 126 MB L2: marking everything evict_last marks nothing.
+  const int keep_from = (hints >= 2) ? i_end - static_cast<int>(static_cast<long long>(i_end - i_begin) * hints / 100) : i_begin;
+  auto ld1 = [&](int i) { return hints ? ldg_hint(src4 + i, i >= keep_from ? pol_keep : pol_drop) : __ldg(src4 + i); };
   auto ld2 = [&](int i) { return hints ? ldg_hint(src4 + i, pol_drop) : __ldg(src4 + i); };
   {
     float lo = INFINITY, hi = -INFINITY;
@@ -962,7 +966,10 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
         int cta_cluster = 1;  // 4: split the two streaming passes of a map over a 4-CTA cluster
         if (const char* e = knob("AGENDA_CCL_CTA_CLUSTER")) { const int c = atoi(e); cta_cluster = (c == 4 || c == 2) ? c : 1; }
         if (n_words < 64) cta_cluster = 1;
-        int hints = 1;  // measured: +1-2 % (pass 2 still misses L2: ~300 MB of maps are in flight, L2 is 126 MB)
+        // 25: the last quarter of the map (read last in pass 1, first in pass 2) is marked evict_last, the rest evict_first.
+        // Measured on 2048 config-5 maps: no hints 1.196 ms, everything evict_last 1.184, 15 % 1.165, 25 % 1.154, 35 % 1.159,
+        // 50 % 1.173 (profiles/r02_ccl_l2_keep_fraction_sweep.txt): ~300 MB of maps are in flight against 126 MB of L2
+        int hints = 25;
         if (const char* e = knob("AGENDA_CCL_HINTS")) hints = atoi(e);
         int cta_threads = n_px >= 65536 ? 1024 : (n_px >= 16384 ? 256 : 128);
         if (const char* e = knob("AGENDA_CCL_CTA_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) cta_threads = t; }
