@@ -69,11 +69,14 @@ struct TCfg {
   static constexpr int kKVBytes = kKBytes + kVBytes;     // one (batch, head) block of the packed context
   static constexpr int kKBufs = (D <= 80) ? 2 : 1;
   static constexpr int kVBufs = (D <= 64) ? 2 : 1;
-  static constexpr int kQBBufs = 2;
+  static constexpr int kQBBufs = 2;                    // bf16 operand buffers: conversion of chunk j waits for QK(j - kQBBufs)
   static constexpr bool kAliasP = (2 * kTSlot + 2 * kTPSlot + 2 * kDP > 512);  // d = 160: P overwrites its S slot
-  static constexpr int kColP = kAliasP ? 0 : 2 * kTSlot;
+  // score slots: QK runs up to kSSlots steps ahead of the softmax that consumes it (P / O keep one slot per warpgroup)
+  // (measured, tools/bench_cross_x3.py: a third slot helps d = 64 — 169.8 -> 165.2 us at N = 9216 — and costs ~2 us at d = 40 / 80)
+  static constexpr int kSSlots = (D == 64) ? 3 : 2;
+  static constexpr int kColP = kAliasP ? 0 : kSSlots * kTSlot;
   static constexpr int kPStride = kAliasP ? kTSlot : kTPSlot;
-  static constexpr int kColO = kAliasP ? 2 * kTSlot : 2 * kTSlot + 2 * kTPSlot;
+  static constexpr int kColO = kAliasP ? 2 * kTSlot : kSSlots * kTSlot + 2 * kTPSlot;
   static constexpr int kFixedBytes = kQBBufs * kQBBytes + kKBufs * kKBytes + kVBufs * kVBytes;
   static_assert(D % kW == 0, "head dim must be a whole number of chunks");
   static_assert(kColO + 2 * kDP <= 512, "TMEM overflow");
@@ -82,8 +85,8 @@ struct TCfg {
 struct TBarriers {
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   uint64_t q32_full[kTMaxStages], q32_empty[kTMaxStages];
-  uint64_t qb_full[2], qb_empty[2];
-  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2], o_free[2];
+  uint64_t qb_full[3], qb_empty[3];
+  uint64_t s_full[3], s_free[3], p_full[2], pv_done[2], o_free[2];
   uint32_t tmem_base;
 };
 
@@ -147,10 +150,12 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
     }
     for (int i = 0; i < kTMaxStages; ++i) { mbar_init(&bars->q32_full[i], 1); mbar_init(&bars->q32_empty[i], kTConvThreads); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->qb_full[i], kTConvThreads); mbar_init(&bars->qb_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&bars->qb_full[i], kTConvThreads); mbar_init(&bars->qb_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 128);
+    }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 128); mbar_init(&bars->p_full[i], 128);
-      mbar_init(&bars->pv_done[i], 1); mbar_init(&bars->o_free[i], 128);
+      mbar_init(&bars->p_full[i], 128); mbar_init(&bars->pv_done[i], 1); mbar_init(&bars->o_free[i], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,12 +224,13 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
     int gq = 0;                          // running Q chunk counter (operand-buffer ring position)
     int k_waited = -1, v_waited = -1;    // last head whose K / V block has been observed
     auto issue_qk = [&](int j) {  // S[j & 1] = Q(step j) K_h^T as three bf16 MMA groups per column chunk
-      const int sb = j & 1, hl = j / n_qt, kb = hl % C::kKBufs;
+      const int sb = j % C::kSSlots, hl = j / n_qt, kb = hl % C::kKBufs;
       if (hl > k_waited) {
         mbar_wait(&bars->k_full[kb], (hl / C::kKBufs) & 1);
         k_waited = hl;
       }
-      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j - 2) >> 1) & 1);  // S(j-2) is in the softmax warpgroup's registers
+      // the previous user of this score slot, S(j - kSSlots), is in its softmax warpgroup's registers
+      if (j >= C::kSSlots) mbar_wait(&bars->s_free[sb], ((j - C::kSSlots) / C::kSSlots) & 1);
       for (int c = 0; c < C::kNC; ++c, ++gq) {
         const int cb = gq % C::kQBBufs;
         mbar_wait(&bars->qb_full[cb], (gq / C::kQBBufs) & 1);
@@ -269,10 +275,10 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
       }
       __syncwarp();
     };
-    // QK runs up to two steps ahead of PV (one when P aliases S: QK(s+2) would overwrite P(s) before PV(s) has read it)
+    // QK runs up to kSSlots steps ahead of PV (one when P aliases S: QK(s+2) would overwrite P(s) before PV(s) has read it)
     int nq = 0;
     for (int s = 0; s < n_steps; ++s) {
-      while (nq < n_steps && nq <= s + (C::kAliasP ? 1 : 2)) {
+      while (nq < n_steps && nq <= s + (C::kAliasP ? 1 : C::kSSlots)) {
         issue_qk(nq);
         ++nq;
       }
@@ -384,13 +390,13 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
     int hl = 0, qt = wg;  // step s = hl * n_qt + qt, advanced by kWGs per iteration
     while (qt >= n_qt && n_qt > 0) { qt -= n_qt; ++hl; }
     for (int s = wg; s < n_steps; s += kWGs) {
-      const int sb = s & 1, h = h_begin + hl;
+      const int sb = s & 1, ss = s % C::kSSlots, h = h_begin + hl;   // P / O slot of this warpgroup, score slot of this step
       const int n = (tile0 + qt) * 128 + row;
-      mbar_wait(&bars->s_full[sb], (s >> 1) & 1);
+      mbar_wait(&bars->s_full[ss], (s / C::kSSlots) & 1);
       tc_fence_after();
       float sv[96];
       float sel[kAll ? 1 : kTFew];
-      const uint32_t s_taddr = tmem + lane_base + sb * kTSlot;
+      const uint32_t s_taddr = tmem + lane_base + ss * kTSlot;
       tmem_ld32(s_taddr, sv);
       tmem_ld32(s_taddr + 32, sv + 32);
       tmem_ld16(s_taddr + 64, sv + 64);
@@ -401,7 +407,7 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
       }
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&bars->s_free[sb]);  // S(s) is in registers
+      mbar_arrive(&bars->s_free[ss]);  // S(s) is in registers
       if (M >= 64) {
 #pragma unroll
         for (int i = 64; i < kTMPad; ++i)
