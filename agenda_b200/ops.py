@@ -17,6 +17,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """The C ABI launches on the calling thread's CURRENT device and torch's current stream of that device.  A caller
+    whose tensors live on another GPU of the process (HeatmapPipeline(device="cuda:1") while cuda:0 is current, a
+    device_map-sharded UNet) gets the right device made current for the duration of the call."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+            if isinstance(a, ContextKV):
+                continue
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _dev(t: torch.Tensor, name: str, dtype=None) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"agenda_b200: `{name}` must be a CUDA tensor (no CPU fallback exists)")
@@ -35,6 +55,7 @@ def _dtype_code(t: torch.Tensor) -> int:
 
 # ------------------------------------------------------------------ attention (hook.py:104-115) ---------------
 
+@_on_tensor_device
 def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
               precision: str = "bf16") -> torch.Tensor:
     """softmax(scale * q k^T) v per head.  q/k/v [B,N,H*d] token-major (to_q/to_k/to_v outputs).
@@ -69,6 +90,7 @@ def attn_self(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     return out
 
 
+@_on_tensor_device
 def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = None,
                         prescaled: bool = False) -> torch.Tensor:
     """Self-attention on the output of ONE fused q/k/v projection: qkv bf16 [B,N,3C] with q = [..,:C], k = [..,C:2C],
@@ -88,6 +110,7 @@ def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = 
     return out
 
 
+@_on_tensor_device
 def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, maps: Optional[torch.Tensor],
                     token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
                     scale: Optional[float] = None, force_f32_kernel: bool = False,
@@ -137,6 +160,7 @@ def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
 SELF_BWD_HEAD_DIMS = (40, 64, 80, 160)
 
 
+@_on_tensor_device
 def attn_self_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, heads: int,
                   scale: Optional[float] = None):
     """Backward of attn_self on the tensor cores (agenda_attn_self_bwd): q/k/v/out/d_out [B,N,H*d] -> (dq, dk, dv) in
@@ -171,6 +195,7 @@ def linear_split_f32_supported(x: torch.Tensor, w: torch.Tensor) -> bool:
             and w.shape[1] % 64 == 0 and w.shape[0] % 160 == 0 and x.shape[-1] == w.shape[1])
 
 
+@_on_tensor_device
 def linear_split_f32(x: torch.Tensor, w_hi: torch.Tensor, w_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x bf16 [..., K] @ (w_hi + w_lo)[N, K]^T -> fp32 [..., N] in one tcgen05 GEMM (agenda_linear_split_f32): fp32
     accumulation AND fp32 output, both weight halves into the same accumulator.  w_lo None: plain fp32-output GEMM."""
@@ -198,6 +223,7 @@ class ContextKV:
         self.blob, self.B, self.M, self.heads, self.d = blob, B, M, heads, d
 
 
+@_on_tensor_device
 def pack_context_kv(k32: torch.Tensor, v: torch.Tensor, heads: int, out: Optional[ContextKV] = None) -> ContextKV:
     """k32 fp32 [B,M,H*d] (the key projection in fp32), v fp32 or bf16 [B,M,H*d] -> ContextKV.  Pass `out` to refill an
     existing blob in place (same shapes): captured CUDA graphs keep reading the same buffer."""
@@ -221,6 +247,7 @@ def pack_context_kv(k32: torch.Tensor, v: torch.Tensor, heads: int, out: Optiona
     return out
 
 
+@_on_tensor_device
 def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Tensor],
                        token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
                        scale: Optional[float] = None, per_head: bool = False,
@@ -262,6 +289,7 @@ def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Ten
     return out
 
 
+@_on_tensor_device
 def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor,
                    d_maps: Optional[torch.Tensor], heads: int, token_idx: Optional[Sequence[int]] = None,
                    b_first: int = 0, scale: Optional[float] = None):
@@ -297,6 +325,7 @@ def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: tor
 
 # ------------------------------------------------------------------ heat maps (hook.py:59-81) -----------------
 
+@_on_tensor_device
 def heat_upsample_accum(maps: torch.Tensor, acc: torch.Tensor) -> None:
     """acc[..., L, L] += clamp(bicubic(maps[..., h, w] -> L x L), min=0)  (hook.py:72), in place."""
     maps, acc = _dev(maps, "maps", torch.float32), _dev(acc, "acc", torch.float32)
@@ -310,6 +339,7 @@ def heat_upsample_accum(maps: torch.Tensor, acc: torch.Tensor) -> None:
     _lib.call("agenda_heat_upsample_accum", maps.data_ptr(), acc.data_ptr(), n, h, w, L, _stream())
 
 
+@_on_tensor_device
 def heat_upsample_accum_heads(maps: torch.Tensor, acc: torch.Tensor) -> None:
     """DAAM-style aggregation: maps fp32 [B', G, T, h, w] (G = heads) -> acc fp32 [B', T, L, L] +=
     sum_g clamp(bicubic(maps[:, g]), min=0), every (batch, head, token) plane upsampled and clamped on its own."""
@@ -323,6 +353,7 @@ def heat_upsample_accum_heads(maps: torch.Tensor, acc: torch.Tensor) -> None:
     _lib.call("agenda_heat_upsample_accum_heads", maps.data_ptr(), acc.data_ptr(), Bp * T, T, G, h, w, L, _stream())
 
 
+@_on_tensor_device
 def heat_finalize(acc: torch.Tensor, count: int) -> torch.Tensor:
     """acc / count (the mean over the (layer x step) list, hook.py:79)."""
     acc = _dev(acc, "acc", torch.float32)
@@ -333,6 +364,7 @@ def heat_finalize(acc: torch.Tensor, count: int) -> torch.Tensor:
 
 # ------------------------------------------------------------------ post-processing ----------------------------
 
+@_on_tensor_device
 def heat_normalize_u8(heat: torch.Tensor) -> torch.Tensor:
     """data_generation.py:82 + astype(uint8): heat fp32 [..., h, w] -> u8 same shape, per-map min-max."""
     heat = _dev(heat, "heat", torch.float32)
@@ -342,6 +374,7 @@ def heat_normalize_u8(heat: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def resize_bicubic_u8(img: torch.Tensor, size) -> torch.Tensor:
     """PIL Image.resize((W,H)) default filter for mode 'L' (data_generation.py:85), bit-exact.  img u8 [...,h,w]."""
     img = _dev(img, "img", torch.uint8)
@@ -353,6 +386,7 @@ def resize_bicubic_u8(img: torch.Tensor, size) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def heat_to_u8_image(heat: torch.Tensor, size) -> torch.Tensor:
     """data_generation.py:82-85 fused: fp32 [...,h,w] -> min-max -> u8 -> PIL-bicubic resize -> u8 [...,Ho,Wo]."""
     heat = _dev(heat, "heat", torch.float32)
@@ -364,6 +398,7 @@ def heat_to_u8_image(heat: torch.Tensor, size) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def stack_heatmaps_u8(obj: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor):
     """postprocess_heatmap.py:44-46: returns (stack u8 [...,H,W,3], inv_bg u8 [...,H,W])."""
     obj, fg, bg = (_dev(t, n, torch.uint8) for t, n in ((obj, "obj"), (fg, "fg"), (bg, "bg")))
@@ -378,6 +413,7 @@ def stack_heatmaps_u8(obj: torch.Tensor, fg: torch.Tensor, bg: torch.Tensor):
     return stack, inv
 
 
+@_on_tensor_device
 def heat_postprocess_stack(heat: torch.Tensor, size):
     """a7+a8 fused for (object, fg, bg) triples: heat fp32 [n,3,h,w] -> (planes u8 [n,3,Ho,Wo], stack u8
     [n,Ho,Wo,3], inv_bg u8 [n,Ho,Wo])."""
@@ -394,6 +430,7 @@ def heat_postprocess_stack(heat: torch.Tensor, size):
     return planes, stack, inv
 
 
+@_on_tensor_device
 def ccl_bbox(heat: torch.Tensor, thr: float = 0.5, max_boxes: int = 256, want_labels: bool = True):
     """Threshold + 4-connected components + boxes.  heat fp32 [n,H,W] ->
     (labels int32 [n,H,W] or None, counts int32 [n], boxes int32 [n,max_boxes,5] = x,y,w,h,area)."""

@@ -244,6 +244,50 @@ def test_cross_attention_backward_kernel(cuda_ok, monkeypatch, dtype, B, N, H, d
         assert (a.float() - b_).abs().max().item() < tol * b_.abs().max().item()
 
 
+def test_cross_attention_backward_fp16(cuda_ok):
+    """fp16 training (accelerate mixed_precision=fp16, which finetune_sd_token.py supports): forward AND backward of the
+    cross-attention Function take fp16 tensors and hand fp16 gradients back."""
+    from agenda_b200.autograd import CrossAttentionHeatFn
+    from oracle import hook_oracle as O
+    B, N, H, d, M, T = 2, 256, 8, 40, 77, [2, 5]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q0, k0, v0, go = (torch.randn(B, n, H * d, device="cuda", generator=g).half() for n in (N, M, M, N))
+    gm = torch.randn(B, len(T), N, device="cuda", generator=g)
+    q, k, v = (t.clone().requires_grad_(True) for t in (q0, k0, v0))
+    out, maps = CrossAttentionHeatFn.apply(q, k, v, H, d ** -0.5, T, 0)
+    assert out.dtype == torch.float16
+    torch.autograd.backward((out, maps), (go, gm))
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q0, k0, v0))
+    ref, p = O.attention_core(qr, kr, vr, H)
+    ref_maps = p.reshape(B, H, N, M).mean(1).permute(0, 2, 1)[:, T]
+    torch.autograd.backward((ref, ref_maps), (go.float(), gm))
+    for a, b_ in ((q.grad, qr.grad), (k.grad, kr.grad), (v.grad, vr.grad)):
+        assert a.dtype == torch.float16
+        assert (a.float() - b_).abs().max().item() < 1e-2 * b_.abs().max().item()
+
+
+def test_processor_under_inference_mode_and_on_other_current_device(cuda_ok):
+    """torch.inference_mode() tensors carry no version counter (the prompt K/V cache key must not touch it), and the ops
+    make the tensors' device current for the call (the library launches on the calling thread's current device)."""
+    from agenda_b200 import UNetCrossAttentionHooker, ops
+    from agenda_b200.sd_attention import SDAttention
+    torch.manual_seed(2)
+    attn = SDAttention(320, 768, 8, 40).cuda().bfloat16()
+    proc = UNetCrossAttentionHooker(is_train=False, latent_hw=16, tokens=[3, 9])
+    with torch.inference_mode():
+        x = torch.randn(2, 256, 320, device="cuda").bfloat16()
+        ctx = torch.randn(2, 77, 768, device="cuda").bfloat16()
+        y1 = proc(attn, x, ctx)
+        y2 = proc(attn, x, ctx)              # second call: served from the prompt K/V cache
+        heat = proc.compute_global_heat_map()
+    assert torch.equal(y1, y2) and heat.shape == (1, 2, 16, 16) and torch.isfinite(heat).all()
+    if torch.cuda.device_count() >= 2:
+        q = torch.randn(2, 256, 320, device="cuda:1").bfloat16()
+        with torch.cuda.device(0):
+            o = ops.attn_self(q, q, q, 8)
+        assert o.device.index == 1 and torch.isfinite(o.float()).all()
+
+
 def _train_modules(C, heads, ctx_dim, seed):
     from agenda_b200.sd_attention import SDAttention
     torch.manual_seed(seed)
