@@ -628,6 +628,12 @@ typedef CUresult (*EncodeTiledFnX3)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 // fp32 [B, rows, H*d] viewed as (d, H, rows, B); box (box_cols, 1, box_rows, 1), dense rows (no swizzle), zero fill
 static int make_head_map_f32(CUtensorMap* map, const void* base, int B, int H, int rows, int d, int box_cols, int box_rows) {
+  const unsigned long long Cs = static_cast<unsigned long long>(H) * d;
+  const TensorMapKey key = {base, {static_cast<unsigned long long>(d), static_cast<unsigned long long>(H),
+                                   static_cast<unsigned long long>(rows), static_cast<unsigned long long>(B)},
+                            {static_cast<unsigned long long>(d) * 4, Cs * 4, static_cast<unsigned long long>(rows) * Cs * 4},
+                            {static_cast<unsigned>(box_cols), 1u, static_cast<unsigned>(box_rows), 1u}, 0, 4, 0};
+  if (tensor_map_cache_get(key, map)) return AGENDA_OK;
   bind_primary_context();
   static EncodeTiledFnX3 enc = [] {
     void* p = nullptr;
@@ -648,6 +654,7 @@ static int make_head_map_f32(CUtensorMap* map, const void* base, int B, int H, i
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32 Q) failed (CUresult %d)", static_cast<int>(r));
+  tensor_map_cache_put(key, *map);
   return AGENDA_OK;
 }
 

@@ -298,6 +298,8 @@ static EncodeTiledFn get_encode_fn() {
 // [B, N, H*d] bf16 viewed as (d, H, N, B); box (64, 1, rows, 1), 128-byte swizzle, zero fill out of bounds.
 // cuTensorMapEncodeTiled is a DRIVER entry point: it needs the primary context current on the calling thread.  A thread
 // that has made no runtime call yet (PyTorch's autograd worker on its first backward kernel) has none bound.
+int make_head_map_uncached(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows, long long row_stride);
+
 void bind_primary_context() {
   static thread_local bool bound = false;
   if (!bound) {
@@ -306,7 +308,60 @@ void bind_primary_context() {
   }
 }
 
+namespace {
+struct TensorMapCache {
+  static constexpr int kSlots = 64;
+  TensorMapKey keys[kSlots];
+  CUtensorMap maps[kSlots];
+  int used = 0, next = 0;
+};
+TensorMapCache& tensor_map_cache() {
+  static thread_local TensorMapCache c;
+  return c;
+}
+bool same_key(const TensorMapKey& a, const TensorMapKey& b) {
+  if (a.base != b.base || a.dtype != b.dtype || a.rank != b.rank || a.swizzle != b.swizzle) return false;
+  for (int i = 0; i < 4; ++i)
+    if (a.dims[i] != b.dims[i] || a.box[i] != b.box[i]) return false;
+  for (int i = 0; i < 3; ++i)
+    if (a.strides[i] != b.strides[i]) return false;
+  return true;
+}
+}  // namespace
+
+bool tensor_map_cache_get(const TensorMapKey& key, CUtensorMap* out) {
+  TensorMapCache& c = tensor_map_cache();
+  for (int i = 0; i < c.used; ++i)
+    if (same_key(c.keys[i], key)) {
+      *out = c.maps[i];
+      return true;
+    }
+  return false;
+}
+void tensor_map_cache_put(const TensorMapKey& key, const CUtensorMap& map) {
+  TensorMapCache& c = tensor_map_cache();
+  const int slot = c.next;
+  c.keys[slot] = key;
+  c.maps[slot] = map;
+  c.next = (c.next + 1) % TensorMapCache::kSlots;
+  if (c.used < TensorMapCache::kSlots) ++c.used;
+}
+
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows, long long row_stride) {
+  {
+    const unsigned long long Cs = row_stride ? static_cast<unsigned long long>(row_stride) : static_cast<unsigned long long>(H) * d;
+    TensorMapKey key = {base, {static_cast<unsigned long long>(d), static_cast<unsigned long long>(H),
+                               static_cast<unsigned long long>(N), static_cast<unsigned long long>(B)},
+                        {static_cast<unsigned long long>(d) * 2, Cs * 2, static_cast<unsigned long long>(N) * Cs * 2},
+                        {64u, 1u, static_cast<unsigned>(box_rows), 1u}, 1, 4, 128};
+    if (tensor_map_cache_get(key, map)) return AGENDA_OK;
+    int rc = make_head_map_uncached(map, base, B, H, N, d, box_rows, row_stride);
+    if (rc == AGENDA_OK) tensor_map_cache_put(key, *map);
+    return rc;
+  }
+}
+
+int make_head_map_uncached(CUtensorMap* map, const void* base, int B, int H, int N, int d, int box_rows, long long row_stride) {
   bind_primary_context();
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");

@@ -187,6 +187,10 @@ typedef CUresult (*EncodeTiledFnL)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // row-major [rows, cols] matrix viewed as (cols, rows); box (box_cols, box_rows), 128-byte swizzle
 static int make_matrix_map(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem, long long rows, long long cols,
                            int box_cols, int box_rows) {
+  const TensorMapKey key = {base, {static_cast<unsigned long long>(cols), static_cast<unsigned long long>(rows), 1ull, 1ull},
+                            {static_cast<unsigned long long>(cols) * elem, 0ull, 0ull},
+                            {static_cast<unsigned>(box_cols), static_cast<unsigned>(box_rows), 1u, 1u}, static_cast<int>(dt), 2, 128};
+  if (tensor_map_cache_get(key, map)) return AGENDA_OK;
   bind_primary_context();
   static EncodeTiledFnL enc = [] {
     void* p = nullptr;
@@ -204,6 +208,7 @@ static int make_matrix_map(CUtensorMap* map, const void* base, CUtensorMapDataTy
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AGENDA_ERR_CUDA, "cuTensorMapEncodeTiled (matrix) failed (CUresult %d)", static_cast<int>(r));
+  tensor_map_cache_put(key, *map);
   return AGENDA_OK;
 }
 

@@ -222,6 +222,19 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
 
 // [B, rows, H*d] bf16 viewed as (d, H, rows, B); box (64, 1, box_rows, 1), 128-byte swizzle, zero fill out of bounds.
 void bind_primary_context();
+
+// Descriptor cache (the ABI's one piece of state: "per-device TMA descriptor caches").  A tensor map is a
+// pure function of (address, element type, dims, strides, box, swizzle): the calling thread keeps its most recent ones,
+// so a processor that is called with the same buffers step after step encodes each map once (cuTensorMapEncodeTiled costs
+// about a microsecond; an eager — not graph-captured — denoising step builds ~100 of them).
+struct TensorMapKey {
+  const void* base;
+  unsigned long long dims[4], strides[3];
+  unsigned box[4];
+  int dtype, rank, swizzle;
+};
+bool tensor_map_cache_get(const TensorMapKey& key, CUtensorMap* out);
+void tensor_map_cache_put(const TensorMapKey& key, const CUtensorMap& map);
 // row_stride (elements) = distance between consecutive rows; 0 = packed rows of H*d (q/k/v as column slices of one
 // fused-projection output pass the row length of that output).
 int make_head_map(CUtensorMap* map, const void* base, int B, int H, int rows, int d, int box_rows, long long row_stride = 0);

@@ -8,8 +8,8 @@
  * Conventions (all entry points):
  *   - plain pointers + sizes, no framework types; device pointers unless stated "host".
  *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, nothing synchronises,
- *     nothing allocates device memory, no global state is kept (TMA descriptors are built per call
- *     on the host and passed by value to the kernel).
+ *     nothing allocates device memory, no global state is kept beyond a per-thread cache of TMA descriptors
+ *     (a descriptor is a pure function of address, shape and box; it is passed by value to the kernel).
  *   - returns 0 (AGENDA_OK) or a negative error code; agenda_last_error() gives a thread-local
  *     human-readable message for the last failure on the calling thread.
  *   - re-entrant across streams and devices (uses the calling thread's current device).
