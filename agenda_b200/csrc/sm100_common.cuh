@@ -36,6 +36,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -217,6 +229,46 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+
+// ---- softmax pieces shared by the self-attention kernels ----
+constexpr float kV2RescaleThreshold = 8.0f;  // lazy O rescale: only when the row maximum grows by more than 2^8
+
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU (FlashAttention-4's trick: at small head dims the
+// 16 exp/clk/SM MUFU is the kernel's bottleneck, so a fraction of the exponentials is moved to idle FMA lanes).
+// x = s * scale - m is never formed: u = sat(s * a + b) with a = scale / 253, b = (126 - m) / 253 maps x in
+// [-126, 127] onto [0, 1], so ONE saturating FMA per score scales, shifts and clamps on both sides (below -126 the
+// exponent add would wrap; 127 is the largest finite exponent, and a clamped 2^127 is caught by the row-sum check of
+// the fast path).  Then x = n + f with n = round(x), f in [-0.5, 0.5]: 2^f by a cubic minimax polynomial (max rel.
+// error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n to the exponent field.  253 * u carries an
+// absolute error <= 253 * 2^-25 = 7.5e-6 in x.  (NaN scores saturate to 0 like they did under fmaxf.)
+struct Ex2Emu {
+  uint64_t k253_2, magic_lo2, c0_2, c1_2, c2_2, c3_2;
+  __device__ __forceinline__ Ex2Emu() {
+    k253_2 = pack_f32x2(253.f, 253.f);
+    magic_lo2 = pack_f32x2(12582912.f - 126.f, 12582912.f - 126.f);
+    c0_2 = pack_f32x2(0.9999280572f, 0.9999280572f);
+    c1_2 = pack_f32x2(0.6932609677f, 0.6932609677f);
+    c2_2 = pack_f32x2(0.2426111251f, 0.2426111251f);
+    c3_2 = pack_f32x2(0.0551716648f, 0.0551716648f);
+  }
+  __device__ __forceinline__ void operator()(float s0, float s1, float a, float b, float& r0, float& r1) const {
+    float u0, u1;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u0) : "f"(s0), "f"(a), "f"(b));
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(u1) : "f"(s1), "f"(a), "f"(b));
+    const uint64_t u2 = pack_f32x2(u0, u1);
+    const uint64_t t2 = ffma2(u2, k253_2, magic_lo2);  // x + 1.5 * 2^23: low mantissa bits = n = round(x)
+    const uint64_t g2 = fsub2(magic_lo2, t2);          // -(n + 126)
+    const uint64_t f2 = ffma2(u2, k253_2, g2);         // x - n
+    uint64_t p2 = ffma2(c3_2, f2, c2_2);
+    p2 = ffma2(p2, f2, c1_2);
+    p2 = ffma2(p2, f2, c0_2);
+    float t0, t1, p0, p1;
+    unpack_f32x2(t2, t0, t1);
+    unpack_f32x2(p2, p0, p1);
+    r0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    r1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+  }
+};
 
 }  // namespace sm100
 
