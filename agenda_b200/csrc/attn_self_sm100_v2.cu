@@ -67,13 +67,19 @@ struct V2Cfg {
   // every V tile is set to 1.0, so O[:, D] accumulates the softmax denominator sum_j P (in fp32, from the same
   // bf16-rounded P the numerator uses) and the softmax warps drop one packed add per pair of scores.
   static constexpr bool kSumInMma = (kDP > D);
+  // Q(t) as the A operand FROM TMEM (TS-form QK^T) where the columns are free (d = 40, three tiles: 432 + 72 = 504): the
+  // SS form re-reads the 128 x kDP Q tile from shared memory for every key tile (4 KB per K = 16 step, more than the
+  // K tile itself) — 48 instead of 32 tensor cycles per MMA at 64 keys, and under the board's power cap (DESIGN.md K1
+  // item 6) every byte not moved is time.  kDP / 2 columns of packed bf16 pairs per tile.
+  static constexpr int kColQ = kColO + NT_ * kDP;  // + t * kDP / 2
+  static constexpr bool kQInTmem = (KS_ == 1) && (kColQ + NT_ * kDP / 2 <= 512);
   static_assert(kColO + NT_ * kDP <= 512, "TMEM overflow");
   static_assert(NT_ <= kV2MaxTiles, "too many query tiles");
 };
 
 struct V2Barriers {
   float xmax[2][2][2][128];  // [tile parity][query tile][column half][row]: row-max exchange (KS = 2 only)
-  uint64_t q_full;
+  uint64_t q_full, q_tmem[kV2MaxTiles];
   uint64_t k_full[3], k_empty[3], v_full[3], v_empty[3];
   uint64_t s_full[kV2MaxTiles], s_free[kV2MaxTiles], p_full[kV2MaxTiles], pv_done[kV2MaxTiles];
   uint32_t tmem_base;
@@ -146,7 +152,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       }
       for (int t = 0; t < NT; ++t) {
         mbar_inval(&bars->s_full[t]); mbar_inval(&bars->s_free[t]);
-        mbar_inval(&bars->p_full[t]); mbar_inval(&bars->pv_done[t]);
+        mbar_inval(&bars->p_full[t]); mbar_inval(&bars->pv_done[t]); mbar_inval(&bars->q_tmem[t]);
       }
     }
     mbar_init(&bars->q_full, 1);
@@ -158,6 +164,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     for (int t = 0; t < NT; ++t) {
       mbar_init(&bars->s_full[t], 1); mbar_init(&bars->s_free[t], 128 * KS);
       mbar_init(&bars->p_full[t], 128 * KS); mbar_init(&bars->pv_done[t], 1);
+      mbar_init(&bars->q_tmem[t], 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -222,7 +229,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         for (int kk = 0; kk < C::kDP / 16; ++kk) {
           const uint64_t adesc = q_desc + static_cast<uint64_t>((t * C::kQTileBytes + (kk >> 2) * 128 * 128 + (kk & 3) * 32) >> 4);
           const uint64_t bdesc = k_desc + static_cast<uint64_t>((s * C::kKVBytes + (kk >> 2) * BN * 128 + (kk & 3) * 32) >> 4);
-          umma_ss(tmem + C::kColS + t * BN, adesc, bdesc, idesc_qk, kk != 0);
+          if (C::kQInTmem) umma_ts(tmem + C::kColS + t * BN, tmem + C::kColQ + t * (C::kDP / 2) + kk * 8, bdesc, idesc_qk, kk != 0);
+          else umma_ss(tmem + C::kColS + t * BN, adesc, bdesc, idesc_qk, kk != 0);
         }
         umma_commit(&bars->s_full[t]);
       }
@@ -270,6 +278,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const int t = warp - kMmaWarp;
       if (t < nt) {
         mbar_wait(&bars->q_full, 0);
+        if (C::kQInTmem) mbar_wait(&bars->q_tmem[t], 0);  // the softmax warpgroup has copied Q(t) into TMEM
         mbar_wait(&bars->k_full[0], 0);
         tc_fence_after();
         issue_qk(t, 0);
@@ -295,6 +304,8 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       }
     } else if (warp == kMmaWarp) {
     mbar_wait(&bars->q_full, 0);
+    if (C::kQInTmem)
+      for (int t = 0; t < nt; ++t) mbar_wait(&bars->q_tmem[t], 0);
     mbar_wait(&bars->k_full[0], 0);
     tc_fence_after();
     for (int t = 0; t < nt; ++t) issue_qk(t, 0);
@@ -397,6 +408,25 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     float m_used = (kUnit && fast) ? 0.f : -INFINITY;  // (kUnit fast pass: fixed reference 0)
     float l_run = 0.f;
     const uint64_t scale2 = pack_f32x2(scale_log2, scale_log2);
+    if (C::kQInTmem) {
+      // Q(t) -> TMEM, the A-operand layout of a TS-form MMA (lane = row, one column = two consecutive bf16): this
+      // thread's row out of the 128B-swizzled tile TMA wrote (16-byte piece p of row r sits at p ^ (r & 7)); the
+      // pieces beyond D are the zero fill of the tensor map's out-of-bounds columns
+      mbar_wait(&bars->q_full, 0);
+      const unsigned char* qrow = sQ + t * C::kQTileBytes + row * 128;  // (+ 128 * 128 per 64-element chunk of the row)
+      uint32_t qv[C::kDP / 2];
+#pragma unroll
+      for (int pc = 0; pc < C::kDP / 8; ++pc) {
+        const uint4 v4 = *reinterpret_cast<const uint4*>(qrow + (pc >> 3) * 128 * 128 + (((pc & 7) ^ (row & 7)) << 4));
+        qv[4 * pc] = v4.x; qv[4 * pc + 1] = v4.y; qv[4 * pc + 2] = v4.z; qv[4 * pc + 3] = v4.w;
+      }
+      const uint32_t q_taddr = tmem + lane_base + C::kColQ + t * (C::kDP / 2);
+#pragma unroll
+      for (int c = 0; c < C::kDP / 2; c += 8) tmem_st8(q_taddr + c, qv + c);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars->q_tmem[t]);
+    }
     const bool pingpong = (NT == 2) && (nt == 2) && ((issue_order & 3) >= 2) && (issue_order & 4);
     if (pingpong && t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(3), "r"(2 * KS * 128) : "memory");  // tile 0 goes first
     // One key tile.  kMasked is only instantiated for a ragged last tile: with a run-time test the compiler

@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
     cudaMemcpy(ho.data(), o, n * 2, cudaMemcpyDeviceToHost);
     double worst = 0;
     for (int pick = 0; pick < 6; ++pick) {
-      const int b = pick < 3 ? 0 : B - 1, hh = pick < 3 ? 0 : H - 1, r = (pick % 3) * 1531 + 7;
+      const int b = pick < 3 ? 0 : B - 1, hh = pick < 3 ? 0 : H - 1, r = ((pick % 3) * 1531 + 7) % N;
       std::vector<double> p(N);
       double mx = -1e300, l = 0;
       for (int c = 0; c < N; ++c) {
