@@ -38,6 +38,8 @@ _SIGNATURES = {
     "agenda_attn_cross_fwd_heat_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p, c_int,
                                        c_void_p],
+    "agenda_attn_fwd_masked": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                               c_void_p, c_int, ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "agenda_linear_split_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "agenda_pack_context_kv": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_attn_cross_fwd_heat_x3": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,

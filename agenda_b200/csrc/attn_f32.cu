@@ -28,7 +28,8 @@ template <typename T, bool CROSS>
 __global__ void __launch_bounds__(kWarps * 32) attn_f32_kernel(const T* __restrict__ q, const T* __restrict__ k,
                                                                const T* __restrict__ v, T* __restrict__ out, int B,
                                                                int H, int N, int M, int d, float scale, TokenList tl,
-                                                               int b_first, float* __restrict__ maps, int accumulate) {
+                                                               int b_first, float* __restrict__ maps, int accumulate,
+                                                               const float* __restrict__ mask, int mask_rows) {
   extern __shared__ __align__(16) float smem[];
   const int ldk = d + 1;  // padded K rows: lane <-> key reads are bank-conflict free
   float* sQ = smem;                   // [kTQ][d]
@@ -98,6 +99,10 @@ __global__ void __launch_bounds__(kWarps * 32) attn_f32_kernel(const T* __restri
 #pragma unroll
         for (int j = 0; j < kTK / 32; ++j) {
           s[r][j] = (lane + 32 * j < kl) ? s[r][j] * scale : -INFINITY;
+          if (mask != nullptr && lane + 32 * j < kl) {  // additive mask [B*H, 1 | N, M] (hook.py:92,108: baddbmm input)
+            const int n = min(q0 + wid * kRPW + r, N - 1);
+            s[r][j] += mask[(static_cast<long long>(b * H + h) * mask_rows + (mask_rows == 1 ? 0 : n)) * M + kv0 + lane + 32 * j];
+          }
           tmax = fmaxf(tmax, s[r][j]);
         }
         tmax = warp_max(tmax);
@@ -189,14 +194,15 @@ static size_t attn_f32_smem(int d, int T) {
 
 template <typename T, bool CROSS>
 static int launch_attn_f32(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int M, int d,
-                           float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream) {
+                           float scale, const TokenList& tl, int b_first, float* maps, int accumulate, void* stream,
+                           const float* mask = nullptr, int mask_rows = 1) {
   const size_t smem = attn_f32_smem(d, CROSS ? tl.n : 0);
   auto kern = attn_f32_kernel<T, CROSS>;
   AGENDA_DYN_SMEM(kern, smem);
   dim3 grid((N + kTQ - 1) / kTQ, CROSS ? B : B * H);
   attn_f32_kernel<T, CROSS><<<grid, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v), static_cast<T*>(out), B, H, N, M,
-      d, scale, tl, b_first, maps, accumulate);
+      d, scale, tl, b_first, maps, accumulate, mask, mask_rows);
   AGENDA_LAUNCH_CHECK("attn_f32_kernel");
   return AGENDA_OK;
 }
@@ -253,4 +259,37 @@ extern "C" int agenda_attn_self_fwd_f32(const void* q, const void* k, const void
   return dtype == AGENDA_F32
              ? launch_attn_f32<float, false>(q, k, v, out, B, H, N, N, d, scale, tl, 0, nullptr, 0, stream)
              : launch_attn_f32<__nv_bfloat16, false>(q, k, v, out, B, H, N, N, d, scale, tl, 0, nullptr, 0, stream);
+}
+
+// Attention with an additive mask (hook.py:92: `attn.prepare_attention_mask` -> [B*H, 1 | N, M], added to the scaled
+// logits by `get_attention_scores`' baddbmm, hook.py:108).  The SD UNets pass none; pipelines that do (padding masks
+// of a text encoder) get the exact fp32 path: one kernel for self- and cross-attention, heat maps as in
+// agenda_attn_cross_fwd_heat when `maps` is given (then M <= 128).  A fully masked row gives NaN, as in torch.
+extern "C" int agenda_attn_fwd_masked(const void* q, const void* k, const void* v, void* out, int dtype, int B, int H, int N,
+                                      int M, int d, float scale, const float* mask, int mask_rows,
+                                      const int32_t* token_idx, int T, int b_first, int per_head, float* maps,
+                                      int accumulate, void* stream) {
+  int rc = attn_common_checks("attn_fwd_masked", q, k, v, out, dtype, B, H, N, M, d);
+  if (rc != AGENDA_OK) return rc;
+  if (d > kMaxD) return fail(AGENDA_ERR_UNSUPPORTED, "attn_fwd_masked: d=%d > %d", d, kMaxD);
+  if (mask == nullptr) return fail(AGENDA_ERR_NULL_POINTER, "attn_fwd_masked: mask is NULL (use the unmasked entry points)");
+  if (mask_rows != 1 && mask_rows != N)
+    return fail(AGENDA_ERR_BAD_SHAPE, "attn_fwd_masked: mask_rows=%d must be 1 (broadcast over queries) or N=%d", mask_rows, N);
+  TokenList tl;
+  tl.n = 0;
+  tl.per_head = 0;
+  if (maps != nullptr) {
+    if (M > kTK) return fail(AGENDA_ERR_UNSUPPORTED, "attn_fwd_masked: heat maps need M=%d <= %d", M, kTK);
+    if (b_first < 0 || b_first >= B) return fail(AGENDA_ERR_BAD_SHAPE, "attn_fwd_masked: b_first=%d outside [0,%d)", b_first, B);
+    if ((rc = build_token_list("attn_fwd_masked", token_idx, T, M, &tl)) != AGENDA_OK) return rc;
+    tl.per_head = per_head ? 1 : 0;
+    return dtype == AGENDA_F32 ? launch_attn_f32<float, true>(q, k, v, out, B, H, N, M, d, scale, tl, b_first, maps, accumulate,
+                                                              stream, mask, mask_rows)
+                               : launch_attn_f32<__nv_bfloat16, true>(q, k, v, out, B, H, N, M, d, scale, tl, b_first, maps,
+                                                                      accumulate, stream, mask, mask_rows);
+  }
+  return dtype == AGENDA_F32
+             ? launch_attn_f32<float, false>(q, k, v, out, B, H, N, M, d, scale, tl, 0, nullptr, 0, stream, mask, mask_rows)
+             : launch_attn_f32<__nv_bfloat16, false>(q, k, v, out, B, H, N, M, d, scale, tl, 0, nullptr, 0, stream, mask,
+                                                     mask_rows);
 }

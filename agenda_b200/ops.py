@@ -111,6 +111,44 @@ def attn_self_fused_qkv(qkv: torch.Tensor, heads: int, scale: Optional[float] = 
 
 
 @_on_tensor_device
+def attn_masked(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, mask: torch.Tensor,
+                maps: Optional[torch.Tensor] = None, token_idx: Optional[Sequence[int]] = None, b_first: int = 0,
+                accumulate: bool = False, scale: Optional[float] = None, per_head: bool = False) -> torch.Tensor:
+    """softmax(scale q k^T + mask) v with the additive mask `attn.prepare_attention_mask` returns (hook.py:92,108):
+    mask [B*heads, 1 | N, M] (any float dtype; bool / 0-1 masks must already be additive, as diffusers makes them).
+    Self- and cross-attention alike; `maps` etc. as in attn_cross_heat.  Exact fp32 CUDA-core path."""
+    q = _dev(q, "q")
+    if q.dtype == torch.float16:
+        return attn_masked(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16), heads, mask, maps, token_idx,
+                           b_first, accumulate, scale, per_head).to(torch.float16)
+    k, v = _dev(k, "k", q.dtype), _dev(v, "v", q.dtype)
+    B, N, C = q.shape
+    M = k.shape[1]
+    d = C // heads
+    scale = float(d ** -0.5 if scale is None else scale)
+    if mask.dim() != 3 or mask.shape[0] != B * heads or mask.shape[1] not in (1, N) or mask.shape[2] != M:
+        raise ValueError(f"mask must be [B*heads={B * heads}, 1 or N={N}, M={M}], got {tuple(mask.shape)}")
+    mask = mask.to(device=q.device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(q)
+    if maps is not None:
+        maps = _dev(maps, "maps", torch.float32)
+        T = M if token_idx is None else len(token_idx)
+        lead = (B - b_first, heads, T) if per_head else (B - b_first, T)
+        if tuple(maps.shape[:len(lead)]) != lead or maps.numel() != N * int(torch.tensor(lead).prod()):
+            raise ValueError(f"maps must be {list(lead)} + [{N}], got {tuple(maps.shape)}")
+        if not maps.is_contiguous():
+            raise ValueError("maps must be contiguous (it is written in place)")
+        idx = None if token_idx is None else (ctypes.c_int32 * T)(*[int(i) for i in token_idx])
+        mp = maps.data_ptr()
+    else:
+        T, idx, mp = 0, None, None
+    _lib.call("agenda_attn_fwd_masked", q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _dtype_code(q),
+              B, heads, N, M, d, scale, mask.data_ptr(), int(mask.shape[1]), idx, T, int(b_first), int(bool(per_head)), mp,
+              int(bool(accumulate)), _stream())
+    return out
+
+
+@_on_tensor_device
 def attn_cross_heat(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, maps: Optional[torch.Tensor],
                     token_idx: Optional[Sequence[int]] = None, b_first: int = 0, accumulate: bool = False,
                     scale: Optional[float] = None, force_f32_kernel: bool = False,

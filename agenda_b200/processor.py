@@ -303,12 +303,15 @@ class UNetCrossAttentionHooker:
     # ---- hook.py:83-122 ------------------------------------------------------------------------------------
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
         batch_size, sequence_length, _ = hidden_states.shape
+        # hook.py:92.  The SD UNets pass no mask; when one arrives (additive, [B*heads, 1 | N, M]) the exact fp32 kernel
+        # adds it to the scaled logits like get_attention_scores' baddbmm (hook.py:108).  `upcast_attention` /
+        # `upcast_softmax` need no branch: every kernel here accumulates the logits and takes the softmax in fp32.
         attention_mask = attn.prepare_attention_mask(attention_mask, sequence_length, batch_size)
-        if attention_mask is not None:
-            raise NotImplementedError("agenda_b200: attention masks are not supported (the SD UNet passes none)")
         if torch.is_grad_enabled() and self._wants_grad(attn, hidden_states, encoder_hidden_states):
+            if attention_mask is not None:
+                raise NotImplementedError("agenda_b200: attention masks are not supported in training mode")
             return self._call_with_autograd(attn, hidden_states, encoder_hidden_states)
-        if (encoder_hidden_states is None and self.fuse_qkv and self.precision == "bf16"
+        if (encoder_hidden_states is None and attention_mask is None and self.fuse_qkv and self.precision == "bf16"
                 and hidden_states.dtype == torch.bfloat16 and hidden_states.is_cuda):
             w, prescaled = self._fused_qkv_weight(attn)
             if w is not None:
@@ -325,8 +328,8 @@ class UNetCrossAttentionHooker:
         scale = float(attn.scale)
         in_dtype = hidden_states.dtype
 
-        x3 = is_cross_attn and hidden_states.is_cuda and self._use_x3(attn, attn.to_q.weight.shape[0],
-                                                                       encoder_hidden_states.shape[1])
+        x3 = (is_cross_attn and attention_mask is None and hidden_states.is_cuda
+              and self._use_x3(attn, attn.to_q.weight.shape[0], encoder_hidden_states.shape[1]))
         if x3:
             query = self._query_fp32(attn, hidden_states)
             if self.cache_context_kv and attn.norm_cross is None:
@@ -348,6 +351,9 @@ class UNetCrossAttentionHooker:
                 value = attn.to_v(encoder_hidden_states)
 
             def cross(maps, accumulate, per_head=False):
+                if attention_mask is not None:
+                    return ops.attn_masked(query, key, value, heads, attention_mask, maps, self.tokens, b_first,
+                                           accumulate=accumulate, scale=scale, per_head=per_head)
                 return ops.attn_cross_heat(query, key, value, heads, maps, self.tokens, b_first, accumulate=accumulate,
                                            scale=scale, per_head=per_head)
 
@@ -382,6 +388,8 @@ class UNetCrossAttentionHooker:
                 if self.record_maps:
                     self.cross_attn_maps.append(maps)
             self._count += 1
+        elif attention_mask is not None:
+            hidden_states = ops.attn_masked(query, key, value, heads, attention_mask, scale=scale)
         else:
             hidden_states = ops.attn_self(query, key, value, heads, scale=scale, precision=self.precision)
 

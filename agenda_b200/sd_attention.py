@@ -37,6 +37,14 @@ class SDAttention(nn.Module):
         self.processor = processor
 
     def prepare_attention_mask(self, attention_mask, target_length, batch_size):
+        """diffusers' contract: an additive mask [B, M], [B, 1 | N, M] or already [B*heads, 1 | N, M] comes back as
+        [B*heads, 1 | N, M] (repeated over the heads)."""
+        if attention_mask is None:
+            return None
+        if attention_mask.dim() == 2:
+            attention_mask = attention_mask[:, None, :]
+        if attention_mask.shape[0] == batch_size:
+            attention_mask = attention_mask.repeat_interleave(self.heads, dim=0)
         return attention_mask
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None):

@@ -166,6 +166,19 @@ int agenda_attn_cross_fwd_heat_f32(const void* q, const void* k, const void* v, 
                                    const int32_t* token_idx, int T, int b_first,
                                    float* maps, int accumulate, void* stream);
 
+/* Attention with an additive mask: data_generation/hook.py:92 (`attn.prepare_attention_mask`) and :108
+ * (`attn.get_attention_scores(query, key, attention_mask)` = baddbmm(mask, q, k^T, alpha = scale) + softmax).
+ * mask: fp32 [B*H, mask_rows, M] with mask_rows 1 (broadcast over queries) or N, what prepare_attention_mask returns.
+ * One entry for both attention kinds: maps == NULL: out = softmax(scale q k^T + mask) v (self-attention: M = N);
+ * maps != NULL: cross-attention with the heat epilogue of agenda_attn_cross_fwd_heat (token_idx, T, b_first,
+ * accumulate as there; per_head != 0: planes [B - b_first, H, T, N] without the head mean), M <= 128.
+ * q [B,N,H*d], k / v [B,M,H*d], out [B,N,H*d] in `dtype` (f32 or bf16).  Exact fp32 CUDA-core path (the SD UNets pass
+ * no mask; this is for pipelines that do).  A fully masked row yields NaN, as torch's softmax does. */
+int agenda_attn_fwd_masked(const void* q, const void* k, const void* v, void* out, int dtype, int B, int H, int N,
+                           int M, int d, float scale, const float* mask, int mask_rows,
+                           const int32_t* token_idx, int T, int b_first, int per_head, float* maps,
+                           int accumulate, void* stream);
+
 /* ---- a4: compute_global_heat_map (data_generation/hook.py:59-81), streaming form ----------------------
  * acc[i, y, x] += max(0, bicubic(maps[i])[y, x]) for i < n_planes; maps fp32 [n_planes,h,w] -> acc fp32
  * [n_planes,L,L].  Bicubic = torch F.interpolate(mode='bicubic', align_corners=False): A=-0.75,

@@ -42,9 +42,12 @@ def batch_to_head_dim(x: torch.Tensor, heads: int) -> torch.Tensor:
     return x.reshape(bh // heads, heads, s, d).permute(0, 2, 1, 3).reshape(bh // heads, s, d * heads)
 
 
-def attention_probs(q: torch.Tensor, k: torch.Tensor, scale: float) -> torch.Tensor:
-    """attn.get_attention_scores (hook.py:108): softmax(scale * q k^T) over the key axis, fp32."""
+def attention_probs(q: torch.Tensor, k: torch.Tensor, scale: float, mask: torch.Tensor = None) -> torch.Tensor:
+    """attn.get_attention_scores (hook.py:108): softmax(scale * q k^T [+ attention_mask]) over the key axis, fp32.
+    mask: what attn.prepare_attention_mask returned (hook.py:92), additive, [B*H, 1 | N, M] (baddbmm input, beta = 1)."""
     s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    if mask is not None:
+        s = s + mask.float()
     return s.softmax(dim=-1)
 
 
@@ -61,7 +64,7 @@ def unravel_attn(probs: torch.Tensor, heads: int, is_train: bool) -> torch.Tenso
     return x.mean(dim=1)
 
 
-def processor_call(hidden_states, encoder_hidden_states, wq, wk, wv, wo, bo, heads: int, is_train: bool):
+def processor_call(hidden_states, encoder_hidden_states, wq, wk, wv, wo, bo, heads: int, is_train: bool, mask=None):
     """hook.py:83-122 with explicit weights (to_q/to_k/to_v bias-free, to_out[0] with bias, dropout p=0).
 
     Returns (out [B,N,C], maps [B',M,h,w] or None for self-attention)."""
@@ -73,7 +76,7 @@ def processor_call(hidden_states, encoder_hidden_states, wq, wk, wv, wo, bo, hea
     v = ehs @ wv.float().t()
     d = q.shape[-1] // heads
     qh, kh, vh = (head_to_batch_dim(t, heads) for t in (q, k, v))
-    p = attention_probs(qh, kh, d ** -0.5)
+    p = attention_probs(qh, kh, d ** -0.5, mask)
     maps = unravel_attn(p, heads, is_train) if is_cross else None
     o = batch_to_head_dim(torch.bmm(p, vh), heads)
     out = o @ wo.float().t() + bo.float()

@@ -271,3 +271,45 @@ def test_processor_fp16_pipeline(ops):
     assert (z.float().cpu() - zr).abs().max().item() < TOL_BF16_OUT * 3
     heat = proc.compute_global_heat_map().cpu()
     assert (heat - mr[:, [3, 9]]).abs().max().item() < 2e-3   # q/k rounded fp16 -> bf16 before the scores
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows", ["broadcast", "per_query"])
+def test_processor_attention_mask(ops, dtype, rows):
+    """hook.py:92,108: an attention mask goes through attn.prepare_attention_mask and is ADDED to the scaled logits
+    (baddbmm).  The SD UNets pass none; when one comes the processor takes the exact fp32 kernel: self- and
+    cross-attention outputs and the heat maps against the oracle with the same additive mask (padding keys at -1e4 as
+    diffusers builds them, plus finite per-key offsets; ragged N / M)."""
+    from agenda_b200 import UNetCrossAttentionHooker
+    from agenda_b200.sd_attention import SDAttention
+    torch.manual_seed(11)
+    C, H, hw, M = 320, 8, 12, 53
+    B, N = 4, hw * hw
+    a_self = SDAttention(C, None, H, C // H).cuda().to(dtype)
+    a_cross = SDAttention(C, 768, H, C // H).cuda().to(dtype)
+    x = torch.randn(B, N, C, device="cuda").to(dtype)
+    ctx = torch.randn(B, M, 768, device="cuda").to(dtype)
+    nq = 1 if rows == "broadcast" else N
+    m_cross = torch.randn(B, nq, M, device="cuda")
+    m_cross[:, :, 40:] = -10000.0          # padding keys
+    m_cross[3, :, 17] = -10000.0       # one real token of the second conditional image
+    m_self = torch.randn(B, nq, N, device="cuda") * 2
+    m_self[:, :, -9:] = -10000.0
+    proc = UNetCrossAttentionHooker(is_train=False, latent_hw=hw, tokens=[2, 17, 39])
+    with torch.no_grad():
+        y = a_self.set_processor(proc) or a_self(x, attention_mask=m_self.to(dtype))
+        z = a_cross.set_processor(proc) or a_cross(x, encoder_hidden_states=ctx, attention_mask=m_cross.to(dtype))
+    w = lambda m: m.weight.detach().float().cpu()
+    rep = lambda m: m.to(dtype).float().cpu().repeat_interleave(H, dim=0)
+    yr, _ = O.processor_call(x.float().cpu(), None, w(a_self.to_q), w(a_self.to_k), w(a_self.to_v), w(a_self.to_out[0]),
+                             a_self.to_out[0].bias.detach().float().cpu(), H, False, mask=rep(m_self))
+    zr, mr = O.processor_call(x.float().cpu(), ctx.float().cpu(), w(a_cross.to_q), w(a_cross.to_k), w(a_cross.to_v),
+                              w(a_cross.to_out[0]), a_cross.to_out[0].bias.detach().float().cpu(), H, False, mask=rep(m_cross))
+    tol_out = 2e-4 if dtype == torch.float32 else TOL_BF16_OUT * 3
+    assert (y.float().cpu() - yr).abs().max().item() < tol_out
+    assert (z.float().cpu() - zr).abs().max().item() < tol_out
+    heat = proc.compute_global_heat_map().cpu()
+    assert heat.shape == (B // 2, 3, hw, hw)
+    assert (heat - mr[:, [2, 17, 39]]).abs().max().item() < (2e-6 if dtype == torch.float32 else 2e-3)
+    # the masked token of batch element 3 (second image of the conditional half) carries no probability
+    assert float(heat[1, 1].abs().max()) < 1e-6 and float(heat[0, 1].abs().max()) > 1e-4
