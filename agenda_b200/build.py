@@ -38,7 +38,10 @@ def build(force: bool = False, verbose: bool = False, variants=None) -> str:
     """variants=True (or AGENDA_BUILD_VARIANTS=1) adds -DAGENDA_VARIANTS: the measurement / test variants of the
     self-attention kernel (agenda_attn_self_fwd_variant 10..58).  The product library does not carry them."""
     variants = _variants_wanted() if variants is None else variants
-    if not force and not _stale():
+    flavor = "variants" if variants else "product"
+    stamp = LIB + ".flavor"   # which of the two the library on disk is: asking for the other one rebuilds
+    have = open(stamp).read().strip() if os.path.exists(stamp) else "product"
+    if not force and not _stale() and have == flavor:
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -50,6 +53,8 @@ def build(force: bool = False, verbose: bool = False, variants=None) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(stamp, "w") as f:
+        f.write(flavor + "\n")
     return LIB
 
 

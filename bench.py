@@ -143,7 +143,11 @@ def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
 
 # ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the probes below (profiles/r02_*_key_metrics.txt);
 # None = not captured for that shape
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    "heat_upsample_accum_32to64": 669.5e6,      # r02_heat_upsample_full_key_metrics.txt: 403.7 MB read + 265.8 MB written
+    "heat_postprocess_stack_64to112": 1069.3e6,  # r02_postprocess_stack_full_key_metrics.txt: 402.8 MB + 666.5 MB
+    "cross_attention_backward": 11.2e6,          # r02_cross_bwd_full_key_metrics.txt (the operands stay in L2)
+}
 
 
 def _time_launches(fn, reps, graph=False):
@@ -535,6 +539,9 @@ def run_ours(args):
                                          "frac": gbs / hbm_gbs, "avg_launch_ms": ms_x / n_x, "launches_timed": n_x,
                                          "ms_per_denoise_step_all_layers": ms_x_all / 5.0,
                                          "share_of_step": (ms_x_all / 5.0 * NUM_DENOISE_STEPS) / (ms_dev / args.steps),
+                                         # r02_cross_x3_d40_full_key_metrics.txt: 90.1 MB read + 8.3 MB written (part of
+                                         # Q, written by the to_q GEMM just before, is served by the 126 MB L2)
+                                         "traffic": 98.5e6 if (kern == "attn_cross_sm100_x3_kernel" and n_img == 8 and not sd21) else None,
                                          "note": "N=%d layers; algorithmic bytes = %s" % (big_n, note)}
 
     extra.update(probe_hbm_kernels(dev, hbm_gbs))
