@@ -548,7 +548,7 @@ __device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
 template <int kThreads, int kCS>
 __global__ void __launch_bounds__(kThreads)
 ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__ labels, int32_t* __restrict__ counts,
-                    int32_t* __restrict__ boxes, int max_boxes, int H, int W, int cap, int hints) {
+                    int32_t* __restrict__ boxes, int max_boxes, int H, int W, int cap, int hints, int use_tab) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ float red_min[32], red_max[32];
   __shared__ int red_nan[32], warp_tot[32];
@@ -569,6 +569,13 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   uint32_t* bits = reinterpret_cast<uint32_t*>(dyn_smem);
   uint32_t* slots = bits + n_words;
   unsigned short* base = reinterpret_cast<unsigned short*>(slots + cap);  // first piece id of every word
+  // Per-word range table (use_tab; kCS == 1 only): pass 1 leaves, for every 32-pixel word, the upper 16 bits of the ordered
+  // keys of its minimum and maximum (min | max << 16).  Once h* is known a word whose maximum lies below it is all
+  // background and a word whose minimum lies above it all foreground WITHOUT a second look at the pixels; only words whose
+  // 16-bit range straddles h* (the contour of the components: ~3 % of a config-5 map) are read again.  The table overlays
+  // the slots / base areas, which are not live before pass 2 has finished (needs 2 * cap >= n_words).
+  uint32_t* wtab = slots;
+  const bool tab = (kCS == 1) && use_tab;
   const float4* src4 = reinterpret_cast<const float4*>(heat + map * n_px);
   const int n4 = n_px >> 2;
   // this CTA's share of the two passes: whole mask words (8 float4 each)
@@ -581,7 +588,19 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   // evict_last; the rest streams with evict_first.  With ~300 maps in flight only a fraction of each can stay in the
   // 126 MB L2: marking everything evict_last marks nothing.
   const int keep_from = (hints >= 2) ? i_end - static_cast<int>(static_cast<long long>(i_end - i_begin) * hints / 100) : i_begin;
-  auto ld1 = [&](int i) { return hints ? ldg_hint(src4 + i, i >= keep_from ? pol_keep : pol_drop) : __ldg(src4 + i); };
+  auto ld1 = [&](int i) {
+    return hints ? ldg_hint(src4 + i, (hints > 0 && i >= keep_from) ? pol_keep : pol_drop) : __ldg(src4 + i);
+  };
+  const unsigned group_mask = 0xFFu << (lane & 24);  // the 8 lanes that hold one mask word (8 float4)
+  // word range: ordered keys of the float4's minimum / maximum, reduced over the word's 8 lanes (NaNs drop out of
+  // fminf / fmaxf; a map with a NaN never consults the table)
+  auto note_word = [&](int i, const float4& v) {
+    uint32_t kmn = f2key(fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+    uint32_t kmx = f2key(fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    kmn = __reduce_min_sync(group_mask, kmn);
+    kmx = __reduce_max_sync(group_mask, kmx);
+    if ((lane & 7) == 0) wtab[i >> 3] = (kmn >> 16) | (kmx & 0xFFFF0000u);
+  };
   auto ld2 = [&](int i) { return hints ? ldg_hint(src4 + i, pol_drop) : __ldg(src4 + i); };
   {
     float lo = INFINITY, hi = -INFINITY;
@@ -596,12 +615,15 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
       nan |= (a.x != a.x) | (a.y != a.y) | (a.z != a.z) | (a.w != a.w) | (b.x != b.x) | (b.y != b.y) | (b.z != b.z) |
              (b.w != b.w) | (c.x != c.x) | (c.y != c.y) | (c.z != c.z) | (c.w != c.w) | (d.x != d.x) | (d.y != d.y) |
              (d.z != d.z) | (d.w != d.w);
+      // (i_begin, i_end and kThreads are multiples of 8: the 8 lanes of a word enter and leave these loops together)
+      if (tab) { note_word(i, a); note_word(i + kThreads, b); note_word(i + 2 * kThreads, c); note_word(i + 3 * kThreads, d); }
     }
     for (; i < i_end; i += kThreads) {
       const float4 a = ld1(i);
       lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
       hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
       nan |= (a.x != a.x) | (a.y != a.y) | (a.z != a.z) | (a.w != a.w);
+      if (tab) note_word(i, a);
     }
     lo = warp_min(lo); hi = warp_max(hi);
     nan = __any_sync(0xffffffffu, nan);
@@ -679,7 +701,28 @@ ccl_bbox_cta_kernel(const float* __restrict__ heat, float thr, int32_t* __restri
   // ---- pass 2 (reverse order: the end of the range is the most recently used part of L2): threshold -> mask words,
   //      written into the LEADER's mask (its own shared memory when kCS == 1) ----
   uint32_t* lead_bits = (kCS > 1) ? cluster.map_shared_rank(bits, 0) : bits;
-  if (mode == 0) {
+  if (mode == 0 && tab) {
+    // key(a) < key(h) implies a < h (or a == -0, h == +0, which the search cannot produce: both zeros normalise alike),
+    // and comparing the upper halves of two keys is conservative, so equal upper halves count as "straddles"
+    const uint32_t ks16 = f2key(hstar) >> 16;
+    const int span = i_end - i_begin;
+    const int iters = (span + kThreads - 1) / kThreads;
+    for (int it = 0; it < iters; ++it) {
+      const int i = i_begin + it * kThreads + tid;
+      if (i < i_end) {  // (uniform over the 8 lanes of a word)
+        const uint32_t t = wtab[i >> 3];
+        uint32_t word;
+        if ((t >> 16) < ks16) word = 0u;
+        else if ((t & 0xFFFFu) > ks16) word = 0xFFFFFFFFu;
+        else {
+          const float4 v = ld2(i);
+          const uint32_t nib = (v.x >= hstar ? 1u : 0u) | (v.y >= hstar ? 2u : 0u) | (v.z >= hstar ? 4u : 0u) | (v.w >= hstar ? 8u : 0u);
+          word = __reduce_or_sync(group_mask, nib << ((lane & 7) * 4));
+        }
+        if ((lane & 7) == 0) bits[i >> 3] = word;
+      }
+    }
+  } else if (mode == 0) {
     const int span = i_end - i_begin;
     const int iters = (span + kThreads - 1) / kThreads;
     for (int it = iters - 1; it >= 0; --it) {
@@ -941,7 +984,7 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
       a4[0].val.clusterDim.x = 2; a4[0].val.clusterDim.y = 1; a4[0].val.clusterDim.z = 1;                              \
       c4.attrs = a4; c4.numAttrs = 1;                                                                                  \
       AGENDA_CUDA(cudaLaunchKernelEx(&c4, ccl_bbox_cta_kernel<T, 2>, heat, thr, labels, counts, boxes, max_boxes, H,   \
-                                     W, static_cast<int>(cap), hints));                                                \
+                                     W, static_cast<int>(cap), hints, use_tab));                                             \
     } else if (cta_cluster == 4) {                                                                                     \
       AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                        static_cast<int>(smem_cta)));                                                   \
@@ -955,12 +998,12 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
       a4[0].val.clusterDim.x = 4; a4[0].val.clusterDim.y = 1; a4[0].val.clusterDim.z = 1;                              \
       c4.attrs = a4; c4.numAttrs = 1;                                                                                  \
       AGENDA_CUDA(cudaLaunchKernelEx(&c4, ccl_bbox_cta_kernel<T, 4>, heat, thr, labels, counts, boxes, max_boxes, H,   \
-                                     W, static_cast<int>(cap), hints));                                                \
+                                     W, static_cast<int>(cap), hints, use_tab));                                             \
     } else {                                                                                                           \
       AGENDA_CUDA(cudaFuncSetAttribute(ccl_bbox_cta_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                        static_cast<int>(smem_cta)));                                                   \
       ccl_bbox_cta_kernel<T, 1><<<n, T, smem_cta, st>>>(heat, thr, labels, counts, boxes, max_boxes, H, W,             \
-                                                        static_cast<int>(cap), hints);                                 \
+                                                        static_cast<int>(cap), hints, use_tab);                             \
     }                                                                                                                  \
   } while (0)
         int cta_cluster = 1;  // 4: split the two streaming passes of a map over a 4-CTA cluster
@@ -971,6 +1014,10 @@ extern "C" int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, in
         // 50 % 1.173 (profiles/r02_ccl_l2_keep_fraction_sweep.txt): ~300 MB of maps are in flight against 126 MB of L2
         int hints = 25;
         if (const char* e = knob("AGENDA_CCL_HINTS")) hints = atoi(e);
+        // per-word range table (see the kernel): pass 2 re-reads only the words whose range straddles the threshold
+        int use_tab = (cta_cluster == 1 && 2 * cap >= n_words) ? 1 : 0;
+        if (const char* e = knob("AGENDA_CCL_TAB")) use_tab = use_tab && atoi(e) != 0;
+        if (use_tab && !knob("AGENDA_CCL_HINTS")) hints = 0;  // nothing to keep in L2 for a sparse second pass
         int cta_threads = n_px >= 65536 ? 1024 : (n_px >= 16384 ? 256 : 128);
         if (const char* e = knob("AGENDA_CCL_CTA_THREADS")) { const int t = atoi(e); if (t == 128 || t == 256 || t == 512 || t == 1024) cta_threads = t; }
         if (cta_threads == 1024) AGENDA_CCL_CTA(1024);

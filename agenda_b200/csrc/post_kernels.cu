@@ -67,37 +67,108 @@ __device__ __forceinline__ uint8_t pil_clip8(int v) {
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int j) { return __byte_perm(w, 0u, 0x4440u | j); }
+
 // in [Hi,Wi] u8 (smem) -> tmp [Hi,Wo] (smem) -> out [Ho,Wo] (smem or global), Pillow's horizontal-then-vertical
 // order.  Coefficient tables must already be in smem.  Caller syncs before.
+// Fast forms for Pillow's five-tap support (every upscale; the tables are zero-filled past a window's real length, so
+// the five taps are always taken — a tap with weight 0 may read a few bytes past its row or plane, still inside the
+// CTA's carve-up, see resize_smem_bytes):
+//   horizontal: a thread owns one output COLUMN (window start and the five weights in registers) and walks the rows;
+//   vertical:   a thread owns four adjacent output columns (one 32-bit load per tap) and walks the output rows.
+// No integer division per output, ~3x fewer instructions than the generic (i / Wo, variable-length window) loops below.
 __device__ void pil_resize_smem(const uint8_t* in, uint8_t* tmp, uint8_t* out, int Hi, int Wi, int Ho, int Wo,
                                 const int* bx, const int* kx, int ksx, const int* by, const int* ky, int ksy) {
   const uint8_t* hsrc = in;
+  const int T = blockDim.x, tid = threadIdx.x;
+  constexpr int kHalf = 1 << (kPilPrecisionBits - 1);
+  const bool roomy = Hi >= 8 && Ho >= 8;  // (zero-weight taps past the end stay inside the next buffer of the carve-up)
   if (Wo != Wi) {
-    for (int i = threadIdx.x; i < Hi * Wo; i += blockDim.x) {
-      const int y = i / Wo, xx = i - y * Wo;
-      const int x0 = bx[2 * xx], n = bx[2 * xx + 1];
-      int acc = 1 << (kPilPrecisionBits - 1);
-      for (int x = 0; x < n; ++x) acc += static_cast<int>(in[y * Wi + x0 + x]) * kx[xx * ksx + x];
-      tmp[i] = pil_clip8(acc);
+    if (ksx == 5 && Wo <= T && roomy) {
+      const int groups = T / Wo, g = tid / Wo, xx = tid - g * Wo;
+      if (g < groups) {
+        const int* k = kx + xx * 5;
+        const int w0 = k[0], w1 = k[1], w2 = k[2], w3 = k[3], w4 = k[4];
+        const uint8_t* r = in + bx[2 * xx] + g * Wi;
+        uint8_t* o = tmp + g * Wo + xx;
+        const int rs = groups * Wi, os = groups * Wo;
+        for (int y = g; y < Hi; y += groups, r += rs, o += os) {
+          const int acc = kHalf + r[0] * w0 + r[1] * w1 + r[2] * w2 + r[3] * w3 + r[4] * w4;
+          *o = pil_clip8(acc);
+        }
+      }
+    } else {
+      for (int i = tid; i < Hi * Wo; i += T) {
+        const int y = i / Wo, xx = i - y * Wo;
+        const int x0 = bx[2 * xx], n = bx[2 * xx + 1];
+        int acc = kHalf;
+        for (int x = 0; x < n; ++x) acc += static_cast<int>(in[y * Wi + x0 + x]) * kx[xx * ksx + x];
+        tmp[i] = pil_clip8(acc);
+      }
     }
     hsrc = tmp;
     __syncthreads();
   }
   if (Ho != Hi) {
-    for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
-      const int yy = i / Wo, x = i - yy * Wo;
-      const int y0 = by[2 * yy], n = by[2 * yy + 1];
-      int acc = 1 << (kPilPrecisionBits - 1);
-      for (int y = 0; y < n; ++y) acc += static_cast<int>(hsrc[(y0 + y) * Wo + x]) * ky[yy * ksy + y];
-      out[i] = pil_clip8(acc);
+    const int q = Wo >> 2;  // four-column groups per row
+    if (ksy == 5 && (Wo & 3) == 0 && q <= T && roomy && (reinterpret_cast<uintptr_t>(hsrc) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+      const int groups = T / q, g = tid / q, x4 = tid - g * q;
+      if (g < groups) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(hsrc) + x4;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out) + x4;
+        for (int yy = g; yy < Ho; yy += groups) {
+          const int* k = ky + yy * 5;
+          const uint32_t* r = src + by[2 * yy] * q;
+          int a0 = kHalf, a1 = kHalf, a2 = kHalf, a3 = kHalf;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const uint32_t w = r[t * q];
+            const int c = k[t];
+            a0 += static_cast<int>(byte_of(w, 0)) * c;
+            a1 += static_cast<int>(byte_of(w, 1)) * c;
+            a2 += static_cast<int>(byte_of(w, 2)) * c;
+            a3 += static_cast<int>(byte_of(w, 3)) * c;
+          }
+          dst[yy * q] = static_cast<uint32_t>(pil_clip8(a0)) | (static_cast<uint32_t>(pil_clip8(a1)) << 8) |
+                        (static_cast<uint32_t>(pil_clip8(a2)) << 16) | (static_cast<uint32_t>(pil_clip8(a3)) << 24);
+        }
+      }
+    } else {
+      for (int i = tid; i < Ho * Wo; i += T) {
+        const int yy = i / Wo, x = i - yy * Wo;
+        const int y0 = by[2 * yy], n = by[2 * yy + 1];
+        int acc = kHalf;
+        for (int y = 0; y < n; ++y) acc += static_cast<int>(hsrc[(y0 + y) * Wo + x]) * ky[yy * ksy + y];
+        out[i] = pil_clip8(acc);
+      }
     }
   } else {
-    for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) out[i] = hsrc[i];
+    for (int i = tid; i < Ho * Wo; i += T) out[i] = hsrc[i];
   }
   __syncthreads();
 }
 
-// Block-wide min/max of an fp32 map (global), result broadcast through smem scratch red[2*32].
+// Block-wide reduction of per-thread (min, max, saw-a-NaN); result broadcast through smem scratch red[2*32].
+__device__ void block_minmax_reduce(float lo, float hi, bool nan, float* red, float& mn, float& mx) {
+  // warp reduce (NaN-propagating like numpy's min / max: fminf drops NaN, so carry a flag)
+  unsigned any_nan = __ballot_sync(0xffffffffu, nan);
+  lo = warp_min(lo); hi = warp_max(hi);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { red[wid] = any_nan ? NAN : lo; red[32 + wid] = any_nan ? NAN : hi; }
+  __syncthreads();
+  if (wid == 0) {
+    float a = lane < nw ? red[lane] : INFINITY, b = lane < nw ? red[32 + lane] : -INFINITY;
+    unsigned nn = __ballot_sync(0xffffffffu, a != a);
+    a = warp_min(a); b = warp_max(b);
+    if (lane == 0) { red[0] = nn ? NAN : a; red[32] = nn ? NAN : b; }
+  }
+  __syncthreads();
+  mn = red[0]; mx = red[32];
+  __syncthreads();
+}
+
+// Block-wide min/max of an fp32 map (global).
 __device__ void block_minmax(const float* __restrict__ h, int n, float* red, float& mn, float& mx) {
   float lo = INFINITY, hi = -INFINITY;
   bool nan = false;
@@ -119,22 +190,7 @@ __device__ void block_minmax(const float* __restrict__ h, int n, float* red, flo
       lo = fminf(lo, v); hi = fmaxf(hi, v); nan |= (v != v);
     }
   }
-  if (nan) { lo = NAN; hi = NAN; }  // numpy min/max propagate NaN
-  // warp reduce (NaN-propagating: fminf drops NaN, so carry a flag)
-  unsigned any_nan = __ballot_sync(0xffffffffu, nan);
-  lo = warp_min(lo); hi = warp_max(hi);
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  if (lane == 0) { red[wid] = any_nan ? NAN : lo; red[32 + wid] = any_nan ? NAN : hi; }
-  __syncthreads();
-  if (wid == 0) {
-    float a = lane < nw ? red[lane] : INFINITY, b = lane < nw ? red[32 + lane] : -INFINITY;
-    unsigned nn = __ballot_sync(0xffffffffu, a != a);
-    a = warp_min(a); b = warp_max(b);
-    if (lane == 0) { red[0] = nn ? NAN : a; red[32] = nn ? NAN : b; }
-  }
-  __syncthreads();
-  mn = red[0]; mx = red[32];
-  __syncthreads();
+  block_minmax_reduce(lo, hi, nan, red, mn, mx);
 }
 
 __device__ __forceinline__ uint8_t quantize_u8(float h, float mn, float denom) {
@@ -238,11 +294,15 @@ __global__ void __launch_bounds__(256) stack_kernel(const uint8_t* __restrict__ 
   }
 }
 
-// a7 + a8 fused: one CTA per image, 3 maps (object, fg token, bg token).
+// a7 + a8 fused: 3 maps per image (object, fg token, bg token).  PERSISTENT CTAs: the Pillow coefficient tables (double
+// precision, ~2 x 112 windows) are built once per CTA and serve every image the CTA walks (img = blockIdx.x, += gridDim.x)
+// instead of once per image; a map small enough (<= 16 floats per thread) is read from HBM exactly once, into registers
+// — min / max and the u8 quantisation both work from there — and the NEXT map's loads are issued before the current
+// map's resize, so their latency hides behind the integer filter.  Outputs leave as 32-bit words.
 __global__ void __launch_bounds__(kPostThreads) postprocess_stack_kernel(const float* __restrict__ heat,
                                                                         uint8_t* __restrict__ planes,
                                                                         uint8_t* __restrict__ stack,
-                                                                        uint8_t* __restrict__ inv, int Hi, int Wi,
+                                                                        uint8_t* __restrict__ inv, int n, int Hi, int Wi,
                                                                         int Ho, int Wo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ float red[64];
@@ -250,31 +310,98 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_stack_kernel(const f
   ResizeSmem s = carve(smem, Hi, Wi, Ho, Wo, ksx, ksy);
   pil_coeffs(Wi, Wo, ksx, s.bx, s.kx);
   pil_coeffs(Hi, Ho, ksy, s.by, s.ky);
-  const int hw = Hi * Wi, n_out = Ho * Wo;
-  const long long img = blockIdx.x;
-  for (int t = 0; t < 3; ++t) {
-    const float* h = heat + (img * 3 + t) * hw;
-    float mn, mx;
-    block_minmax(h, hw, red, mn, mx);
-    const float denom = np_denominator(mn, mx);
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) s.in[i] = quantize_u8(__ldg(h + i), mn, denom);
-    __syncthreads();
-    pil_resize_smem(s.in, s.tmp, s.out + t * n_out, Hi, Wi, Ho, Wo, s.bx, s.kx, ksx, s.by, s.ky, ksy);
-  }
-  // planes (as generated, before inversion), then stack with inverted bg
-  if (planes) {
-    uint8_t* p = planes + img * 3 * n_out;
-    for (int i = threadIdx.x; i < 3 * n_out; i += blockDim.x) p[i] = s.out[i];
-  }
-  uint8_t* st = stack + img * 3 * n_out;
-  for (int i = threadIdx.x; i < 3 * n_out; i += blockDim.x) {
-    const int px = i / 3, c = i - px * 3;
-    const uint8_t v = s.out[c * n_out + px];
-    st[i] = (c == 2) ? static_cast<uint8_t>(255 - v) : v;
-  }
-  if (inv) {
-    uint8_t* iv = inv + img * n_out;
-    for (int i = threadIdx.x; i < n_out; i += blockDim.x) iv[i] = static_cast<uint8_t>(255 - s.out[2 * n_out + i]);
+  const int hw = Hi * Wi, n_out = Ho * Wo, hw4 = hw >> 2;
+  const int tid = threadIdx.x, T = kPostThreads;
+  const bool in_regs = (hw & 3) == 0 && hw4 <= 4 * T && (reinterpret_cast<uintptr_t>(heat) & 15) == 0;
+  const bool words_ok = (n_out & 3) == 0 && (reinterpret_cast<uintptr_t>(stack) & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(planes) & 3) == 0 && (reinterpret_cast<uintptr_t>(inv) & 3) == 0;
+  float4 nxt[4];
+  auto fetch = [&](long long m) {  // map m (= img * 3 + t) -> registers
+    const float4* h4 = reinterpret_cast<const float4*>(heat + m * hw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + j * T;
+      if (i < hw4) nxt[j] = __ldg(h4 + i);
+    }
+  };
+  if (in_regs && blockIdx.x < n) fetch(static_cast<long long>(blockIdx.x) * 3);
+  for (long long img = blockIdx.x; img < n; img += gridDim.x) {
+    for (int t = 0; t < 3; ++t) {
+      const float* h = heat + (img * 3 + t) * hw;
+      float mn, mx;
+      if (in_regs) {
+        float4 cur[4];
+        float lo = INFINITY, hi = -INFINITY;
+        bool nan = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cur[j] = nxt[j];
+          if (tid + j * T < hw4) {
+            const float4 v = cur[j];
+            lo = fminf(fminf(lo, v.x), fminf(v.y, fminf(v.z, v.w)));
+            hi = fmaxf(fmaxf(hi, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+            nan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+          }
+        }
+        // the next map of this CTA (next plane, or plane 0 of its next image): in flight during this map's resize
+        const long long m_next = (t < 2) ? img * 3 + t + 1 : (img + gridDim.x) * 3;
+        if (m_next < static_cast<long long>(n) * 3) fetch(m_next);
+        block_minmax_reduce(lo, hi, nan, red, mn, mx);
+        const float denom = np_denominator(mn, mx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = tid + j * T;
+          if (i < hw4) {
+            const float4 v = cur[j];
+            reinterpret_cast<uint32_t*>(s.in)[i] =
+                static_cast<uint32_t>(quantize_u8(v.x, mn, denom)) | (static_cast<uint32_t>(quantize_u8(v.y, mn, denom)) << 8) |
+                (static_cast<uint32_t>(quantize_u8(v.z, mn, denom)) << 16) | (static_cast<uint32_t>(quantize_u8(v.w, mn, denom)) << 24);
+          }
+        }
+      } else {
+        block_minmax(h, hw, red, mn, mx);
+        const float denom = np_denominator(mn, mx);
+        for (int i = tid; i < hw; i += T) s.in[i] = quantize_u8(__ldg(h + i), mn, denom);
+      }
+      __syncthreads();
+      pil_resize_smem(s.in, s.tmp, s.out + t * n_out, Hi, Wi, Ho, Wo, s.bx, s.kx, ksx, s.by, s.ky, ksy);
+    }
+    // planes (as generated, before inversion), then stack with inverted bg
+    if (words_ok) {
+      const int n4 = n_out >> 2;
+      const uint32_t* a4 = reinterpret_cast<const uint32_t*>(s.out);
+      const uint32_t *b4 = a4 + n4, *c4 = b4 + n4;
+      if (planes) {
+        uint32_t* p = reinterpret_cast<uint32_t*>(planes + img * 3 * n_out);
+        for (int i = tid; i < 3 * n4; i += T) p[i] = a4[i];
+      }
+      uint32_t* st = reinterpret_cast<uint32_t*>(stack + img * 3 * n_out);
+      uint32_t* iv = inv ? reinterpret_cast<uint32_t*>(inv + img * n_out) : nullptr;
+      for (int i = tid; i < n4; i += T) {
+        const uint32_t a = a4[i], b = b4[i], c = ~c4[i];  // 255 - x per byte
+        // bytes: a0 b0 c0 a1 | b1 c1 a2 b2 | c2 a3 b3 c3
+        st[3 * i + 0] = __byte_perm(__byte_perm(a, b, 0x0140), c, 0x3410) ;
+        st[3 * i + 1] = __byte_perm(__byte_perm(b, c, 0x0051), a, 0x6210) | (__byte_perm(b, 0u, 0x2444) & 0xff000000u);
+        st[3 * i + 2] = __byte_perm(__byte_perm(c, a, 0x0072), b, 0x3710) | (__byte_perm(c, 0u, 0x3444) & 0xff000000u);
+        if (iv) iv[i] = c;
+      }
+    } else {
+      if (planes) {
+        uint8_t* p = planes + img * 3 * n_out;
+        for (int i = tid; i < 3 * n_out; i += T) p[i] = s.out[i];
+      }
+      uint8_t* st = stack + img * 3 * n_out;
+      for (int i = tid; i < 3 * n_out; i += T) {
+        const int px = i / 3, c = i - px * 3;
+        const uint8_t v = s.out[c * n_out + px];
+        st[i] = (c == 2) ? static_cast<uint8_t>(255 - v) : v;
+      }
+      if (inv) {
+        uint8_t* iv = inv + img * n_out;
+        for (int i = tid; i < n_out; i += T) iv[i] = static_cast<uint8_t>(255 - s.out[2 * n_out + i]);
+      }
+    }
+    __syncthreads();  // s.out is rewritten by the next image
   }
 }
 

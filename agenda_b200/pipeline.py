@@ -132,6 +132,58 @@ class HeatmapPipeline:
         return host
 
     @torch.no_grad()
+    def run_host_batches(self, batches, staging: Optional[Dict] = None):
+        """A stream of host batches `(hs_host, ctx_host)` (pinned) in, one dict of pinned host records out per batch
+        (a generator; the record buffers are re-used, consume them before asking for the next).  Same work per batch as
+        `run_host`, but the H2D copy of batch i+1 runs on a copy stream into a second set of device buffers while batch
+        i computes; a device-to-device copy (tens of microseconds) then moves it into the buffers the captured CUDA graph
+        reads.  Only the first batch's upload is exposed — on a box with a slow host link `run_host` spends 15 % of
+        its time there."""
+        it = iter(batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        if staging is None:
+            staging = self.make_staging(*cur)
+        if "hs_next" not in staging:
+            staging["hs_next"] = {k: torch.empty_like(v) for k, v in staging["hs"].items()}
+            staging["ctx_next"] = torch.empty_like(staging["ctx"])
+            staging["copy_stream"] = torch.cuda.Stream(device=self.device)
+        main, side = torch.cuda.current_stream(self.device), staging["copy_stream"]
+        uploaded, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+        def upload(batch):
+            hs_host, ctx_host = batch
+            with torch.cuda.stream(side):
+                for k, v in hs_host.items():
+                    staging["hs_next"][k].copy_(v, non_blocking=True)
+                staging["ctx_next"].copy_(ctx_host, non_blocking=True)
+                uploaded.record(side)
+
+        side.wait_stream(main)
+        upload(cur)
+        while cur is not None:
+            main.wait_event(uploaded)
+            for k, v in staging["hs_next"].items():
+                staging["hs"][k].copy_(v, non_blocking=True)
+            staging["ctx"].copy_(staging["ctx_next"], non_blocking=True)
+            consumed.record(main)
+            nxt = next(it, None)
+            if nxt is not None:
+                side.wait_event(consumed)
+                upload(nxt)
+            out = self.run_device(staging["hs"], staging["ctx"])
+            self.last_device_out = out
+            host = staging["out"]
+            for name in ("stack", "inv", "planes", "counts", "boxes", "heat"):
+                if name not in host:
+                    host[name] = torch.empty(out[name].shape, dtype=out[name].dtype).pin_memory()
+                host[name].copy_(out[name], non_blocking=True)
+            main.synchronize()
+            yield host
+            cur = nxt
+
+    @torch.no_grad()
     def run_seeds(self, seeds: Sequence[int], batch_size: int = 8, staging: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
         """The sharded-generation loop of one rank (data_generation.py:56-59 over this rank's seeds): batches of
         `batch_size` images, inputs drawn on the device from each image's own seed, persistent staging buffers (one CUDA

@@ -160,6 +160,23 @@ def test_pipeline_host_api_equals_device_api(cuda_ok):
     assert pipe.h2d_bytes(hs_h, ctx_h) > 0 and pipe.d2h_bytes(host) > 0
 
 
+def test_pipeline_host_batches_prefetch_equals_one_by_one(cuda_ok):
+    """run_host_batches overlaps the next batch's upload with the current batch's compute; records must equal run_host's."""
+    from agenda_b200.pipeline import HeatmapPipeline
+    pipe = HeatmapPipeline(_small_blocks(), 768, tokens=[1, 2, 3], num_steps=2, latent_hw=16, use_cuda_graph=True)
+    batches = [pipe.make_inputs(2, seed=s, pinned_host=True) for s in (1, 5, 9)]
+    want = [{k: v.clone() for k, v in pipe.run_host(hs, ctx).items()} for hs, ctx in batches]
+    staging = pipe.make_staging(*batches[0])
+    n = 0
+    for host, ref in zip(pipe.run_host_batches(iter(batches), staging), want):
+        for k in ("heat", "stack", "inv", "counts", "boxes"):
+            assert torch.equal(host[k], ref[k]), (n, k)
+        n += 1
+    assert n == 3
+    assert not torch.equal(want[0]["heat"], want[1]["heat"])
+    assert list(pipe.run_host_batches(iter([]), staging)) == []
+
+
 def test_pipeline_graph_replay_follows_in_place_input_updates(cuda_ok):
     """The captured graph reads the cached prompt K/V: overwriting the prompt embedding (and hidden states) in place
     between runs must be picked up (refresh_context_kv), exactly as an eager run on fresh tensors would."""
