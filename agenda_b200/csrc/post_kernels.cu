@@ -2,6 +2,8 @@
 // and invert + channel stack (data_generation/postprocess_heatmap.py:44-46).  Byte/integer results are
 // bit-exact with numpy + PIL.  One CTA per image; everything between the fp32 read and the u8 write lives in
 // shared memory, so HBM traffic is the algorithmic minimum (read Hi*Wi*4 per map, write Ho*Wo per plane).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace agenda {
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(256) stack_kernel(const uint8_t* __restrict__ 
 // instead of once per image; a map small enough (<= 16 floats per thread) is read from HBM exactly once, into registers
 // — min / max and the u8 quantisation both work from there — and the NEXT map's loads are issued before the current
 // map's resize, so their latency hides behind the integer filter.  Outputs leave as 32-bit words.
-__global__ void __launch_bounds__(kPostThreads) postprocess_stack_kernel(const float* __restrict__ heat,
+__global__ void __launch_bounds__(kPostThreads, 4) postprocess_stack_kernel(const float* __restrict__ heat,
                                                                         uint8_t* __restrict__ planes,
                                                                         uint8_t* __restrict__ stack,
                                                                         uint8_t* __restrict__ inv, int n, int Hi, int Wi,
@@ -380,9 +382,9 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_stack_kernel(const f
       for (int i = tid; i < n4; i += T) {
         const uint32_t a = a4[i], b = b4[i], c = ~c4[i];  // 255 - x per byte
         // bytes: a0 b0 c0 a1 | b1 c1 a2 b2 | c2 a3 b3 c3
-        st[3 * i + 0] = __byte_perm(__byte_perm(a, b, 0x0140), c, 0x3410) ;
-        st[3 * i + 1] = __byte_perm(__byte_perm(b, c, 0x0051), a, 0x6210) | (__byte_perm(b, 0u, 0x2444) & 0xff000000u);
-        st[3 * i + 2] = __byte_perm(__byte_perm(c, a, 0x0072), b, 0x3710) | (__byte_perm(c, 0u, 0x3444) & 0xff000000u);
+        st[3 * i + 0] = __byte_perm(__byte_perm(a, b, 0x1040), c, 0x3410);
+        st[3 * i + 1] = __byte_perm(__byte_perm(a, b, 0x6205), c, 0x3250);
+        st[3 * i + 2] = __byte_perm(__byte_perm(a, b, 0x0730), c, 0x7216);
         if (iv) iv[i] = c;
       }
     } else {
@@ -483,8 +485,11 @@ extern "C" int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes,
   if (rc != AGENDA_OK) return rc;
   if (n == 0) return AGENDA_OK;
   AGENDA_DYN_SMEM(postprocess_stack_kernel, smem);
-  postprocess_stack_kernel<<<n, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(heat, planes, stack, inv, Hi,
-                                                                                        Wi, Ho, Wo);
+  // persistent CTAs: as many as fit the GPU at once (shared memory / 2048 threads per SM), each walking n / grid images
+  const int per_sm = std::max(1, std::min(2048 / kPostThreads, static_cast<int>((220 * 1024) / (smem + 1024))));
+  const int grid = std::min(n, num_sms() * per_sm);
+  postprocess_stack_kernel<<<grid, kPostThreads, smem, static_cast<cudaStream_t>(stream)>>>(heat, planes, stack, inv, n,
+                                                                                           Hi, Wi, Ho, Wo);
   AGENDA_LAUNCH_CHECK("postprocess_stack_kernel");
   return AGENDA_OK;
 }

@@ -146,7 +146,7 @@ def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
 # None = not captured for that shape
 NCU_TRAFFIC = {
     "heat_upsample_accum_32to64": 669.5e6,      # r02_heat_upsample_full_key_metrics.txt: 403.7 MB read + 265.8 MB written
-    "heat_postprocess_stack_64to112": 1069.3e6,  # r02_postprocess_stack_full_key_metrics.txt: 402.8 MB + 666.5 MB
+    "heat_postprocess_stack_64to112": 1067.7e6,  # r02b_postprocess_stack_persistent_full_key_metrics.txt: 402.8 MB + 664.9 MB
     "cross_attention_backward": 11.2e6,          # r02_cross_bwd_full_key_metrics.txt (the operands stay in L2)
 }
 
@@ -201,8 +201,10 @@ def probe_hbm_kernels(dev, hbm_gbs):
     out["heat_postprocess_stack_64to112"] = {"kernel": "postprocess_stack_kernel", "bound": "hbm", "achieved": by / ms / 1e6,
                                              "peak": hbm_gbs, "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms,
                                              "images": n_img, "traffic": NCU_TRAFFIC.get("heat_postprocess_stack_64to112"),
-                                             "note": "algorithmic bytes per image = 3*L*L*4 read + S*S*(3+3+1) written; bound "
-                                                     "by PIL's exact two-pass 8-bit fixed-point filter arithmetic, not by HBM"}
+                                             "note": "algorithmic bytes per image = 3*L*L*4 read + S*S*(3+3+1) written; persistent CTAs "
+                                                     "(coefficient tables once per CTA), maps held in registers, five-tap column-"
+                                                     "owner passes; still bound by PIL's exact 8-bit fixed-point filter arithmetic "
+                                                     "(issue slots 70 % busy), not by HBM"}
     del heat
     # K7: cross-attention backward at the 64x64 layer shape of one training sample pair (B = 2)
     B, N, H, d, T = 2, 4096, 8, 40, 3
@@ -532,10 +534,12 @@ def run_ours(args):
                                            "ms_per_denoise_step": ms_all / 5.0},
              "ccl_bbox_512": {"bound": "hbm", "achieved": ccl_gbs, "peak": hbm_gbs, "unit": "GB/s",
                               "frac": ccl_gbs / hbm_gbs, "maps": n_maps, "ms": ccl_ms,
-                              "traffic": 2.79e6,
+                              "traffic": 2.144e6,
                               "note": "BASELINE configs[4] generator (Gaussian blobs + noise floor), 64 distinct maps "
                                       "tiled, labels + boxes written; algorithmic bytes = H*W*(4 read + 4 written) per map; "
-                                      "traffic = ncu dram bytes per map (the two-pass one-CTA kernel re-reads the map)"}}
+                                      "traffic = ncu dram bytes per map (profiles/r02b_ccl_bbox_cta_range_table_full_key_metrics.txt: "
+                                      "a per-word range table lets the second pass re-read only the ~3 % of words that "
+                                      "straddle the threshold)"}}
 
     # cross-attention + heat epilogue (K2, HBM-bound): the same eager replay, in-pipeline cache state (Q was just
     # written by the to_q GEMM).  The shipped path is the split-precision kernel (fp32 Q in, bf16 O out):
