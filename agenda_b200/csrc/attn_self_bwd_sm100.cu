@@ -21,7 +21,16 @@
 // one accumulator per kernel (TMEM: T1 128 + T2 128 + G 64 + accumulator <= 160 columns), no atomics and no dQ
 // round trips through global memory.
 //
-// Warps: 0-3 row threads (thread == row of the tile == TMEM lane), 4 TMA producer, 5 TMEM allocator + MMA issuer.
+// Warps: 0-3 and 4-7 row warpgroups (thread == row of the tile == TMEM lane; warpgroup hf owns the 64-column half hf of
+// the score tile, i.e. streamed rows hf*64 .. hf*64+63), 8 TMA producer, 9 TMEM allocator + MMA issuer.
+//
+// Pipeline (second version; the first one ran MMA -> 128 row threads -> MMA strictly in turn, 0.088 of the bf16 peak):
+//   * the score tiles T1 / T2 are produced as two N = 64 halves with their own full / free barriers, so a warpgroup starts
+//     on its half as soon as it exists and hands it back as soon as its last tcgen05.ld has landed;
+//   * the issuer puts the T halves of tile it+1 on the tensor pipe BEFORE the accumulating MMAs of tile it (they only
+//     need the half to be free and the next streamed tile to be resident), so the next scores are computed while the
+//     row warpgroups are still exponentiating tile it; G is double buffered where TMEM has room (head dim <= 128);
+//   * two row warps per SM sub-partition instead of one halve the issue-bound exponential / pack phase.
 #include <cstdlib>
 
 #include "sm100_common.cuh"
@@ -29,7 +38,7 @@
 namespace agenda {
 namespace sm100 {
 
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;
 constexpr int kBwdLSE = 0, kBwdDQ = 1, kBwdDK = 2, kBwdDV = 3;
 
 template <int D>
@@ -38,15 +47,18 @@ struct BCfg {
   static constexpr int kChunks = (D + 63) / 64;
   static constexpr int kTileBytes = kChunks * 128 * 128;   // 128 rows, 64-column swizzle chunks
   static constexpr int kStages = (kChunks <= 2) ? 2 : 1;
-  static constexpr int kColT1 = 0, kColT2 = 128, kColG = 256, kColAcc = 320;
+  static constexpr int kNG = (kDP <= 128) ? 2 : 1;          // G buffers (64 columns each)
+  static constexpr int kColT1 = 0, kColT2 = 128, kColG = 256, kColAcc = 256 + 64 * kNG;
   static_assert(kColAcc + kDP <= 512, "TMEM overflow");
 };
 
 struct BBarriers {
-  float vec[2][128];   // DK / DV: lse2 / Delta of the streamed query tile (column vectors)
+  float vec[2][2][2][64];   // DK / DV: [warpgroup][tile parity][lse2 | Delta][its 64 streamed queries]; LSE: (m, l) exchange
   uint64_t fixed_full;
   uint64_t st_full[2], st_empty[2];
-  uint64_t t_full, t_free, g_full, g_done;
+  uint64_t t_full[2], t_free[2];      // per half
+  uint64_t g_full[2][2];              // [half][G buffer]
+  uint64_t g_done[2];                 // [G buffer]
   uint32_t tmem_base;
 };
 
@@ -67,6 +79,8 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
   constexpr bool kAcc = (MODE != kBwdLSE);
   constexpr bool kColVec = (MODE == kBwdDK || MODE == kBwdDV);  // lse2 / Delta indexed by the streamed (query) tile
   constexpr int ST = C::kStages;
+  constexpr int NG = C::kNG;
+  constexpr bool kEarlyT = (ST >= 2);   // T(it+1) ahead of acc(it) needs tile it+1 resident while tile it is still read
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sR1 = smem;
@@ -81,17 +95,20 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
   const int r0 = rt * 128;
   const float c_log2 = scale * 1.4426950408889634f;
 
-  if (tid == 4 * 32) {
+  if (tid == 8 * 32) {
     tma_prefetch_desc(&map_r1); tma_prefetch_desc(&map_c1);
     if (kT2) tma_prefetch_desc(&map_r2);
     if (MODE != kBwdLSE) tma_prefetch_desc(&map_c2);
     mbar_init(&bars->fixed_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->st_full[s], 1); mbar_init(&bars->st_empty[s], 1); }
-    mbar_init(&bars->t_full, 1); mbar_init(&bars->t_free, 128);
-    mbar_init(&bars->g_full, 128); mbar_init(&bars->g_done, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->st_full[s], 1); mbar_init(&bars->st_empty[s], 1);
+      mbar_init(&bars->t_full[s], 1); mbar_init(&bars->t_free[s], 128);
+      mbar_init(&bars->g_full[s][0], 128); mbar_init(&bars->g_full[s][1], 128);
+      mbar_init(&bars->g_done[s], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -101,7 +118,7 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
   constexpr bool kAccFromC2 = (MODE == kBwdDV);
   constexpr bool kLoadC2 = kT2 || kAccFromC2;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== TMA producer ==============================
     if (elect_one()) {
       mbar_expect_tx(&bars->fixed_full, (kT2 ? 2 : 1) * C::kTileBytes);
@@ -127,106 +144,132 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
       __syncwarp();
       if (++s == ST) { s = 0; ph ^= 1u; }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================== MMA issuer ==============================
-    constexpr uint32_t idesc_t = make_idesc(128, 128, 0);
+    constexpr uint32_t idesc_t = make_idesc(128, 64, 0);
     constexpr uint32_t idesc_acc = make_idesc(128, C::kDP, 1);
     const uint64_t r1_desc = make_sdesc(smem_u32(sR1), 16, 1024);
     const uint64_t r2_desc = make_sdesc(smem_u32(sR2), 16, 1024);
     const uint64_t c_desc = make_sdesc(smem_u32(sC), 16, 1024);
     const uint64_t cacc_desc = make_sdesc(smem_u32(sC), 128 * 128, 1024);   // MN-major view: LBO = chunk stride
-    mbar_wait(&bars->fixed_full, 0);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < n_tiles; ++it) {
-      mbar_wait(&bars->st_full[s], ph);
-      if (it > 0) mbar_wait(&bars->t_free, (it - 1) & 1);   // T1 / T2 of the previous tile are in registers
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t c1_off = (2 * s) * C::kTileBytes, c2_off = c1_off + C::kTileBytes;
+    // both halves of the score tile(s) of streamed tile `it`: waits for the stage and for each half to be free
+    auto issue_T = [&](int it) {
+      const int s = it % ST;
+      mbar_wait(&bars->st_full[s], static_cast<uint32_t>(it / ST) & 1u);
+      const uint32_t c1_off = (2 * s) * C::kTileBytes, c2_off = c1_off + C::kTileBytes;
 #pragma unroll
-        for (int kk = 0; kk < C::kDP / 16; ++kk) {
-          const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
-          umma_ss(tmem + C::kColT1, r1_desc + static_cast<uint64_t>(ko >> 4), c_desc + static_cast<uint64_t>((c1_off + ko) >> 4),
-                  idesc_t, kk != 0);
-        }
-        if (kT2) {
+      for (int hf = 0; hf < 2; ++hf) {
+        if (it > 0) mbar_wait(&bars->t_free[hf], static_cast<uint32_t>(it - 1) & 1u);   // the half is in registers
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t row_off = hf * 64 * 128;   // streamed rows hf*64.. inside every 64-column chunk
 #pragma unroll
           for (int kk = 0; kk < C::kDP / 16; ++kk) {
             const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
-            umma_ss(tmem + C::kColT2, r2_desc + static_cast<uint64_t>(ko >> 4), c_desc + static_cast<uint64_t>((c2_off + ko) >> 4),
-                    idesc_t, kk != 0);
+            umma_ss(tmem + C::kColT1 + hf * 64, r1_desc + static_cast<uint64_t>(ko >> 4),
+                    c_desc + static_cast<uint64_t>((c1_off + ko + row_off) >> 4), idesc_t, kk != 0);
           }
-        }
-        umma_commit(&bars->t_full);
-        if (!kAcc) umma_commit(&bars->st_empty[s]);
-      }
-      __syncwarp();
-      if (kAcc) {
-        mbar_wait(&bars->g_full, it & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t acc_off = (2 * s + (kAccFromC2 ? 1 : 0)) * C::kTileBytes;
+          if (kT2) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // contraction over the 128 rows of the streamed tile, 16 per MMA
-            umma_ts(tmem + C::kColAcc, tmem + C::kColG + kk * 8, cacc_desc + static_cast<uint64_t>((acc_off + kk * 2048) >> 4),
-                    idesc_acc, !(it == 0 && kk == 0));
-          umma_commit(&bars->g_done);
-          umma_commit(&bars->st_empty[s]);
+            for (int kk = 0; kk < C::kDP / 16; ++kk) {
+              const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
+              umma_ss(tmem + C::kColT2 + hf * 64, r2_desc + static_cast<uint64_t>(ko >> 4),
+                      c_desc + static_cast<uint64_t>((c2_off + ko + row_off) >> 4), idesc_t, kk != 0);
+            }
+          }
+          umma_commit(&bars->t_full[hf]);
+          if (!kAcc && hf == 1) umma_commit(&bars->st_empty[s]);
         }
         __syncwarp();
       }
-      if (++s == ST) { s = 0; ph ^= 1u; }
+    };
+    mbar_wait(&bars->fixed_full, 0);
+    if (kEarlyT) issue_T(0);
+    for (int it = 0; it < n_tiles; ++it) {
+      if (kEarlyT) { if (it + 1 < n_tiles) issue_T(it + 1); }
+      else issue_T(it);
+      if (kAcc) {
+        const int s = it % ST, buf = it % NG;
+        const uint32_t gph = static_cast<uint32_t>(it / NG) & 1u;
+        const uint32_t acc_off = (2 * s + (kAccFromC2 ? 1 : 0)) * C::kTileBytes;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&bars->g_full[hf][buf], gph);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {   // contraction over the half's 64 streamed rows, 16 per MMA
+              const int kk = hf * 4 + k4;
+              umma_ts(tmem + C::kColAcc, tmem + C::kColG + buf * 64 + kk * 8,
+                      cacc_desc + static_cast<uint64_t>((acc_off + kk * 2048) >> 4), idesc_acc, !(it == 0 && kk == 0));
+            }
+            if (hf == 1) { umma_commit(&bars->g_done[buf]); umma_commit(&bars->st_empty[s]); }
+          }
+          __syncwarp();
+        }
+      }
     }
   } else {
-    // ============================== row threads (thread == row of this CTA's tile) ==============================
-    const int row = tid;
+    // ============================== row warpgroups (thread == row of this CTA's tile) ==============================
+    const int hf = warp >> 2;          // column half of the score tile this warpgroup owns
+    const int row = tid & 127;
     const int n_row = r0 + row;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const long long vec_base = static_cast<long long>(bh) * N;
+    // DK / DV: this thread's element of the streamed tile's lse2 (rows 0-63 of the warpgroup) or Delta (rows 64-127) is
+    // fetched one tile ahead into a register, so its global-load latency hides behind the current tile
+    auto fetch_vec = [&](int it) -> float {
+      const int qn = it * 128 + hf * 64 + (row & 63);
+      if (it >= n_tiles) return 0.f;
+      if (row < 64) return (qn < N) ? lse2[vec_base + qn] : INFINITY;   // out-of-range queries: lse2 = +inf, i.e. E = 0
+      return (kT2 && qn < N) ? delta[vec_base + qn] : 0.f;
+    };
+    float vec_next = kColVec ? fetch_vec(0) : 0.f;
     float lse_r = 0.f, delta_r = 0.f;
     if (!kColVec && MODE != kBwdLSE) {
       lse_r = (n_row < N) ? lse2[vec_base + n_row] : 0.f;
       if (kT2) delta_r = (n_row < N) ? delta[vec_base + n_row] : 0.f;
     }
-    float m_run = -INFINITY, l_run = 0.f;   // LSE mode
+    float m_run = -INFINITY, l_run = 0.f;   // LSE mode (over this warpgroup's columns)
     for (int it = 0; it < n_tiles; ++it) {
-      const int c0 = it * 128;   // first row of the streamed tile == first column of T1 / T2
+      const int c0 = it * 128 + hf * 64;   // first streamed row == first score column of this warpgroup's half
+      const int buf = it % NG;
+      const float* vl = bars->vec[hf][it & 1][0];
+      const float* vd = bars->vec[hf][it & 1][1];
       if (kColVec) {
-        // lse2 / Delta of the streamed query tile: one element per thread into shared memory, read back as broadcasts.
-        // Out-of-range queries get lse2 = +inf, i.e. E = 0.
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers are done
-        bars->vec[0][row] = (c0 + row < N) ? lse2[vec_base + c0 + row] : INFINITY;
-        if (kT2) bars->vec[1][row] = (c0 + row < N) ? delta[vec_base + c0 + row] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // park the prefetched element in this tile's buffer (double buffered: the writers of tile it+1 passed this
+        // barrier, so every reader of tile it-1 — same buffer — had finished), read back as broadcasts
+        bars->vec[hf][it & 1][row >> 6][row & 63] = vec_next;
+        vec_next = fetch_vec(it + 1);
+        if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
-      mbar_wait(&bars->t_full, it & 1);
+      mbar_wait(&bars->t_full[hf], static_cast<uint32_t>(it) & 1u);
       tc_fence_after();
-      if (kAcc && it > 0) {   // the accumulating MMA of the previous tile has finished reading G
-        mbar_wait(&bars->g_done, (it - 1) & 1);
-        tc_fence_after();
-      }
-      float tile_max = -INFINITY;
       if (MODE == kBwdLSE) {
-        // pass A over the 128 columns: the tile's row maximum (columns beyond N masked)
+        // pass A over the half's 64 columns: the tile's row maximum (columns beyond N masked)
+        float tile_max = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float t1[32];
-          tmem_ld32(tmem + lane_base + C::kColT1 + c * 32, t1);
+          tmem_ld32(tmem + lane_base + C::kColT1 + hf * 64 + c * 32, t1);
           tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) tile_max = fmaxf(tile_max, (c0 + c * 32 + i < N) ? t1[i] : -INFINITY);
         }
         const float m_new = fmaxf(m_run, tile_max * c_log2);
-        l_run *= ex2(m_run - m_new);   // (first tile: 2^-inf = 0)
+        l_run = (m_new == -INFINITY) ? 0.f : l_run * ex2(m_run - m_new);   // (first tile: 2^-inf = 0)
         m_run = m_new;
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float t1[32], t2[32];
-        tmem_ld32(tmem + lane_base + C::kColT1 + c * 32, t1);
-        if (kT2) tmem_ld32(tmem + lane_base + C::kColT2 + c * 32, t2);
+        tmem_ld32(tmem + lane_base + C::kColT1 + hf * 64 + c * 32, t1);
+        if (kT2) tmem_ld32(tmem + lane_base + C::kColT2 + hf * 64 + c * 32, t2);
         tmem_wait_ld();
+        if (c == 1) {   // this half of T1 / T2 is in registers: the next tile's scores may overwrite it
+          tc_fence_before();
+          mbar_arrive(&bars->t_free[hf]);
+        }
         if (MODE == kBwdLSE) {
           float sum = 0.f;
 #pragma unroll
@@ -239,9 +282,9 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
             float g[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const int col = c * 32 + i + e;
+              const int col = c * 32 + i + e;   // within the half
               float lse_x, delta_x;
-              if (kColVec) { lse_x = bars->vec[0][col]; delta_x = kT2 ? bars->vec[1][col] : 0.f; }
+              if (kColVec) { lse_x = vl[col]; delta_x = kT2 ? vd[col] : 0.f; }
               else { lse_x = lse_r; delta_x = delta_r; }
               float p = ex2(fmaf(t1[i + e], c_log2, -lse_x));
               if (!kColVec && c0 + col >= N) p = 0.f;   // keys beyond the sequence (DQ); DK / DV: lse2 = +inf did it
@@ -249,26 +292,40 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
             }
             u[i >> 1] = pack_bf16(g[0], g[1]);
           }
-          tmem_st16(tmem + lane_base + C::kColG + c * 16, u);
+          if (c == 0 && it >= NG) {   // the accumulating MMAs that read this G buffer last (tile it - NG) are done
+            mbar_wait(&bars->g_done[buf], static_cast<uint32_t>(it / NG - 1) & 1u);
+            tc_fence_after();
+          }
+          tmem_st16(tmem + lane_base + C::kColG + buf * 64 + hf * 32 + c * 16, u);
         }
       }
-      tc_fence_before();
-      mbar_arrive(&bars->t_free);   // T1 / T2 may be overwritten
       if (kAcc) {
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->g_full);
+        mbar_arrive(&bars->g_full[hf][buf]);
       }
     }
     // ---- epilogue ----
     if (MODE == kBwdLSE) {
-      if (n_row < N) lse2[vec_base + n_row] = m_run + log2f(l_run);
+      // combine the two halves' (m, l): warpgroup 1 parks its pair in shared memory (the vec area is idle in this mode)
+      float* ex_m = &bars->vec[0][0][0][0];
+      float* ex_l = ex_m + 128;
+      if (hf == 1) { ex_m[row] = m_run; ex_l[row] = l_run; }
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      if (hf == 0 && n_row < N) {
+        const float m1 = ex_m[row], l1 = ex_l[row];
+        const float m = fmaxf(m_run, m1);
+        const float l = ((m_run == -INFINITY) ? 0.f : l_run * ex2(m_run - m)) + ((m1 == -INFINITY) ? 0.f : l1 * ex2(m1 - m));
+        lse2[vec_base + n_row] = m + log2f(l);
+      }
     } else {
-      mbar_wait(&bars->g_done, (n_tiles - 1) & 1);
+      const int last = n_tiles - 1;
+      mbar_wait(&bars->g_done[last % NG], static_cast<uint32_t>(last / NG) & 1u);
       tc_fence_after();
       __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
 #pragma unroll
       for (int c = 0; c < C::kDP / 16; ++c) {
+        if ((c & 1) != hf) continue;   // the two warpgroups take alternate 16-column chunks of the accumulator
         float o[16];
         tmem_ld16(tmem + lane_base + C::kColAcc + c * 16, o);
         tmem_wait_ld();
@@ -284,7 +341,7 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

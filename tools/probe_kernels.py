@@ -1,5 +1,5 @@
 """A few launches of one HBM-bound kernel at bench.py's probe shape (for ncu).
-usage: python tools/probe_kernels.py upsample|postprocess|cross_bwd|ccl"""
+usage: python tools/probe_kernels.py upsample|postprocess|cross_bwd|self_bwd|ccl"""
 import os
 import sys
 
@@ -28,6 +28,12 @@ elif which == "cross_bwd":
     gm = torch.randn(B, T, N, device=dev)
     for _ in range(3):
         ops.attn_cross_bwd(q, k, v, go, gm, H, [5, 6, 7], 0)
+elif which == "self_bwd":
+    B, N, H, d = 2, 4096, 8, 40
+    q, k, v, go = (torch.randn(B, N, H * d, device=dev).bfloat16() for _ in range(4))
+    out = ops.attn_self(q, k, v, H)
+    for _ in range(3):
+        ops.attn_self_bwd(q, k, v, out, go, H)
 elif which == "ccl":
     from agenda_b200.synthetic import synthetic_heatmaps
     base = torch.from_numpy(synthetic_heatmaps(64, 512, seed=0)).to(dev)
