@@ -58,10 +58,14 @@ _SIGNATURES = {
     "agenda_stack_heatmaps_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "agenda_heat_postprocess_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p],
+    "agenda_groupnorm_nhwc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
+                              c_void_p],
+    "agenda_geglu": [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p],
+    "agenda_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_void_p],
     "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 EXPORTS = (["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes",
-            "agenda_attn_self_bwd_workspace_bytes"] + list(_SIGNATURES))
+            "agenda_attn_self_bwd_workspace_bytes", "agenda_groupnorm_workspace_bytes"] + list(_SIGNATURES))
 
 _lib = None
 
@@ -86,6 +90,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_context_blob_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_attn_self_bwd_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_attn_self_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.agenda_groupnorm_workspace_bytes.restype = ctypes.c_longlong
+    lib.agenda_groupnorm_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, argtypes in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

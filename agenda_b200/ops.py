@@ -468,6 +468,68 @@ def heat_postprocess_stack(heat: torch.Tensor, size):
     return planes, stack, inv
 
 
+def groupnorm_nhwc_supported(x: torch.Tensor, groups: int) -> bool:
+    """A bf16 CUDA tensor [B,C,H,W] in channels-last memory (or [B,HW,C] contiguous) the NHWC GroupNorm kernel takes."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() in (3, 4)):
+        return False
+    C = x.shape[1] if x.dim() == 4 else x.shape[2]
+    if C % 8 or C % groups or groups > 64:
+        return False
+    return x.permute(0, 2, 3, 1).is_contiguous() if x.dim() == 4 else x.is_contiguous()
+
+
+@_on_tensor_device
+def groupnorm_nhwc(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], groups: int,
+                   eps: float = 1e-5, silu: bool = False) -> torch.Tensor:
+    """torch.nn.GroupNorm (+ SiLU) on a channels-last bf16 tensor without leaving the channels-last layout
+    (agenda_groupnorm_nhwc).  x [B,C,H,W] channels-last -> same shape / strides; x [B,HW,C] -> [B,HW,C]."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError("agenda_b200: `x` must be a CUDA tensor (no CPU fallback exists)")
+    if not groupnorm_nhwc_supported(x, groups):   # (no .contiguous() here: that would turn channels-last into NCHW)
+        raise ValueError("groupnorm_nhwc: need a channels-last bf16 tensor with C % 8 == 0 and C % groups == 0")
+    if x.dim() == 4:
+        B, C, H, W = x.shape
+        HW = H * W
+        y = torch.empty_like(x)            # preserves the channels-last strides
+    else:
+        B, HW, C = x.shape
+        y = torch.empty_like(x)
+    ws = torch.empty(_lib.load().agenda_groupnorm_workspace_bytes(B, HW, C, groups) // 4, dtype=torch.float32, device=x.device)
+    w = None if weight is None else _dev(weight, "weight", torch.bfloat16).contiguous()
+    b = None if bias is None else _dev(bias, "bias", torch.bfloat16).contiguous()
+    _lib.call("agenda_groupnorm_nhwc", x.data_ptr(), 0 if w is None else w.data_ptr(), 0 if b is None else b.data_ptr(),
+              y.data_ptr(), ws.data_ptr(), B, HW, C, groups, float(eps), 1 if silu else 0, _stream())
+    return y
+
+
+@_on_tensor_device
+def layernorm(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    """torch.nn.LayerNorm over the last dim of a bf16 tensor (agenda_layernorm): one warp per row, fp32 statistics."""
+    x = _dev(x, "x", torch.bfloat16)
+    C = x.shape[-1]
+    if C % 8:
+        raise ValueError("layernorm: last dim must be a multiple of 8")
+    y = torch.empty_like(x)
+    w = None if weight is None else _dev(weight, "weight", torch.bfloat16)
+    b = None if bias is None else _dev(bias, "bias", torch.bfloat16)
+    _lib.call("agenda_layernorm", x.data_ptr(), 0 if w is None else w.data_ptr(), 0 if b is None else b.data_ptr(),
+              y.data_ptr(), x.numel() // C, C, float(eps), _stream())
+    return y
+
+
+@_on_tensor_device
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    """x [..., 2*inner] = [a | gate] (bf16) -> a * gelu(gate) [..., inner] (agenda_geglu; diffusers GEGLU.forward after
+    its projection)."""
+    x = _dev(x, "x", torch.bfloat16).contiguous()
+    inner = x.shape[-1] // 2
+    if x.shape[-1] % 16:
+        raise ValueError("geglu: last dim must be a multiple of 16")
+    y = torch.empty(x.shape[:-1] + (inner,), dtype=x.dtype, device=x.device)
+    _lib.call("agenda_geglu", x.data_ptr(), y.data_ptr(), x.numel() // x.shape[-1], inner, _stream())
+    return y
+
+
 @_on_tensor_device
 def ccl_bbox(heat: torch.Tensor, thr: float = 0.5, max_boxes: int = 256, want_labels: bool = True):
     """Threshold + 4-connected components + boxes.  heat fp32 [n,H,W] ->

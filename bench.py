@@ -246,7 +246,8 @@ def full_unet_step(dev, n_img, reps=2):
             "images_per_step": n_img, "denoise_steps": NUM_DENOISE_STEPS, "boxes_found": int(out["counts"].sum().item()),
             "note": "SD-1.x UNet skeleton (random init, 859.5 M parameters, bf16) at UNet batch %d with CFG 7.5 + DDIM; the "
                     "hidden states that reach the 32 attention calls are produced by the real dataflow and change every "
-                    "step; convolutions / linears / norms are library kernels (cuDNN / cuBLAS)" % (2 * n_img)}
+                    "step; convolutions / linears are library kernels (cuDNN / cuBLAS); GroupNorm(+SiLU), LayerNorm and GEGLU are "
+                    "hand-written channels-last kernels (agenda_groupnorm_nhwc / agenda_layernorm / agenda_geglu)" % (2 * n_img)}
 
 
 def run_reference(args):

@@ -215,6 +215,25 @@ int agenda_stack_heatmaps_u8(const uint8_t* obj, const uint8_t* fg, const uint8_
 int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes, uint8_t* stack, uint8_t* inv, int n,
                                   int Hi, int Wi, int Ho, int Wo, void* stream);
 
+/* ---- N4: element-wise glue of the rest of the denoising step (data_generation/data_generation.py:59 runs a diffusers
+ * UNet2DConditionModel around the attention processor; SURVEY.md §8 f N4).  bf16, channels-last. -----------------------
+ * agenda_groupnorm_nhwc: torch.nn.GroupNorm(G, C, eps) on x [B, HW, C] (a channels-last [B,C,H,W] tensor's memory),
+ * statistics in fp32 over each (batch, group) = HW * C/G values, biased variance, y = (x - mean) * rstd * gamma + beta,
+ * optionally followed by SiLU (diffusers ResnetBlock2D: conv(silu(norm(x)))); y [B, HW, C] bf16.  gamma / beta bf16 [C]
+ * (NULL: 1 / 0).  workspace: agenda_groupnorm_workspace_bytes(B, HW, C, G) bytes (per-slab partial sums; no atomics, so
+ * results are bit-reproducible).  C % 8 == 0, C % G == 0, G <= 64; x, y, workspace 16-byte aligned.
+ * agenda_geglu: diffusers GEGLU after its projection: x [M, 2*inner] = [a | gate] -> y [M, inner] = a * gelu(gate)
+ * (erf form), fp32 arithmetic, one rounding to bf16.  inner % 8 == 0. */
+long long agenda_groupnorm_workspace_bytes(int B, int HW, int C, int G);
+int agenda_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* y, void* workspace, int B, int HW,
+                          int C, int G, float eps, int silu, void* stream);
+int agenda_geglu(const void* x, void* y, long long M, int inner, void* stream);
+/* torch.nn.LayerNorm(C, eps) over the last dim of x [M, C] bf16 (the three norms of diffusers' BasicTransformerBlock):
+ * mean and centred variance in fp32, y = (x - mean) * rstd * gamma + beta, one rounding to bf16.  gamma / beta bf16 [C]
+ * (NULL: 1 / 0).  C % 8 == 0; pointers 16-byte aligned. */
+int agenda_layernorm(const void* x, const void* gamma, const void* beta, void* y, long long M, int C, float eps,
+                     void* stream);
+
 /* ---- a9: threshold / connected components / bbox (NOT in the reference; spec SURVEY.md §8 a9) ------------
  * Per map: nrm=(h-min)/((max-min)+1e-8f) fp32; mask = nrm > thr; 4-connectivity; labels 1..K in raster order
  * of each component's first pixel (scipy.ndimage.label numbering); boxes[k] = {x, y, w, h, area}.

@@ -100,3 +100,57 @@ def test_unet_cross_attention_calls_match_fp32_reference(cuda_ok):
     err = float(np.abs(out["heat"].cpu().numpy() - ref_heat).max())
     print(f"unet per-call heat err {worst:.2e}, aggregated {err:.2e}")
     assert err < TOL_HEAT
+
+
+@pytest.mark.parametrize("B,C,H,W,silu", [(2, 320, 64, 64, True), (2, 2560, 8, 8, True), (3, 960, 16, 16, False),
+                                           (1, 1920, 16, 16, True), (2, 640, 5, 7, False), (1, 32, 4, 4, True)])
+def test_groupnorm_nhwc_matches_torch_fp32(cuda_ok, B, C, H, W, silu):
+    """agenda_groupnorm_nhwc against torch.nn.functional.group_norm in fp32 on the same bf16-rounded input (the plain
+    PyTorch fp32 reference of this floating-point op): one bf16 rounding of the result, so 1e-2 relative + 1e-2 absolute."""
+    from agenda_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(B, C, H, W, generator=g) * 2 + 0.5).bfloat16()
+    w = (torch.rand(C, generator=g) + 0.5).bfloat16()
+    b = torch.randn(C, generator=g).bfloat16()
+    ref = torch.nn.functional.group_norm(x.float(), 32, w.float(), b.float(), 1e-5)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    xd = x.cuda().contiguous(memory_format=torch.channels_last)
+    assert ops.groupnorm_nhwc_supported(xd, 32)
+    y = ops.groupnorm_nhwc(xd, w.cuda(), b.cuda(), 32, 1e-5, silu)
+    assert y.shape == xd.shape and y.stride() == xd.stride()          # stays channels-last
+    err = (y.float().cpu() - ref).abs()
+    assert float((err - 1e-2 * ref.abs()).max()) < 1e-2, float(err.max())
+    assert torch.equal(y, ops.groupnorm_nhwc(xd, w.cuda(), b.cuda(), 32, 1e-5, silu))   # no atomics: bit-reproducible
+    # the [B, HW, C] view of the same memory gives the same numbers
+    y3 = ops.groupnorm_nhwc(xd.permute(0, 2, 3, 1).reshape(B, H * W, C), w.cuda(), b.cuda(), 32, 1e-5, silu)
+    assert torch.equal(y3.reshape(B, H, W, C).permute(0, 3, 1, 2), y)
+    assert not ops.groupnorm_nhwc_supported(x.cuda(), 32) or H * W == 1 or C == 1   # NCHW memory is declined
+
+
+def test_geglu_matches_torch_fp32(cuda_ok):
+    from agenda_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(2, 77, 2 * 1280, generator=g) * 1.5).bfloat16()
+    a, gate = x.float().chunk(2, dim=-1)
+    ref = a * torch.nn.functional.gelu(gate)
+    y = ops.geglu(x.cuda())
+    assert y.shape == (2, 77, 1280) and y.dtype == torch.bfloat16
+    err = (y.float().cpu() - ref).abs()
+    assert float((err - 8e-3 * ref.abs()).max()) < 1e-3, float(err.max())
+
+
+@pytest.mark.parametrize("M,C", [(2 * 4096, 320), (300, 640), (77, 1280), (5, 2560), (9, 8)])
+def test_layernorm_matches_torch_fp32(cuda_ok, M, C):
+    from agenda_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    x = (torch.randn(M, C, generator=g) * 3 + 1).bfloat16()
+    w = (torch.rand(C, generator=g) + 0.5).bfloat16()
+    b = torch.randn(C, generator=g).bfloat16()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-5)
+    y = ops.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    err = (y.float().cpu() - ref).abs()
+    assert float((err - 8e-3 * ref.abs()).max()) < 1e-2, float(err.max())
+    y0 = ops.layernorm(x.cuda().reshape(1, M, C), None, None, 1e-5)
+    ref0 = torch.nn.functional.layer_norm(x.float(), (C,), None, None, 1e-5)
+    assert float((y0.float().cpu().reshape(M, C) - ref0).abs().max()) < 3e-2

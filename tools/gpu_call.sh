@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_self_bwd.py -q -m gpu -x 2>&1 | tail -3
-timeout 300 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/s9_train.json 2> gpurun_out/s9_train.err; echo "train rc=$?"; python -c "
-import json;d=json.load(open('gpurun_out/s9_train.json'));print(d['ms_per_step'],d['roofline']['avg_launch_ms'],d['roofline']['frac'])"
+timeout 600 python -m pytest tests/test_gpu_unet.py -q -m gpu -x 2>&1 | tail -3
+timeout 400 python - <<'PY' 2>&1 | tail -3
+import sys, json
+sys.argv = ["bench.py"]
+import torch, bench
+out = bench.full_unet_step(torch.device("cuda", 0), 8, reps=2)
+print(json.dumps(out))
+PY
+timeout 300 python tools/profile_unet.py > gpurun_out/s11_unet_profile.txt 2>&1; head -40 gpurun_out/s11_unet_profile.txt | cut -c1-60,150-215
