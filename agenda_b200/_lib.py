@@ -58,8 +58,9 @@ _SIGNATURES = {
     "agenda_stack_heatmaps_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "agenda_heat_postprocess_stack": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p],
-    "agenda_groupnorm_nhwc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
-                              c_void_p],
+    "agenda_groupnorm_nhwc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                              c_int, c_void_p],
+    "agenda_add_bias_residual": [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p],
     "agenda_geglu": [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p],
     "agenda_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_float, c_void_p],
     "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -11,6 +11,7 @@
 //   DQ   rows = queries i, stream K_j, V_j:       T1 = Q_i K_j^T, T2 = dO_i V_j^T;  G = E (T2 - Delta_i) scale;  dQ_i += G K_j
 //   DK   rows = keys j,    stream Q_i, dO_i:      T1 = K_j Q_i^T, T2 = V_j dO_i^T;  G = E (T2 - Delta_i) scale;  dK_j += G Q_i
 //   DV   rows = keys j,    stream Q_i, dO_i:      T1 = K_j Q_i^T;                    G = E;                       dV_j += G dO_i
+//   DKV  (head dim <= 64: both accumulators fit TMEM) DK and DV in one pass: E is formed once, two G tiles, two accumulators
 //   with E = 2^(c T1 - lse2[query]), c = scale log2(e).
 //
 // DK / DV work on the TRANSPOSED score tile (rows = keys), so that every MMA uses an operand form the forward kernels
@@ -39,7 +40,7 @@ namespace agenda {
 namespace sm100 {
 
 constexpr int kBwdThreads = 320;
-constexpr int kBwdLSE = 0, kBwdDQ = 1, kBwdDK = 2, kBwdDV = 3;
+constexpr int kBwdLSE = 0, kBwdDQ = 1, kBwdDK = 2, kBwdDV = 3, kBwdDKV = 4;
 
 template <int D>
 struct BCfg {
@@ -72,14 +73,19 @@ template <int D, int MODE>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_constant__ CUtensorMap map_r2,
                      const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2,
-                     float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ out, int H,
-                     int N, float scale) {
+                     float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ out,
+                     __nv_bfloat16* __restrict__ out2, int H, int N, float scale) {
   using C = BCfg<D>;
-  constexpr bool kT2 = (MODE == kBwdDQ || MODE == kBwdDK);
+  constexpr bool kDual = (MODE == kBwdDKV);   // dK and dV together: G (-> dK) and the bare E (-> dV), two accumulators
+  constexpr bool kT2 = (MODE == kBwdDQ || MODE == kBwdDK || kDual);
   constexpr bool kAcc = (MODE != kBwdLSE);
-  constexpr bool kColVec = (MODE == kBwdDK || MODE == kBwdDV);  // lse2 / Delta indexed by the streamed (query) tile
+  constexpr bool kColVec = (MODE == kBwdDK || MODE == kBwdDV || kDual);  // lse2 / Delta indexed by the streamed (query) tile
   constexpr int ST = C::kStages;
-  constexpr int NG = C::kNG;
+  constexpr int NG = kDual ? 1 : C::kNG;
+  constexpr int kColG2 = C::kColG + 64;                                    // kDual: E tile (bf16) for the dV product
+  constexpr int kColAcc = kDual ? C::kColG + 128 : C::kColAcc;
+  constexpr int kColAcc2 = kColAcc + C::kDP;
+  static_assert(!kDual || kColAcc2 + C::kDP <= 512, "DKV needs both accumulators in TMEM (head dim <= 64)");
   constexpr bool kEarlyT = (ST >= 2);   // T(it+1) ahead of acc(it) needs tile it+1 resident while tile it is still read
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -200,8 +206,17 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {   // contraction over the half's 64 streamed rows, 16 per MMA
               const int kk = hf * 4 + k4;
-              umma_ts(tmem + C::kColAcc, tmem + C::kColG + buf * 64 + kk * 8,
+              umma_ts(tmem + kColAcc, tmem + C::kColG + buf * 64 + kk * 8,
                       cacc_desc + static_cast<uint64_t>((acc_off + kk * 2048) >> 4), idesc_acc, !(it == 0 && kk == 0));
+            }
+            if (kDual) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {   // dV_j += E dO_i (the streamed C2 tile)
+                const int kk = hf * 4 + k4;
+                umma_ts(tmem + kColAcc2, tmem + kColG2 + kk * 8,
+                        cacc_desc + static_cast<uint64_t>((acc_off + C::kTileBytes + kk * 2048) >> 4), idesc_acc,
+                        !(it == 0 && kk == 0));
+              }
             }
             if (hf == 1) { umma_commit(&bars->g_done[buf]); umma_commit(&bars->st_empty[s]); }
           }
@@ -276,10 +291,10 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
           for (int i = 0; i < 32; ++i) sum += (c0 + c * 32 + i < N) ? ex2(fmaf(t1[i], c_log2, -m_run)) : 0.f;
           l_run += sum;
         } else {
-          uint32_t u[16];
+          uint32_t u[16], u2[kDual ? 16 : 1];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float g[2];
+            float g[2], pe[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int col = c * 32 + i + e;   // within the half
@@ -289,14 +304,17 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
               float p = ex2(fmaf(t1[i + e], c_log2, -lse_x));
               if (!kColVec && c0 + col >= N) p = 0.f;   // keys beyond the sequence (DQ); DK / DV: lse2 = +inf did it
               g[e] = kT2 ? p * (t2[i + e] - delta_x) * scale : p;
+              pe[e] = p;
             }
             u[i >> 1] = pack_bf16(g[0], g[1]);
+            if (kDual) u2[i >> 1] = pack_bf16(pe[0], pe[1]);
           }
           if (c == 0 && it >= NG) {   // the accumulating MMAs that read this G buffer last (tile it - NG) are done
             mbar_wait(&bars->g_done[buf], static_cast<uint32_t>(it / NG - 1) & 1u);
             tc_fence_after();
           }
           tmem_st16(tmem + lane_base + C::kColG + buf * 64 + hf * 32 + c * 16, u);
+          if (kDual) tmem_st16(tmem + lane_base + kColG2 + hf * 32 + c * 16, u2);
         }
       }
       if (kAcc) {
@@ -322,19 +340,23 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
       const int last = n_tiles - 1;
       mbar_wait(&bars->g_done[last % NG], static_cast<uint32_t>(last / NG) & 1u);
       tc_fence_after();
-      __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
 #pragma unroll
-      for (int c = 0; c < C::kDP / 16; ++c) {
-        if ((c & 1) != hf) continue;   // the two warpgroups take alternate 16-column chunks of the accumulator
-        float o[16];
-        tmem_ld16(tmem + lane_base + C::kColAcc + c * 16, o);
-        tmem_wait_ld();
-        if (n_row < N) {
-          uint4 lo, hi;
-          lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
-          hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
-          if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
-          if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+      for (int which = 0; which < (kDual ? 2 : 1); ++which) {
+        __nv_bfloat16* orow = (which ? out2 : out) + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
+        const uint32_t acol = which ? kColAcc2 : kColAcc;
+#pragma unroll
+        for (int c = 0; c < C::kDP / 16; ++c) {
+          if ((c & 1) != hf) continue;   // the two warpgroups take alternate 16-column chunks of the accumulator
+          float o[16];
+          tmem_ld16(tmem + lane_base + acol + c * 16, o);
+          tmem_wait_ld();
+          if (n_row < N) {
+            uint4 lo, hi;
+            lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
+            hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
+            if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+            if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+          }
         }
       }
     }
@@ -368,13 +390,15 @@ __global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ o, const
 
 template <int D, int MODE>
 static int launch_bwd_mode(const CUtensorMap& r1, const CUtensorMap& r2, const CUtensorMap& c1, const CUtensorMap& c2,
-                           float* lse2, const float* delta, void* out, int B, int H, int N, float scale, cudaStream_t st) {
+                           float* lse2, const float* delta, void* out, void* out2, int B, int H, int N, float scale,
+                           cudaStream_t st) {
   constexpr size_t smem = sm100::b_smem_bytes<D>();
   auto kern = sm100::attn_self_bwd_kernel<D, MODE>;
   AGENDA_DYN_SMEM(kern, smem);
   const int n_tiles = (N + 127) / 128;
   kern<<<static_cast<unsigned>(n_tiles) * B * H, sm100::kBwdThreads, smem, st>>>(r1, r2, c1, c2, lse2, delta,
-                                                                               static_cast<__nv_bfloat16*>(out), H, N, scale);
+                                                                               static_cast<__nv_bfloat16*>(out),
+                                                                               static_cast<__nv_bfloat16*>(out2), H, N, scale);
   AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel");
   return AGENDA_OK;
 }
@@ -398,10 +422,14 @@ static int attn_self_bwd_d(const void* q, const void* k, const void* v, const vo
                                                              static_cast<const __nv_bfloat16*>(d_o), delta, B, H, N, D);
     AGENDA_LAUNCH_CHECK("attn_bwd_delta_kernel");
   }
-  if ((rc = launch_bwd_mode<D, sm100::kBwdLSE>(mq, mq, mk, mk, lse2, delta, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
-  if ((rc = launch_bwd_mode<D, sm100::kBwdDQ>(mq, mdo, mk, mv, lse2, delta, dq, B, H, N, scale, st)) != AGENDA_OK) return rc;
-  if ((rc = launch_bwd_mode<D, sm100::kBwdDK>(mk, mv, mq, mdo, lse2, delta, dk, B, H, N, scale, st)) != AGENDA_OK) return rc;
-  return launch_bwd_mode<D, sm100::kBwdDV>(mk, mk, mq, mdo, lse2, delta, dv, B, H, N, scale, st);
+  if ((rc = launch_bwd_mode<D, sm100::kBwdLSE>(mq, mq, mk, mk, lse2, delta, nullptr, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  if ((rc = launch_bwd_mode<D, sm100::kBwdDQ>(mq, mdo, mk, mv, lse2, delta, dq, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  if constexpr (D <= 64) {   // both accumulators fit TMEM: dK and dV share the recomputed E
+    return launch_bwd_mode<D, sm100::kBwdDKV>(mk, mv, mq, mdo, lse2, delta, dk, dv, B, H, N, scale, st);
+  } else {
+    if ((rc = launch_bwd_mode<D, sm100::kBwdDK>(mk, mv, mq, mdo, lse2, delta, dk, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
+    return launch_bwd_mode<D, sm100::kBwdDV>(mk, mk, mq, mdo, lse2, delta, dv, nullptr, B, H, N, scale, st);
+  }
 }
 
 }  // namespace agenda

@@ -52,21 +52,22 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 }
 
 // partial[b][slab][g] = (sum, sum of squares) over the slab's pixels and the group's channels
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ partial, int HW, int C, int G,
-                                int vp, int rows, int ppc) {
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ pre_add,
+                                float2* __restrict__ partial, int HW, int C, int G, int vp, int rows, int ppc) {
   extern __shared__ float sm[];   // [rows][C][2]
   const int b = blockIdx.y, slab = blockIdx.x;
   const int v = threadIdx.x % vp, r = threadIdx.x / vp;
   const int p0 = slab * ppc, p1 = min(HW, p0 + ppc);
-  float s[8], q[8];
+  float s[8], q[8], pa[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; pa[j] = 0.f; }
+  if (pre_add) unpack8(__ldg(reinterpret_cast<const uint4*>(pre_add + static_cast<long long>(b) * C) + v), pa);
   const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * HW * C) + v;
   for (int p = p0 + r; p < p1; p += rows) {
     float f[8];
     unpack8(__ldg(src + static_cast<long long>(p) * vp), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    for (int j = 0; j < 8; ++j) { const float t = f[j] + pa[j]; s[j] += t; q[j] = fmaf(t, t, q[j]); }
   }
   float* mine = sm + (static_cast<long long>(r) * C + v * 8) * 2;
 #pragma unroll
@@ -83,8 +84,9 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __r
 
 template <bool kSilu>
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
-                                const __nv_bfloat16* __restrict__ beta, const float2* __restrict__ partial,
-                                __nv_bfloat16* __restrict__ y, int HW, int C, int G, float eps, int vp, int rows, int ppc) {
+                                const __nv_bfloat16* __restrict__ beta, const __nv_bfloat16* __restrict__ pre_add,
+                                const float2* __restrict__ partial, __nv_bfloat16* __restrict__ y, int HW, int C, int G,
+                                float eps, int vp, int rows, int ppc) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
   if (threadIdx.x < G) {
@@ -102,13 +104,16 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_
   __syncthreads();
   const int v = threadIdx.x % vp, r = threadIdx.x / vp;
   const int cg = C / G;
-  float sc[8], sh[8];
+  float sc[8], sh[8], pa[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pa[j] = 0.f;
+  if (pre_add) unpack8(__ldg(reinterpret_cast<const uint4*>(pre_add + static_cast<long long>(b) * C) + v), pa);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = v * 8 + j, g = c / cg;
     const float ga = gamma ? __bfloat162float(gamma[c]) : 1.f, be = beta ? __bfloat162float(beta[c]) : 0.f;
     sc[j] = s_rstd[g] * ga;
-    sh[j] = be - s_mean[g] * sc[j];
+    sh[j] = be + (pa[j] - s_mean[g]) * sc[j];   // (x + pre_add - mean) * rstd * gamma + beta
   }
   const int p0 = slab * ppc, p1 = min(HW, p0 + ppc);
   const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * HW * C) + v;
@@ -146,6 +151,26 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16*
       const float g1 = 0.5f * g[j + 1] * (1.f + erff(g[j + 1] * 0.70710678118654752f));
       oh[j >> 1] = __floats2bfloat162_rn(a[j] * g0, a[j + 1] * g1);
     }
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+// y[r, c] = h[r, c] + bias[c] + res[r, c]  (the tail of diffusers' ResnetBlock2D: conv2 bias + skip connection), 8 per thread
+__global__ void add_bias_residual_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ bias,
+                                         const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y,
+                                         long long n_vec, int vp) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_vec; i += stride) {
+    float a[8], r[8], bb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(h) + i), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(res) + i), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bb[j] = 0.f;
+    if (bias) unpack8(__ldg(reinterpret_cast<const uint4*>(bias) + (i % vp)), bb);
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) oh[j >> 1] = __floats2bfloat162_rn(a[j] + bb[j] + r[j], a[j + 1] + bb[j + 1] + r[j + 1]);
     reinterpret_cast<uint4*>(y)[i] = o;
   }
 }
@@ -237,15 +262,16 @@ extern "C" long long agenda_groupnorm_workspace_bytes(int B, int HW, int C, int 
   return static_cast<long long>(B) * kGnMaxSlabs * G * 8;
 }
 
-extern "C" int agenda_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* y, void* workspace, int B,
-                                     int HW, int C, int G, float eps, int silu, void* stream) {
+extern "C" int agenda_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* pre_add, void* y,
+                                     void* workspace, int B, int HW, int C, int G, float eps, int silu, void* stream) {
   const char* who = "groupnorm_nhwc";
   if (B == 0) return AGENDA_OK;
   if (!x || !y || !workspace) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   if (B < 0 || HW <= 0 || C <= 0 || G <= 0 || G > 64 || C % G != 0 || C % 8 != 0 || C > 8 * 1024 || B > 65535)
     return fail(AGENDA_ERR_BAD_SHAPE, "%s: B=%d HW=%d C=%d G=%d (C %% 8 == 0, C %% G == 0, G <= 64)", who, B, HW, C, G);
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(workspace)) & 15)
-    return fail(AGENDA_ERR_MISALIGNED, "%s: x, y, workspace must be 16-byte aligned", who);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(workspace) |
+       reinterpret_cast<uintptr_t>(pre_add)) & 15)
+    return fail(AGENDA_ERR_MISALIGNED, "%s: x, y, workspace, pre_add must be 16-byte aligned", who);
   const GnPlan p = gn_plan(B, HW, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(p.rows) * C * 2 * sizeof(float);
@@ -253,13 +279,14 @@ extern "C" int agenda_groupnorm_nhwc(const void* x, const void* gamma, const voi
   const dim3 grid(p.slabs, B);
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
   float2* part = static_cast<float2*>(workspace);
-  gn_stats_kernel<<<grid, p.threads, smem, st>>>(xb, part, HW, C, G, p.vp, p.rows, p.ppc);
+  const __nv_bfloat16* pa = static_cast<const __nv_bfloat16*>(pre_add);
+  gn_stats_kernel<<<grid, p.threads, smem, st>>>(xb, pa, part, HW, C, G, p.vp, p.rows, p.ppc);
   AGENDA_LAUNCH_CHECK("gn_stats_kernel");
   const __nv_bfloat16* ga = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* be = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
-  if (silu) gn_apply_kernel<true><<<grid, p.threads, 0, st>>>(xb, ga, be, part, yb, HW, C, G, eps, p.vp, p.rows, p.ppc);
-  else gn_apply_kernel<false><<<grid, p.threads, 0, st>>>(xb, ga, be, part, yb, HW, C, G, eps, p.vp, p.rows, p.ppc);
+  if (silu) gn_apply_kernel<true><<<grid, p.threads, 0, st>>>(xb, ga, be, pa, part, yb, HW, C, G, eps, p.vp, p.rows, p.ppc);
+  else gn_apply_kernel<false><<<grid, p.threads, 0, st>>>(xb, ga, be, pa, part, yb, HW, C, G, eps, p.vp, p.rows, p.ppc);
   AGENDA_LAUNCH_CHECK("gn_apply_kernel");
   return AGENDA_OK;
 }
@@ -294,5 +321,24 @@ extern "C" int agenda_layernorm(const void* x, const void* gamma, const void* be
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
       static_cast<__nv_bfloat16*>(y), M, C, eps);
   AGENDA_LAUNCH_CHECK("layernorm_kernel");
+  return AGENDA_OK;
+}
+
+extern "C" int agenda_add_bias_residual(const void* h, const void* bias, const void* res, void* y, long long rows, int C,
+                                        void* stream) {
+  const char* who = "add_bias_residual";
+  if (rows == 0) return AGENDA_OK;
+  if (!h || !res || !y) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (rows < 0 || C <= 0 || C % 8 != 0) return fail(AGENDA_ERR_BAD_SHAPE, "%s: rows=%lld C=%d (C %% 8 == 0)", who, rows, C);
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(y) |
+       reinterpret_cast<uintptr_t>(bias)) & 15)
+    return fail(AGENDA_ERR_MISALIGNED, "%s: pointers must be 16-byte aligned", who);
+  const int vp = C / 8;
+  const long long n_vec = rows * vp;
+  const long long blocks = std::min<long long>((n_vec + 255) / 256, static_cast<long long>(num_sms()) * 16);
+  add_bias_residual_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(h), static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(res),
+      static_cast<__nv_bfloat16*>(y), n_vec, vp);
+  AGENDA_LAUNCH_CHECK("add_bias_residual_kernel");
   return AGENDA_OK;
 }

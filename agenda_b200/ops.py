@@ -480,9 +480,10 @@ def groupnorm_nhwc_supported(x: torch.Tensor, groups: int) -> bool:
 
 @_on_tensor_device
 def groupnorm_nhwc(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], groups: int,
-                   eps: float = 1e-5, silu: bool = False) -> torch.Tensor:
+                   eps: float = 1e-5, silu: bool = False, pre_add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """torch.nn.GroupNorm (+ SiLU) on a channels-last bf16 tensor without leaving the channels-last layout
-    (agenda_groupnorm_nhwc).  x [B,C,H,W] channels-last -> same shape / strides; x [B,HW,C] -> [B,HW,C]."""
+    (agenda_groupnorm_nhwc).  x [B,C,H,W] channels-last -> same shape / strides; x [B,HW,C] -> [B,HW,C].
+    pre_add [B,C]: added to x (broadcast over the pixels) before the normalisation."""
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
         raise RuntimeError("agenda_b200: `x` must be a CUDA tensor (no CPU fallback exists)")
     if not groupnorm_nhwc_supported(x, groups):   # (no .contiguous() here: that would turn channels-last into NCHW)
@@ -497,8 +498,28 @@ def groupnorm_nhwc(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Option
     ws = torch.empty(_lib.load().agenda_groupnorm_workspace_bytes(B, HW, C, groups) // 4, dtype=torch.float32, device=x.device)
     w = None if weight is None else _dev(weight, "weight", torch.bfloat16).contiguous()
     b = None if bias is None else _dev(bias, "bias", torch.bfloat16).contiguous()
+    pa = None
+    if pre_add is not None:
+        pa = _dev(pre_add, "pre_add", torch.bfloat16)
+        if tuple(pa.shape) != (B, C):
+            raise ValueError("groupnorm_nhwc: pre_add must be [B, C]")
     _lib.call("agenda_groupnorm_nhwc", x.data_ptr(), 0 if w is None else w.data_ptr(), 0 if b is None else b.data_ptr(),
-              y.data_ptr(), ws.data_ptr(), B, HW, C, groups, float(eps), 1 if silu else 0, _stream())
+              0 if pa is None else pa.data_ptr(), y.data_ptr(), ws.data_ptr(), B, HW, C, groups, float(eps),
+              1 if silu else 0, _stream())
+    return y
+
+
+@_on_tensor_device
+def add_bias_residual(h: torch.Tensor, bias: Optional[torch.Tensor], res: torch.Tensor) -> torch.Tensor:
+    """h + bias[c] + res for channels-last bf16 [B,C,H,W] tensors of identical strides (agenda_add_bias_residual)."""
+    if not (h.is_cuda and h.dtype == torch.bfloat16 and res.dtype == torch.bfloat16 and h.shape == res.shape
+            and h.stride() == res.stride() and h.dim() == 4 and h.permute(0, 2, 3, 1).is_contiguous()):
+        raise ValueError("add_bias_residual: need two channels-last bf16 CUDA tensors of the same shape")
+    B, C, H, W = h.shape
+    y = torch.empty_like(h)
+    b = None if bias is None else _dev(bias, "bias", torch.bfloat16)
+    _lib.call("agenda_add_bias_residual", h.data_ptr(), 0 if b is None else b.data_ptr(), res.data_ptr(), y.data_ptr(),
+              B * H * W, C, _stream())
     return y
 
 

@@ -30,6 +30,10 @@ from .processor import UNetCrossAttentionHooker
 from .sd_attention import SDAttention
 
 
+def _fast(x: torch.Tensor, groups: int = 32) -> bool:
+    return ops.groupnorm_nhwc_supported(x, groups) and not torch.is_grad_enabled()
+
+
 def group_norm(norm: nn.GroupNorm, x: torch.Tensor, silu: bool = False) -> torch.Tensor:
     """GroupNorm (+ SiLU).  bf16 channels-last activations on the GPU — the pipeline's configuration — go through the
     NHWC kernel (agenda_groupnorm_nhwc): torch's native_group_norm converts a channels-last input to NCHW and the next
@@ -60,6 +64,19 @@ class ResnetBlock(nn.Module):
         self.shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
+        if _fast(x, self.norm1.num_groups) and self.conv1.out_channels % (8 * self.norm2.num_groups // math.gcd(8, self.norm2.num_groups)) == 0:
+            # inference fast path: the convolutions run without their bias; conv1's bias + the time-embedding projection
+            # enter the second GroupNorm as a per-(batch, channel) pre-add, conv2's (+ the shortcut's) bias and the skip
+            # connection are one pass — four full-tensor adds fewer per block
+            h = F.conv2d(group_norm(self.norm1, x, silu=True), self.conv1.weight, None, padding=1)
+            h = h.contiguous(memory_format=torch.channels_last)          # (a no-op after a channels-last cuDNN convolution)
+            add = self.time_emb_proj(F.silu(temb)) + self.conv1.bias
+            h = ops.groupnorm_nhwc(h, self.norm2.weight, self.norm2.bias, self.norm2.num_groups, self.norm2.eps, True, add)
+            h = F.conv2d(h, self.conv2.weight, None, padding=1).contiguous(memory_format=torch.channels_last)
+            if self.shortcut is None:
+                return ops.add_bias_residual(h, self.conv2.bias, x)
+            skip = F.conv2d(x, self.shortcut.weight, None).contiguous(memory_format=torch.channels_last)
+            return ops.add_bias_residual(h, self.conv2.bias + self.shortcut.bias, skip)
         h = self.conv1(group_norm(self.norm1, x, silu=True))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(group_norm(self.norm2, h, silu=True))

@@ -220,14 +220,20 @@ int agenda_heat_postprocess_stack(const float* heat, uint8_t* planes, uint8_t* s
  * agenda_groupnorm_nhwc: torch.nn.GroupNorm(G, C, eps) on x [B, HW, C] (a channels-last [B,C,H,W] tensor's memory),
  * statistics in fp32 over each (batch, group) = HW * C/G values, biased variance, y = (x - mean) * rstd * gamma + beta,
  * optionally followed by SiLU (diffusers ResnetBlock2D: conv(silu(norm(x)))); y [B, HW, C] bf16.  gamma / beta bf16 [C]
- * (NULL: 1 / 0).  workspace: agenda_groupnorm_workspace_bytes(B, HW, C, G) bytes (per-slab partial sums; no atomics, so
+ * (NULL: 1 / 0).  pre_add bf16 [B, C] (may be NULL): a per-(batch, channel) term added to x BEFORE the normalisation —
+ * ResnetBlock2D's conv1 bias + time-embedding projection, which otherwise cost two passes over the tensor.
+ * workspace: agenda_groupnorm_workspace_bytes(B, HW, C, G) bytes (per-slab partial sums; no atomics, so
  * results are bit-reproducible).  C % 8 == 0, C % G == 0, G <= 64; x, y, workspace 16-byte aligned.
  * agenda_geglu: diffusers GEGLU after its projection: x [M, 2*inner] = [a | gate] -> y [M, inner] = a * gelu(gate)
  * (erf form), fp32 arithmetic, one rounding to bf16.  inner % 8 == 0. */
 long long agenda_groupnorm_workspace_bytes(int B, int HW, int C, int G);
-int agenda_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, void* y, void* workspace, int B, int HW,
-                          int C, int G, float eps, int silu, void* stream);
+int agenda_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* pre_add, void* y, void* workspace,
+                          int B, int HW, int C, int G, float eps, int silu, void* stream);
 int agenda_geglu(const void* x, void* y, long long M, int inner, void* stream);
+/* y[r, c] = h[r, c] + bias[c] + res[r, c]: the tail of ResnetBlock2D (conv2 bias + skip connection) in one pass.
+ * h, res, y bf16 [rows, C] (channels-last memory), bias bf16 [C] or NULL.  C % 8 == 0; 16-byte aligned. */
+int agenda_add_bias_residual(const void* h, const void* bias, const void* res, void* y, long long rows, int C,
+                             void* stream);
 /* torch.nn.LayerNorm(C, eps) over the last dim of x [M, C] bf16 (the three norms of diffusers' BasicTransformerBlock):
  * mean and centred variance in fp32, y = (x - mean) * rstd * gamma + beta, one rounding to bf16.  gamma / beta bf16 [C]
  * (NULL: 1 / 0).  C % 8 == 0; pointers 16-byte aligned. */

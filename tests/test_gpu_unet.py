@@ -154,3 +154,34 @@ def test_layernorm_matches_torch_fp32(cuda_ok, M, C):
     y0 = ops.layernorm(x.cuda().reshape(1, M, C), None, None, 1e-5)
     ref0 = torch.nn.functional.layer_norm(x.float(), (C,), None, None, 1e-5)
     assert float((y0.float().cpu().reshape(M, C) - ref0).abs().max()) < 3e-2
+
+
+def test_resnet_block_fast_path_matches_plain_torch(cuda_ok):
+    """ResnetBlock's inference fast path (bias-free convolutions, GroupNorm pre-add, fused bias + skip add) against the
+    same block evaluated by plain torch modules in fp32."""
+    from agenda_b200 import ops
+    from agenda_b200.unet import ResnetBlock
+    torch.manual_seed(0)
+    for cin, cout in ((64, 64), (96, 64)):
+        blk = ResnetBlock(cin, cout, temb=128)
+        for p in blk.parameters():
+            torch.nn.init.normal_(p, std=0.05) if p.dim() > 1 else torch.nn.init.normal_(p, mean=0.5, std=0.2)
+        x = torch.randn(2, cin, 16, 16)
+        temb = torch.randn(2, 128)
+        fast = blk.to(device="cuda", dtype=torch.bfloat16).to(memory_format=torch.channels_last)
+        with torch.no_grad():
+            y = fast(x.cuda().bfloat16().contiguous(memory_format=torch.channels_last), temb.cuda().bfloat16())
+            ref_blk = ResnetBlock(cin, cout, temb=128)
+            ref_blk.load_state_dict({k: v.float().cpu() for k, v in fast.state_dict().items()})
+            with torch.enable_grad():      # grad mode selects the plain torch path of the module
+                ref = ref_blk(x.bfloat16().float().requires_grad_(True), temb.bfloat16().float()).detach()
+        assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+        err = (y.float().cpu() - ref).abs().max().item()
+        assert err < 3e-2 * ref.abs().max().item() + 1e-2, err
+    # the GroupNorm pre-add alone
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 8, 8, generator=g).bfloat16()
+    add = torch.randn(2, 64, generator=g).bfloat16()
+    ref = torch.nn.functional.group_norm(x.float() + add.float()[:, :, None, None], 32, None, None, 1e-5)
+    y = ops.groupnorm_nhwc(x.cuda().contiguous(memory_format=torch.channels_last), None, None, 32, 1e-5, False, add.cuda())
+    assert (y.float().cpu() - ref).abs().max().item() < 3e-2
