@@ -47,6 +47,8 @@ _SIGNATURES = {
     "agenda_attn_cross_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int,
                               c_void_p],
+    "agenda_attn_cross_bwd_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p],
     "agenda_attn_self_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_int, c_int, c_int, c_int, c_float, c_void_p],
     "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -66,7 +68,8 @@ _SIGNATURES = {
     "agenda_ccl_bbox": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
 }
 EXPORTS = (["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes",
-            "agenda_attn_self_bwd_workspace_bytes", "agenda_groupnorm_workspace_bytes"] + list(_SIGNATURES))
+            "agenda_attn_self_bwd_workspace_bytes", "agenda_groupnorm_workspace_bytes",
+            "agenda_attn_cross_bwd_tc_workspace_bytes"] + list(_SIGNATURES))
 
 _lib = None
 
@@ -91,6 +94,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_context_blob_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_attn_self_bwd_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_attn_self_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.agenda_attn_cross_bwd_tc_workspace_bytes.restype = ctypes.c_longlong
+    lib.agenda_attn_cross_bwd_tc_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_groupnorm_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_groupnorm_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, argtypes in _SIGNATURES.items():

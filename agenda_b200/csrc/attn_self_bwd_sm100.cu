@@ -32,6 +32,7 @@
 //     need the half to be free and the next streamed tile to be resident), so the next scores are computed while the
 //     row warpgroups are still exponentiating tile it; G is double buffered where TMEM has room (head dim <= 128);
 //   * two row warps per SM sub-partition instead of one halve the issue-bound exponential / pack phase.
+#include <algorithm>
 #include <cstdlib>
 
 #include "sm100_common.cuh"
@@ -54,7 +55,8 @@ struct BCfg {
 };
 
 struct BBarriers {
-  float vec[2][2][2][64];   // DK / DV: [warpgroup][tile parity][lse2 | Delta][its 64 streamed queries]; LSE: (m, l) exchange
+  float vec[2][2][10][64];  // DK / DV: [warpgroup][tile parity][lse2 | Delta | kCross: Delta - heat-map term of token t][its 64
+                            // streamed queries]; LSE: (m, l) exchange
   uint64_t fixed_full;
   uint64_t st_full[2], st_empty[2];
   uint64_t t_full[2], t_free[2];      // per half
@@ -68,14 +70,27 @@ constexpr size_t b_smem_bytes() {
   return 1024 + (2 + 2 * BCfg<D>::kStages) * BCfg<D>::kTileBytes + sizeof(BBarriers) + 64;
 }
 
+// Cross-attention use of the DK / DV / DKV modes (kCross; K7 on the tensor cores): the ROWS are the prompt's M <= 80 keys (one
+// row tile, N = M), the streamed tiles the Nc queries; the streamed range is split over gridDim.y CTAs whose partial dK / dV are
+// added into caller-zeroed fp32 buffers; the gradient of the head-mean heat maps enters dP on the rows that are selected tokens.
+struct CrossBwdArgs {
+  const float* d_maps;   // [B - b_first, T, Nc] fp32 or NULL
+  float* out_f32;        // dK (modes DK, DKV) or dV (mode DV): fp32 [B, M, H*D], atomically accumulated
+  float* out2_f32;       // dV (mode DKV)
+  int Nc;                // streamed (query) length
+  int b_first, T;
+  int tok[8];
+};
+
 // map_r1 / map_r2: the tensors the fixed row tiles come from; map_c1 / map_c2: the streamed ones (see the mode table).
-template <int D, int MODE>
+template <int D, int MODE, bool kCross = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_constant__ CUtensorMap map_r2,
                      const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2,
                      float* __restrict__ lse2, const float* __restrict__ delta, __nv_bfloat16* __restrict__ out,
-                     __nv_bfloat16* __restrict__ out2, int H, int N, float scale) {
+                     __nv_bfloat16* __restrict__ out2, int H, int N, float scale, const CrossBwdArgs cx) {
   using C = BCfg<D>;
+  static_assert(!kCross || MODE == kBwdDK || MODE == kBwdDV || MODE == kBwdDKV, "cross: key-row modes only");
   constexpr bool kDual = (MODE == kBwdDKV);   // dK and dV together: G (-> dK) and the bare E (-> dV), two accumulators
   constexpr bool kT2 = (MODE == kBwdDQ || MODE == kBwdDK || kDual);
   constexpr bool kAcc = (MODE != kBwdLSE);
@@ -95,11 +110,18 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
   BBarriers* bars = reinterpret_cast<BBarriers*>(sC + 2 * ST * C::kTileBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int n_tiles = (N + 127) / 128;
-  const int bh = blockIdx.x / n_tiles, rt = blockIdx.x - bh * n_tiles;
+  const int n_row_tiles = (N + 127) / 128;
+  const int bh = blockIdx.x / n_row_tiles, rt = blockIdx.x - bh * n_row_tiles;
   const int b = bh / H, h = bh - b * H;
   const int r0 = rt * 128;
   const float c_log2 = scale * 1.4426950408889634f;
+  // streamed tiles of this CTA: all of them (self-attention), or its share of the query range (kCross, gridDim.y splits)
+  const int Ns = kCross ? cx.Nc : N;                      // streamed length == length of the lse2 / Delta vectors (queries)
+  const int all_tiles = (Ns + 127) / 128;
+  const int per_split = kCross ? (all_tiles + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y) : all_tiles;
+  const int t_first = kCross ? static_cast<int>(blockIdx.y) * per_split : 0;
+  const int n_tiles = min(per_split, all_tiles - t_first);
+  if (n_tiles <= 0) return;                               // (uniform over the CTA, before any barrier or TMEM allocation)
 
   if (tid == 8 * 32) {
     tma_prefetch_desc(&map_r1); tma_prefetch_desc(&map_c1);
@@ -143,8 +165,8 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
         unsigned char* c2 = c1 + C::kTileBytes;
         mbar_expect_tx(&bars->st_full[s], (kLoadC2 ? 2 : 1) * C::kTileBytes);
         for (int c = 0; c < C::kChunks; ++c) {
-          tma_load_4d(&map_c1, &bars->st_full[s], c1 + c * 128 * 128, c * 64, h, it * 128, b);
-          if (kLoadC2) tma_load_4d(&map_c2, &bars->st_full[s], c2 + c * 128 * 128, c * 64, h, it * 128, b);
+          tma_load_4d(&map_c1, &bars->st_full[s], c1 + c * 128 * 128, c * 64, h, (t_first + it) * 128, b);
+          if (kLoadC2) tma_load_4d(&map_c2, &bars->st_full[s], c2 + c * 128 * 128, c * 64, h, (t_first + it) * 128, b);
         }
       }
       __syncwarp();
@@ -230,14 +252,14 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
     const int row = tid & 127;
     const int n_row = r0 + row;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const long long vec_base = static_cast<long long>(bh) * N;
+    const long long vec_base = static_cast<long long>(bh) * (kColVec ? Ns : N);
     // DK / DV: this thread's element of the streamed tile's lse2 (rows 0-63 of the warpgroup) or Delta (rows 64-127) is
     // fetched one tile ahead into a register, so its global-load latency hides behind the current tile
     auto fetch_vec = [&](int it) -> float {
-      const int qn = it * 128 + hf * 64 + (row & 63);
+      const int qn = (t_first + it) * 128 + hf * 64 + (row & 63);
       if (it >= n_tiles) return 0.f;
-      if (row < 64) return (qn < N) ? lse2[vec_base + qn] : INFINITY;   // out-of-range queries: lse2 = +inf, i.e. E = 0
-      return (kT2 && qn < N) ? delta[vec_base + qn] : 0.f;
+      if (row < 64) return (qn < Ns) ? lse2[vec_base + qn] : INFINITY;   // out-of-range queries: lse2 = +inf, i.e. E = 0
+      return (kT2 && qn < Ns) ? delta[vec_base + qn] : 0.f;
     };
     float vec_next = kColVec ? fetch_vec(0) : 0.f;
     float lse_r = 0.f, delta_r = 0.f;
@@ -246,16 +268,48 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
       if (kT2) delta_r = (n_row < N) ? delta[vec_base + n_row] : 0.f;
     }
     float m_run = -INFINITY, l_run = 0.f;   // LSE mode (over this warpgroup's columns)
+    // kCross: the gradient of the head-mean heat maps enters dP on the key rows that are selected tokens:
+    //   G_jq = E_jq (T2_jq + dm_t[q] / H - Delta_q) scale = E_jq (T2_jq - Delta'_tq) scale,  Delta'_tq = Delta_q - sum_{t': tok[t'] == tok[t]} dm_t'[q] / H,
+    // so a token row simply reads ITS OWN copy of the Delta vector (slot 2 + t) and the inner loop has no branch.  The
+    // threads that park Delta for a column (rows 64-127 of the warpgroup) fetch the column's dm values one tile ahead.
+    const bool has_maps = kCross && kT2 && cx.d_maps != nullptr && b >= cx.b_first;
+    int my_slot = 1;
+    if (has_maps)
+      for (int t = cx.T - 1; t >= 0; --t) my_slot = (cx.tok[t] == r0 + row) ? 2 + t : my_slot;
+    const float* dm_row = has_maps ? cx.d_maps + static_cast<long long>(b - cx.b_first) * cx.T * Ns : nullptr;
+    const float inv_h = 1.0f / static_cast<float>(H);
+    float dmn[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dmn[t] = 0.f;
+    auto fetch_dm = [&](int it) {
+      if (!has_maps || row < 64 || it >= n_tiles) return;
+      const int qn = (t_first + it) * 128 + hf * 64 + (row & 63);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dmn[t] = (t < cx.T && qn < Ns) ? dm_row[static_cast<long long>(t) * Ns + qn] : 0.f;
+    };
+    if (kCross) fetch_dm(0);
     for (int it = 0; it < n_tiles; ++it) {
-      const int c0 = it * 128 + hf * 64;   // first streamed row == first score column of this warpgroup's half
+      const int c0 = (t_first + it) * 128 + hf * 64;   // first streamed row == first score column of this warpgroup's half
       const int buf = it % NG;
       const float* vl = bars->vec[hf][it & 1][0];
-      const float* vd = bars->vec[hf][it & 1][1];
+      const float* vd = bars->vec[hf][it & 1][kCross ? my_slot : 1];
       if (kColVec) {
         // park the prefetched element in this tile's buffer (double buffered: the writers of tile it+1 passed this
         // barrier, so every reader of tile it-1 — same buffer — had finished), read back as broadcasts
         bars->vec[hf][it & 1][row >> 6][row & 63] = vec_next;
+        if (kCross && has_maps && row >= 64) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            if (t < cx.T) {
+              float sum = 0.f;
+#pragma unroll
+              for (int t2 = 0; t2 < 8; ++t2) sum += (t2 < cx.T && cx.tok[t2] == cx.tok[t]) ? dmn[t2] : 0.f;
+              bars->vec[hf][it & 1][2 + t][row & 63] = vec_next - sum * inv_h;
+            }
+          }
+        }
         vec_next = fetch_vec(it + 1);
+        if (kCross) fetch_dm(it + 1);
         if (hf == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
       mbar_wait(&bars->t_full[hf], static_cast<uint32_t>(it) & 1u);
@@ -343,6 +397,7 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
 #pragma unroll
       for (int which = 0; which < (kDual ? 2 : 1); ++which) {
         __nv_bfloat16* orow = (which ? out2 : out) + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
+        float* frow = kCross ? (which ? cx.out2_f32 : cx.out_f32) + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D : nullptr;
         const uint32_t acol = which ? kColAcc2 : kColAcc;
 #pragma unroll
         for (int c = 0; c < C::kDP / 16; ++c) {
@@ -350,7 +405,13 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
           float o[16];
           tmem_ld16(tmem + lane_base + acol + c * 16, o);
           tmem_wait_ld();
-          if (n_row < N) {
+          if (kCross) {   // partial sums of this CTA's query range: result-less fp32 adds into the caller-zeroed buffers
+            if (n_row < N) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k)
+                if (c * 16 + k < D) atomicAdd(frow + c * 16 + k, o[k]);
+            }
+          } else if (n_row < N) {
             uint4 lo, hi;
             lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
             hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
@@ -366,6 +427,193 @@ attn_self_bwd_kernel(const __grid_constant__ CUtensorMap map_r1, const __grid_co
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- K7 on the tensor cores, part 1: dQ of the cross-attention (rows = queries; the prompt's M <= 80 keys are ONE tile) ----
+// CTA = one 128-query tile of one (batch, head).  S = Q K^T and dP = dO V^T (N = 80) land in TMEM; a thread owns a query
+// row: softmax over its 80 scores in registers, the gradient of the head-mean heat maps added to dP on the selected token
+// columns (1 / H each), Delta_i = sum_j P_ij dP_ij, dS = P (dP - Delta) scale back to TMEM as packed bf16, dQ = dS K as a
+// TS-form MMA over the 80 keys.  lse2 / Delta of every query row are left in the workspace for the dK / dV kernel.
+constexpr int kXqThreads = 192;
+struct XqBarriers {
+  uint64_t ld_full, t_full, g_full, acc_full;
+  uint32_t tmem_base;
+};
+template <int D>
+constexpr size_t xq_smem_bytes() { return 1024 + 4 * BCfg<D>::kTileBytes + sizeof(XqBarriers) + 64; }
+
+template <int D>
+__global__ void __launch_bounds__(kXqThreads)
+attn_cross_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_do,
+                         const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                         float* __restrict__ lse2, float* __restrict__ delta, __nv_bfloat16* __restrict__ dq, int H, int N,
+                         int M, float scale, const CrossBwdArgs cx) {
+  using C = BCfg<D>;
+  constexpr int kColS = 0, kColP = 80, kColG = 160, kColAcc = 208;   // S 80 | dP 80 | dS bf16 48 | dQ accumulator
+  constexpr int kCols = (kColAcc + C::kDP <= 256) ? 256 : 512;
+  static_assert(kColAcc + C::kDP <= 512, "TMEM overflow");
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sdO = sQ + C::kTileBytes;
+  unsigned char* sK = sdO + C::kTileBytes;
+  unsigned char* sV = sK + C::kTileBytes;
+  XqBarriers* bars = reinterpret_cast<XqBarriers*>(sV + C::kTileBytes);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (N + 127) / 128;
+  const int bh = blockIdx.x / n_tiles, rt = blockIdx.x - bh * n_tiles;
+  const int b = bh / H, h = bh - b * H;
+  const int r0 = rt * 128;
+  const float c_log2 = scale * 1.4426950408889634f;
+
+  if (tid == 4 * 32) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_do); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    mbar_init(&bars->ld_full, 1); mbar_init(&bars->t_full, 1); mbar_init(&bars->g_full, 128); mbar_init(&bars->acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(&bars->tmem_base, kCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_expect_tx(&bars->ld_full, 4 * C::kTileBytes);
+      for (int c = 0; c < C::kChunks; ++c) {
+        tma_load_4d(&map_q, &bars->ld_full, sQ + c * 128 * 128, c * 64, h, r0, b);
+        tma_load_4d(&map_do, &bars->ld_full, sdO + c * 128 * 128, c * 64, h, r0, b);
+        tma_load_4d(&map_k, &bars->ld_full, sK + c * 128 * 128, c * 64, h, 0, b);
+        tma_load_4d(&map_v, &bars->ld_full, sV + c * 128 * 128, c * 64, h, 0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    constexpr uint32_t idesc_t = make_idesc(128, 80, 0);
+    constexpr uint32_t idesc_acc = make_idesc(128, C::kDP, 1);
+    const uint64_t q_desc = make_sdesc(smem_u32(sQ), 16, 1024), do_desc = make_sdesc(smem_u32(sdO), 16, 1024);
+    const uint64_t k_desc = make_sdesc(smem_u32(sK), 16, 1024), v_desc = make_sdesc(smem_u32(sV), 16, 1024);
+    const uint64_t kacc_desc = make_sdesc(smem_u32(sK), 128 * 128, 1024);   // MN-major view of the key tile
+    mbar_wait(&bars->ld_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < C::kDP / 16; ++kk) {
+        const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
+        umma_ss(tmem + kColS, q_desc + static_cast<uint64_t>(ko >> 4), k_desc + static_cast<uint64_t>(ko >> 4), idesc_t, kk != 0);
+      }
+#pragma unroll
+      for (int kk = 0; kk < C::kDP / 16; ++kk) {
+        const uint32_t ko = (kk >> 2) * 128 * 128 + (kk & 3) * 32;
+        umma_ss(tmem + kColP, do_desc + static_cast<uint64_t>(ko >> 4), v_desc + static_cast<uint64_t>(ko >> 4), idesc_t, kk != 0);
+      }
+      umma_commit(&bars->t_full);
+    }
+    __syncwarp();
+    mbar_wait(&bars->g_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk)   // contraction over the 80 (padded) keys, 16 per MMA
+        umma_ts(tmem + kColAcc, tmem + kColG + kk * 8, kacc_desc + static_cast<uint64_t>((kk * 2048) >> 4), idesc_acc, kk != 0);
+      umma_commit(&bars->acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int row = tid, n_row = r0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    mbar_wait(&bars->t_full, 0);
+    tc_fence_after();
+    // the gradient of the head-mean heat maps enters dP on the selected token columns (1 / H per head): patched into the
+    // TMEM tile one column at a time (the column address is a run-time value; a repeated token is simply added twice)
+    if (cx.d_maps != nullptr && b >= cx.b_first) {
+      for (int t = 0; t < cx.T; ++t) {
+        const float dm = (n_row < N) ? cx.d_maps[(static_cast<long long>(b - cx.b_first) * cx.T + t) * N + n_row] : 0.f;
+        const uint32_t addr = tmem + lane_base + kColP + static_cast<uint32_t>(cx.tok[t]);
+        const float cur = tmem_ld1(addr);
+        tmem_wait_ld();
+        tmem_st1(addr, cur + dm / static_cast<float>(H));
+        tmem_wait_st();
+      }
+    }
+    float p[80];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) tmem_ld16(tmem + lane_base + kColS + c * 16, p + c * 16);
+    tmem_wait_ld();
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 80; ++j) m = fmaxf(m, (j < M) ? p[j] : -INFINITY);
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 80; ++j) {
+      p[j] = (j < M) ? ex2((p[j] - m) * c_log2) : 0.f;
+      l += p[j];
+    }
+    const float inv_l = 1.0f / l;
+#pragma unroll
+    for (int j = 0; j < 80; ++j) p[j] *= inv_l;
+    float dlt = 0.f;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      float raw[16];
+      tmem_ld16(tmem + lane_base + kColP + c * 16, raw);
+      tmem_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dlt = fmaf(p[c * 16 + k], raw[k], dlt);
+    }
+    if (n_row < N) {
+      lse2[static_cast<long long>(bh) * N + n_row] = fmaf(m, c_log2, log2f(l));
+      delta[static_cast<long long>(bh) * N + n_row] = dlt;
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 3; ++c2) {
+      uint32_t u[16];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c = c2 * 2 + hh;
+        if (c < 5) {
+          float raw[16];
+          tmem_ld16(tmem + lane_base + kColP + c * 16, raw);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 16; k += 2) {
+            const float g0 = p[c * 16 + k] * (raw[k] - dlt) * scale;
+            const float g1 = p[c * 16 + k + 1] * (raw[k + 1] - dlt) * scale;
+            u[hh * 8 + (k >> 1)] = pack_bf16(g0, g1);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) u[hh * 8 + k] = 0u;
+        }
+      }
+      tmem_st16(tmem + lane_base + kColG + c2 * 16, u);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    mbar_arrive(&bars->g_full);
+    mbar_wait(&bars->acc_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = dq + (static_cast<long long>(b) * N + n_row) * (H * D) + h * D;
+#pragma unroll
+    for (int c = 0; c < C::kDP / 16; ++c) {
+      float o[16];
+      tmem_ld16(tmem + lane_base + kColAcc + c * 16, o);
+      tmem_wait_ld();
+      if (n_row < N) {
+        uint4 lo, hi;
+        lo.x = pack_bf16(o[0], o[1]); lo.y = pack_bf16(o[2], o[3]); lo.z = pack_bf16(o[4], o[5]); lo.w = pack_bf16(o[6], o[7]);
+        hi.x = pack_bf16(o[8], o[9]); hi.y = pack_bf16(o[10], o[11]); hi.z = pack_bf16(o[12], o[13]); hi.w = pack_bf16(o[14], o[15]);
+        if (c * 16 + 8 <= D) *reinterpret_cast<uint4*>(orow + c * 16) = lo;
+        if (c * 16 + 16 <= D) *reinterpret_cast<uint4*>(orow + c * 16 + 8) = hi;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kCols);
   }
 }
 
@@ -398,7 +646,7 @@ static int launch_bwd_mode(const CUtensorMap& r1, const CUtensorMap& r2, const C
   const int n_tiles = (N + 127) / 128;
   kern<<<static_cast<unsigned>(n_tiles) * B * H, sm100::kBwdThreads, smem, st>>>(r1, r2, c1, c2, lse2, delta,
                                                                                static_cast<__nv_bfloat16*>(out),
-                                                                               static_cast<__nv_bfloat16*>(out2), H, N, scale);
+                                                                               static_cast<__nv_bfloat16*>(out2), H, N, scale, sm100::CrossBwdArgs{});
   AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel");
   return AGENDA_OK;
 }
@@ -432,9 +680,90 @@ static int attn_self_bwd_d(const void* q, const void* k, const void* v, const vo
   }
 }
 
+template <int D>
+static int attn_cross_bwd_tc_d(const void* q, const void* k, const void* v, const void* d_o, const float* d_maps, float* ws,
+                               void* dq, float* dk, float* dv, int B, int H, int N, int M, float scale, const int32_t* token_idx,
+                               int T, int b_first, cudaStream_t st) {
+  CUtensorMap mq, mk, mv, mdo;
+  int rc;
+  if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mdo, d_o, B, H, N, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mk, k, B, H, M, D, 128)) != AGENDA_OK) return rc;
+  if ((rc = make_head_map(&mv, v, B, H, M, D, 128)) != AGENDA_OK) return rc;
+  float* lse2 = ws;
+  float* delta = ws + static_cast<long long>(B) * H * N;
+  sm100::CrossBwdArgs cx{};
+  cx.d_maps = d_maps; cx.Nc = N; cx.b_first = b_first; cx.T = d_maps ? T : 0;
+  for (int t = 0; t < 8; ++t) cx.tok[t] = (d_maps && t < T) ? token_idx[t] : -1;
+  const int n_tiles = (N + 127) / 128;
+  {
+    constexpr size_t smem = sm100::xq_smem_bytes<D>();
+    auto kern = sm100::attn_cross_bwd_dq_kernel<D>;
+    AGENDA_DYN_SMEM(kern, smem);
+    kern<<<static_cast<unsigned>(n_tiles) * B * H, sm100::kXqThreads, smem, st>>>(mq, mdo, mk, mv, lse2, delta,
+                                                                                 static_cast<__nv_bfloat16*>(dq), H, N, M, scale, cx);
+    AGENDA_LAUNCH_CHECK("attn_cross_bwd_dq_kernel");
+  }
+  // dK / dV: rows = keys; the query range is split so that the launch fills the GPU (partials meet in fp32 atomics)
+  const int splits = std::max(1, std::min(n_tiles, (num_sms() + B * H - 1) / (B * H)));
+  const dim3 grid(static_cast<unsigned>(B) * H, static_cast<unsigned>(splits));
+  constexpr size_t smem_b = sm100::b_smem_bytes<D>();
+  if constexpr (D <= 64) {
+    auto kern = sm100::attn_self_bwd_kernel<D, sm100::kBwdDKV, true>;
+    AGENDA_DYN_SMEM(kern, smem_b);
+    cx.out_f32 = dk; cx.out2_f32 = dv;
+    kern<<<grid, sm100::kBwdThreads, smem_b, st>>>(mk, mv, mq, mdo, lse2, delta, nullptr, nullptr, H, M, scale, cx);
+    AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel<DKV, cross>");
+  } else {
+    auto kern_k = sm100::attn_self_bwd_kernel<D, sm100::kBwdDK, true>;
+    AGENDA_DYN_SMEM(kern_k, smem_b);
+    cx.out_f32 = dk; cx.out2_f32 = nullptr;
+    kern_k<<<grid, sm100::kBwdThreads, smem_b, st>>>(mk, mv, mq, mdo, lse2, delta, nullptr, nullptr, H, M, scale, cx);
+    AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel<DK, cross>");
+    auto kern_v = sm100::attn_self_bwd_kernel<D, sm100::kBwdDV, true>;
+    AGENDA_DYN_SMEM(kern_v, smem_b);
+    cx.out_f32 = dv;
+    kern_v<<<grid, sm100::kBwdThreads, smem_b, st>>>(mk, mk, mq, mdo, lse2, delta, nullptr, nullptr, H, M, scale, cx);
+    AGENDA_LAUNCH_CHECK("attn_self_bwd_kernel<DV, cross>");
+  }
+  return AGENDA_OK;
+}
+
 }  // namespace agenda
 
 using namespace agenda;
+
+extern "C" long long agenda_attn_cross_bwd_tc_workspace_bytes(int B, int H, int N) {
+  if (B <= 0 || H <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "attn_cross_bwd_tc_workspace_bytes: B=%d H=%d N=%d", B, H, N);
+  return 2ll * B * H * N * 4;
+}
+
+extern "C" int agenda_attn_cross_bwd_tc(const void* q, const void* k, const void* v, const void* d_out, const float* d_maps,
+                                        void* workspace, void* dq, float* dk, float* dv, int B, int H, int N, int M, int d,
+                                        float scale, const int32_t* token_idx, int T, int b_first, void* stream) {
+  const char* who = "attn_cross_bwd_tc";
+  if (!q || !k || !v || !d_out || !workspace || !dq || !dk || !dv) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (B <= 0 || H <= 0 || N <= 0 || M <= 0 || M > 80 || d <= 0 || static_cast<long long>(B) * H > 65535 || b_first < 0 ||
+      b_first > B)
+    return fail(AGENDA_ERR_BAD_SHAPE, "%s: B=%d H=%d N=%d M=%d d=%d b_first=%d (M <= 80)", who, B, H, N, M, d, b_first);
+  if (d_maps) {
+    if (!token_idx || T < 1 || T > 8) return fail(AGENDA_ERR_UNSUPPORTED, "%s: 1..8 selected tokens (T=%d)", who, T);
+    for (int t = 0; t < T; ++t)
+      if (token_idx[t] < 0 || token_idx[t] >= M) return fail(AGENDA_ERR_BAD_SHAPE, "%s: token index %d outside [0, %d)", who, token_idx[t], M);
+  }
+  const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(workspace);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: q, k, v, d_out, dq, workspace must be 16-byte aligned", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(workspace);
+  switch (d) {
+    case 40: return attn_cross_bwd_tc_d<40>(q, k, v, d_out, d_maps, ws, dq, dk, dv, B, H, N, M, scale, token_idx, T, b_first, st);
+    case 64: return attn_cross_bwd_tc_d<64>(q, k, v, d_out, d_maps, ws, dq, dk, dv, B, H, N, M, scale, token_idx, T, b_first, st);
+    case 80: return attn_cross_bwd_tc_d<80>(q, k, v, d_out, d_maps, ws, dq, dk, dv, B, H, N, M, scale, token_idx, T, b_first, st);
+    case 160: return attn_cross_bwd_tc_d<160>(q, k, v, d_out, d_maps, ws, dq, dk, dv, B, H, N, M, scale, token_idx, T, b_first, st);
+    default: return fail(AGENDA_ERR_UNSUPPORTED, "%s: head dim %d not in {40,64,80,160}", who, d);
+  }
+}
 
 extern "C" long long agenda_attn_self_bwd_workspace_bytes(int B, int H, int N) {
   if (B <= 0 || H <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "attn_self_bwd_workspace_bytes: B=%d H=%d N=%d", B, H, N);

@@ -6,6 +6,7 @@ raises if handed a CPU tensor (there is no CPU path in the product).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -356,8 +357,18 @@ def attn_cross_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: tor
         mp = d_maps.data_ptr()
     else:
         T, idx, mp = 0, None, None
-    _lib.call("agenda_attn_cross_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), mp, dq.data_ptr(),
-              dk.data_ptr(), dv.data_ptr(), _dtype_code(q), B, heads, N, M, d, scale, idx, T, int(b_first), _stream())
+    # bf16 tensors with at most 8 selected tokens (every caller of the reference) take the tensor-core kernels; fp32
+    # tensors, all-token maps and AGENDA_CROSS_BWD_TC=0 the exact fp32 CUDA-core kernel
+    use_tc = (q.dtype == torch.bfloat16 and M <= 80 and d in (40, 64, 80, 160) and (mp is None or 1 <= T <= 8)
+              and os.environ.get("AGENDA_CROSS_BWD_TC", "1") != "0")
+    if use_tc:
+        ws = torch.empty(_lib.load().agenda_attn_cross_bwd_tc_workspace_bytes(B, heads, N) // 4, dtype=torch.float32,
+                         device=q.device)
+        _lib.call("agenda_attn_cross_bwd_tc", q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), mp, ws.data_ptr(),
+                  dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), B, heads, N, M, d, scale, idx, T, int(b_first), _stream())
+    else:
+        _lib.call("agenda_attn_cross_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), mp, dq.data_ptr(),
+                  dk.data_ptr(), dv.data_ptr(), _dtype_code(q), B, heads, N, M, d, scale, idx, T, int(b_first), _stream())
     return dq, dk.to(k.dtype), dv.to(v.dtype)
 
 

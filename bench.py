@@ -147,7 +147,6 @@ def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
 NCU_TRAFFIC = {
     "heat_upsample_accum_32to64": 669.5e6,      # r02_heat_upsample_full_key_metrics.txt: 403.7 MB read + 265.8 MB written
     "heat_postprocess_stack_64to112": 1067.7e6,  # r02b_postprocess_stack_persistent_full_key_metrics.txt: 402.8 MB + 664.9 MB
-    "cross_attention_backward": 11.2e6,          # r02_cross_bwd_full_key_metrics.txt (the operands stay in L2)
 }
 
 
@@ -217,11 +216,14 @@ def probe_hbm_kernels(dev, hbm_gbs):
     ms = _time_launches(lambda: ops.attn_cross_bwd(q, k, v, go, gm, H, toks, 0), 20, graph=True)
     by = 3 * B * N * H * d * 2 + 2 * B * 77 * H * d * 2 + 2 * B * 77 * H * d * 4 + gm.numel() * 4
     fl = 10.0 * B * H * N * 77 * d
-    out["cross_attention_backward"] = {"kernel": "attn_cross_bwd_kernel", "bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm_gbs,
-                                       "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms, "fp32_tflops": fl / ms / 1e9,
-                                       "traffic": NCU_TRAFFIC.get("cross_attention_backward"),
-                                       "note": "B=2, N=4096, d=40, T=3 (includes the memsets / casts of dK, dV); far from both "
-                                               "roofs: fp32 CUDA-core kernel, shared-memory and atomics bound"}
+    out["cross_attention_backward"] = {"kernel": "attn_cross_bwd_dq_kernel + attn_self_bwd_kernel<DKV, cross> (tcgen05)",
+                                       "bound": "hbm", "achieved": by / ms / 1e6, "peak": hbm_gbs,
+                                       "unit": "GB/s", "frac": by / ms / 1e6 / hbm_gbs, "ms": ms, "tflops": fl / ms / 1e9,
+                                       "traffic": None,
+                                       "note": "B=2, N=4096, d=40, T=3 (includes the memsets / casts of dK, dV): two tensor-core "
+                                               "launches (dQ with the row softmax in registers; dK / dV on the transposed "
+                                               "tiles, query range split over the SMs); 17 MB of operands, so launch- and "
+                                               "latency-bound, not HBM-bound; the round-1 fp32 CUDA-core kernel took 198 us"}
     return out
 
 
@@ -714,9 +716,12 @@ def run_train(args):
     tgt = torch.rand(B, len(TOKENS), 64, 64, device=dev)
     proc = UNetCrossAttentionHooker(is_train=True, latent_hw=64, tokens=list(TOKENS), precision="bf16")
 
-    def step():
+    static_ctx = ctx0.clone().requires_grad_(True)
+
+    def step(ctx=None):
         proc.clear()
-        ctx = ctx0.clone().requires_grad_(True)
+        if ctx is None:
+            ctx = ctx0.clone().requires_grad_(True)
         loss = 0.0
         for b, a1, a2 in zip(stack.blocks, stack.attn1, stack.attn2):
             x = hs[(b.hw, b.channels)]
@@ -740,6 +745,38 @@ def run_train(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     launches = _lib.launches - l0
+    # the same step (forward + loss + backward, gradient into a static prompt-embedding leaf) replayed from ONE CUDA graph:
+    # at batch 2 the eager step is bound by the host (Python autograd, ~400 launches of ~20 us kernels), the graph shows
+    # what the kernels take
+    graph_ms, graph_err = None, None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    static_ctx.grad = None
+                    step(static_ctx)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            static_ctx.grad = None
+            g_train = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_train):
+                static_loss = step(static_ctx)
+            for _ in range(2):
+                g_train.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                g_train.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            graph_ms = e0.elapsed_time(e1) / args.steps
+            grad_ok = bool(torch.isfinite(static_ctx.grad.float()).all()) and float(static_ctx.grad.float().abs().max()) > 0
+            if not grad_ok or not bool(torch.isfinite(static_loss)):
+                graph_ms, graph_err = None, "graph replay produced a non-finite loss or an empty gradient"
+        except Exception as exc:  # capture is an optimisation of the measurement, not of the product path
+            graph_ms, graph_err = None, f"{type(exc).__name__}: {exc}"[:200]
     clocks = sampler.stop()
     _, _, tf_sust, peak_src = measured_peaks()
     # self-attention backward alone at the 64x64 layer shape
@@ -755,13 +792,18 @@ def run_train(args):
             "config": {"workload": "training-mode processor: SD-1.5 attention stack, 48 processor calls forward + backward "
                                    f"(self -> cross -> self per block), batch {B}, frozen weights, prompt embedding with grad, "
                                    "output + heat-map L1 loss; forward = the inference kernels, backward = agenda_attn_self_bwd "
-                                   "(tcgen05) + agenda_attn_cross_bwd (fp32 CUDA cores)", "samples_per_step": B},
+                                   "+ agenda_attn_cross_bwd_tc (both tcgen05)", "samples_per_step": B},
             "gpu_launches": launches, "clocks": clocks, "loss": float(loss),
-            "roofline": {"kernel": "attn_self_bwd_kernel<40, LSE|DQ|DK|DV> (N=4096, B*H=%d)" % (B * H), "bound": "tensor",
+            "cuda_graph": {"ms_per_step": graph_ms, "samples_per_s": (B / (graph_ms / 1000.0)) if graph_ms else None,
+                           "error": graph_err,
+                           "note": "the same train step (forward + loss + backward) captured once and replayed; `value` "
+                                   "above is the eager step"},
+            "roofline": {"kernel": "attn_self_bwd_kernel<40, LSE|DQ|DKV> (N=4096, B*H=%d)" % (B * H), "bound": "tensor",
                          "achieved": flops / ms_b / 1e9, "peak": tf_sust, "unit": "TFLOP/s", "frac": flops / ms_b / 1e9 / tf_sust,
                          "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained", "avg_launch_ms": ms_b,
-                         "how": "CUDA events around 10 calls (5 launches each: Delta, LSE, dQ, dK, dV); useful FLOPs "
-                                "10*B*H*N*N*d (five GEMMs); the kernels execute 9 GEMM units (S recomputed three times, dP twice)"}}
+                         "how": "CUDA events around 10 calls (4 launches each: Delta, LSE, dQ, dK+dV); useful FLOPs "
+                                "10*B*H*N*N*d (five GEMMs); the kernels execute 8 GEMM units (S recomputed three times, dP twice, "
+                                "dK and dV sharing one of each)"}}
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 

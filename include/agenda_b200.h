@@ -148,6 +148,17 @@ int agenda_attn_cross_bwd(const void* q, const void* k, const void* v, const voi
                           void* dq, float* dk, float* dv, int dtype, int B, int H, int N, int M, int d, float scale,
                           const int32_t* token_idx, int T, int b_first, void* stream);
 
+/* The same backward on the tcgen05 tensor cores, for bf16 tensors and the few-token form (d_maps NULL or 1 <= T <= 8
+ * selected tokens; M <= 80; d in {40,64,80,160}).  Two stages: dQ (a thread owns a query row: softmax over the 77 scores in
+ * registers, the heat-map gradient patched into the dP tile's token columns, Delta, dS = P (dP - Delta) scale, dQ = dS K as a
+ * TS-form MMA), which leaves every row's log-sum-exp and Delta in `workspace`; then dK / dV on the transposed tiles (rows =
+ * keys, the query range split over the SMs, partial sums ADDED into the caller-zeroed fp32 dk / dv [B,M,H*d] with atomics).
+ * q, k, v, d_out, dq bf16; workspace: agenda_attn_cross_bwd_tc_workspace_bytes(B, H, N) bytes, 16-byte aligned. */
+long long agenda_attn_cross_bwd_tc_workspace_bytes(int B, int H, int N);
+int agenda_attn_cross_bwd_tc(const void* q, const void* k, const void* v, const void* d_out, const float* d_maps,
+                             void* workspace, void* dq, float* dk, float* dv, int B, int H, int N, int M, int d,
+                             float scale, const int32_t* token_idx, int T, int b_first, void* stream);
+
 /* Backward of agenda_attn_self_fwd (training mode, SURVEY.md §8 f N3: autograd of hook.py:104-115 with
  * encoder_hidden_states None, as exercised by finetune_sd_token.py:1043-1069,1089) on the tcgen05 tensor cores.
  * q, k, v, out (the forward result), d_out and the gradients dq, dk, dv are bf16 [B,N,H*d].  P is recomputed from a

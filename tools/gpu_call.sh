@@ -1,9 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python tools/profile_unet.py > gpurun_out/s16_unet_profile.txt 2>&1; head -36 gpurun_out/s16_unet_profile.txt | cut -c1-60,150-215
-timeout 400 python - <<'PY' 2>&1 | tail -2
-import sys, json
-sys.argv = ["bench.py"]
-import torch, bench
-out = bench.full_unet_step(torch.device("cuda", 0), 8, reps=2)
-print(out["value"], out["ms_per_denoise_step"])
-PY
+timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_self_bwd.py -q -m gpu -x -k "backward or training" 2>&1 | tail -3
+timeout 120 python tools/profile_cross_bwd.py 2>&1 | cut -c1-92,180-240 | tail -12 | head -6
+timeout 120 python tools/profile_cross_bwd.py 2 1024 8 80 3 2>&1 | cut -c1-92,180-240 | tail -12 | head -6
+timeout 300 python bench.py --workload train --steps 5 --warmup 3 > gpurun_out/s20_train.json 2> gpurun_out/s20_train.err; echo "train rc=$?"; python -c "
+import json;d=json.load(open('gpurun_out/s20_train.json'));print(d['ms_per_step'],d['cuda_graph'])"
