@@ -255,8 +255,12 @@ class UNetHeatmapPipeline:
     def __init__(self, tokens: Sequence[int] = (5, 6, 7), num_steps: int = 50, latent_hw: int = 64, image_size: int = 112,
                  dtype: torch.dtype = torch.bfloat16, device="cuda", guidance_scale: float = 7.5, thr: float = 0.5,
                  max_boxes: int = 64, seed: int = 0, use_cuda_graph: bool = True,
-                 channels: Sequence[int] = (320, 640, 1280, 1280), context_dim: int = 768, cross_logits: str = "fp32"):
+                 channels: Sequence[int] = (320, 640, 1280, 1280), context_dim: int = 768, cross_logits: str = "fp32",
+                 cudnn_benchmark: bool = False):
         from .mixed import compensate_cross_projections
+        if cudnn_benchmark:
+            # process-wide torch switch: cuDNN times its convolution algorithms once per shape (-11 % convolution time here)
+            torch.backends.cudnn.benchmark = True
         self.device = torch.device(device)
         self.dtype = dtype
         self.tokens = list(tokens)

@@ -233,7 +233,7 @@ def full_unet_step(dev, n_img, reps=2):
     else on cuDNN / cuBLAS), classifier-free guidance and the DDIM update — one CUDA graph per step, 50 steps."""
     import torch
     from agenda_b200.unet import UNetHeatmapPipeline
-    up = UNetHeatmapPipeline(tokens=TOKENS, num_steps=NUM_DENOISE_STEPS, device=dev)
+    up = UNetHeatmapPipeline(tokens=TOKENS, num_steps=NUM_DENOISE_STEPS, device=dev, cudnn_benchmark=True)
     lat, ctx = up.make_inputs(list(range(n_img)))
     up.run(lat, ctx)                                   # warm-up + graph capture
     torch.cuda.synchronize()
