@@ -112,6 +112,70 @@ __global__ void __launch_bounds__(256) heat_upsample_accum_tiled_kernel(const fl
   int ix[4]; float wx[4];
   cubic_src(x, sx, w, ix, wx);
   const int quads_per_row = L >> 2;
+  const int n_quads = L * quads_per_row;
+  // Fast form (one source plane per accumulator plane, at most four output quads and four source floats per thread — the
+  // 64 x 64 latent of every SD pipeline): persistent CTAs; the accumulator quads of THIS plane are requested before its
+  // source is even staged, and the NEXT plane's source floats are fetched into registers during the two filter passes, so
+  // neither HBM round trip (16 KB of accumulator, 4 KB of source per plane) sits on the CTA's critical path.
+  if (G == 1 && n_quads <= 4 * nthr && h * w <= 4 * nthr) {
+    float nsrc[4];
+    auto fetch_src = [&](int plane) {
+      const float* __restrict__ src = maps + static_cast<long long>(plane) * h * w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * nthr;
+        nsrc[k] = (plane < n_planes && i < h * w) ? __ldg(src + i) : 0.f;
+      }
+    };
+    fetch_src(blockIdx.x);
+    for (int plane = blockIdx.x; plane < n_planes; plane += gridDim.x) {
+      float4* dst_plane = reinterpret_cast<float4*>(acc + static_cast<long long>(plane) * L * L);
+      float4 a[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = tid + k * nthr;
+        if (q < n_quads) a[k] = dst_plane[q];
+      }
+      __syncthreads();  // the previous plane's s_src / s_tmp readers are done (and the tables are written)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = tid + k * nthr;
+        if (i < h * w) s_src[i] = nsrc[k];
+      }
+      fetch_src(plane + gridDim.x);
+      __syncthreads();
+      for (int r = r0; r < h; r += r_step) {
+        const float* row = s_src + r * w;
+        s_tmp[r * L + x] = row[ix[0]] * wx[0] + row[ix[1]] * wx[1] + row[ix[2]] * wx[2] + row[ix[3]] * wx[3];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int q = tid + k * nthr;
+        if (q < n_quads) {
+          const int y = q / quads_per_row, qx = q - y * quads_per_row;
+          const int4 iy = *reinterpret_cast<const int4*>(s_iy + 4 * y);
+          const float4 wy = *reinterpret_cast<const float4*>(s_wy + 4 * y);
+          const float4 t0 = *reinterpret_cast<const float4*>(s_tmp + iy.x + 4 * qx);
+          const float4 t1 = *reinterpret_cast<const float4*>(s_tmp + iy.y + 4 * qx);
+          const float4 t2 = *reinterpret_cast<const float4*>(s_tmp + iy.z + 4 * qx);
+          const float4 t3 = *reinterpret_cast<const float4*>(s_tmp + iy.w + 4 * qx);
+          // o = 0; o += rsum_j * wy_j for j = 0..3 (the streaming kernel's order)
+          const float o0 = ((0.f + t0.x * wy.x) + t1.x * wy.y) + t2.x * wy.z + t3.x * wy.w;
+          const float o1 = ((0.f + t0.y * wy.x) + t1.y * wy.y) + t2.y * wy.z + t3.y * wy.w;
+          const float o2 = ((0.f + t0.z * wy.x) + t1.z * wy.y) + t2.z * wy.z + t3.z * wy.w;
+          const float o3 = ((0.f + t0.w * wy.x) + t1.w * wy.y) + t2.w * wy.z + t3.w * wy.w;
+          float4 v = a[k];
+          v.x += fmaxf(o0, 0.f);
+          v.y += fmaxf(o1, 0.f);
+          v.z += fmaxf(o2, 0.f);
+          v.w += fmaxf(o3, 0.f);
+          dst_plane[q] = v;
+        }
+      }
+    }
+    return;
+  }
   for (int plane = blockIdx.x; plane < n_planes; plane += gridDim.x) {  // tables are shared by every plane of the CTA
   const int bp = plane / T, tt = plane - bp * T;
   float4* dst_plane = reinterpret_cast<float4*>(acc + static_cast<long long>(plane) * L * L);
@@ -200,7 +264,12 @@ static int heat_upsample_accum_impl(const float* maps, float* acc, int n_planes,
                                          4 * L) + sizeof(int) * 4 * L;
     AGENDA_DYN_SMEM(heat_upsample_accum_tiled_kernel, smem);
     // small source planes: several planes per CTA (the tap tables are built once); larger ones: one CTA per plane
-    const int grid_t = (h * w <= 256) ? std::min(n_planes, num_sms() * 8) : n_planes;
+    // persistent: as many CTAs as are resident at once (tap tables once per CTA, HBM latencies overlapped by prefetch)
+    int per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heat_upsample_accum_tiled_kernel, threads_t, smem) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 4;
+    const int grid_t = std::min(n_planes, num_sms() * per_sm);
     heat_upsample_accum_tiled_kernel<<<grid_t, threads_t, smem, static_cast<cudaStream_t>(stream)>>>(maps, acc, n_planes,
                                                                                                      h, w, L, T, G);
     AGENDA_LAUNCH_CHECK("heat_upsample_accum_tiled_kernel");

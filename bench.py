@@ -145,7 +145,7 @@ def heat_parity(pipe, hs_dev, ctx_dev, n_img, n_check):
 # ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the probes below (profiles/r02_*_key_metrics.txt);
 # None = not captured for that shape
 NCU_TRAFFIC = {
-    "heat_upsample_accum_32to64": 669.5e6,      # r02_heat_upsample_full_key_metrics.txt: 403.7 MB read + 265.8 MB written
+    "heat_upsample_accum_32to64": 672.4e6,      # r02b_heat_upsample_persistent_full_key_metrics.txt: 403.7 MB read + 268.7 MB written
     "heat_postprocess_stack_64to112": 1067.7e6,  # r02b_postprocess_stack_persistent_full_key_metrics.txt: 402.8 MB + 664.9 MB
 }
 
