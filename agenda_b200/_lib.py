@@ -41,9 +41,12 @@ _SIGNATURES = {
     "agenda_attn_fwd_masked": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                c_void_p, c_int, ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "agenda_linear_split_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "agenda_linear_split_f32_heads": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_pack_context_kv": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_attn_cross_fwd_heat_x3": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                       ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "agenda_attn_cross_fwd_heat_x3_hm": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                         ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "agenda_attn_cross_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int,
                               c_void_p],

@@ -108,7 +108,8 @@ template <int D, typename OutT, bool kAll>
 __global__ void __launch_bounds__(kAll ? 256 : 384, 1)
 attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsigned char* __restrict__ kv_blob,
                            OutT* __restrict__ out, float* __restrict__ maps, const TokenList tl, int H, int N, int M,
-                           int QT, int n_stages, int b_first, int accumulate, float scale_log2) {
+                           int QT, int n_stages, int b_first, int accumulate, float scale_log2,
+                           const float* __restrict__ q_hm) {
   using C = TCfg<D>;
   constexpr int W = C::kW;
   constexpr int kWGs = kAll ? 1 : 2;
@@ -133,7 +134,7 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
   const bool want_heat = (maps != nullptr) && (b >= b_first);
 
   if (tid == kProdWarp * 32) {
-    tma_prefetch_desc(&map_q);
+    if (q_hm == nullptr) tma_prefetch_desc(&map_q);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->k_full[i], 1); mbar_init(&bars->k_empty[i], 1);
       mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1);
@@ -179,9 +180,27 @@ attn_cross_sm100_x3_kernel(const __grid_constant__ CUtensorMap map_q, const unsi
         progress = true;
       }
       if (qi < n_qchunks && mbar_test(&bars->q32_empty[st], ph ^ 1)) {
-        if (elect_one()) {
-          const int s = qi / C::kNC, c = qi - s * C::kNC;
-          const int hl = s / n_qt, qt = s - hl * n_qt;
+        const int s = qi / C::kNC, c = qi - s * C::kNC;
+        const int hl = s / n_qt, qt = s - hl * n_qt;
+        if (q_hm != nullptr) {
+          // chunk-major Q (agenda_linear_split_f32_heads): the 128-query chunk of (batch, head, column chunk) is one dense
+          // block -> ONE bulk copy instead of a 128-row tensor load.  A ragged last tile copies its rows only; the tail of
+          // the stage is zero-filled first (what the tensor map's out-of-bounds fill did), by the whole warp.
+          const int row0 = (tile0 + qt) * 128;
+          const int rows = min(128, N - row0);
+          unsigned char* dst = sQ32 + st * C::kQ32Bytes;
+          if (rows < 128) {
+            const int lane = tid & 31;
+            for (int off = rows * W * 4 + lane * 16; off < C::kQ32Bytes; off += 32 * 16)
+              *reinterpret_cast<uint4*>(dst + off) = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+          }
+          if (elect_one()) {
+            const float* src = q_hm + ((((static_cast<size_t>(b) * H + (h_begin + hl)) * C::kNC + c) * N + row0) * W);
+            mbar_expect_tx(&bars->q32_full[st], rows * W * 4);
+            bulk_load(dst, src, rows * W * 4, &bars->q32_full[st]);
+          }
+        } else if (elect_one()) {
           mbar_expect_tx(&bars->q32_full[st], C::kQ32Bytes);
           tma_load_4d(&map_q, &bars->q32_full[st], sQ32 + st * C::kQ32Bytes, c * W, h_begin + hl, (tile0 + qt) * 128, b);
         }
@@ -649,11 +668,13 @@ static int make_head_map_f32(CUtensorMap* map, const void* base, int B, int H, i
 
 template <int D, typename OutT, bool kAll>
 static int launch_cross_x3(const float* q, const void* kv_blob, void* out, int B, int H, int N, int M, float scale,
-                           const TokenList& tl, int b_first, float* maps, int accumulate, cudaStream_t stream) {
+                           const TokenList& tl, int b_first, float* maps, int accumulate, cudaStream_t stream, int q_hm) {
   using C = sm100::TCfg<D>;
-  CUtensorMap mq;
+  CUtensorMap mq = {};
   int rc;
-  if ((rc = make_head_map_f32(&mq, q, B, H, N, D, C::kW, 128)) != AGENDA_OK) return rc;
+  if (q_hm) {
+    if (C::kW != 40) return fail(AGENDA_ERR_UNSUPPORTED, "attn_cross_fwd_heat_x3_hm: chunk-major Q needs a head dim that is a multiple of 40 (d=%d)", D);
+  } else if ((rc = make_head_map_f32(&mq, q, B, H, N, D, C::kW, 128)) != AGENDA_OK) return rc;
   const int n_tiles = (N + 127) / 128, sms = num_sms();
   const int n_heat = (kAll || maps == nullptr || tl.per_head) ? 0 : tl.n;
   // shared memory: fixed part (operand tiles, K / V buffers) + heat rows + as many fp32 Q stages as fit (2..6)
@@ -687,7 +708,8 @@ static int launch_cross_x3(const float* q, const void* kv_blob, void* out, int B
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = hs;
   cfg.attrs = attr; cfg.numAttrs = hs > 1 ? 1 : 0;
   AGENDA_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, static_cast<const unsigned char*>(kv_blob), static_cast<OutT*>(out), maps, tl,
-                                 H, N, M, QT, n_stages, b_first, accumulate, scale * 1.4426950408889634f));
+                                 H, N, M, QT, n_stages, b_first, accumulate, scale * 1.4426950408889634f,
+                                 q_hm ? q : static_cast<const float*>(nullptr)));
   AGENDA_LAUNCH_CHECK("attn_cross_sm100_x3_kernel");
   return AGENDA_OK;
 }
@@ -746,10 +768,9 @@ extern "C" int agenda_pack_context_kv(const float* k32, const void* v, int v_dty
   }
 }
 
-extern "C" int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob, void* out, int out_dtype, int B, int H,
-                                             int N, int M, int d, float scale, const int32_t* token_idx, int T,
-                                             int b_first, int per_head, float* maps, int accumulate, void* stream) {
-  const char* who = "attn_cross_fwd_heat_x3";
+static int cross_x3_impl(const char* who, int q_hm, const float* q, const void* kv_blob, void* out, int out_dtype, int B, int H,
+                         int N, int M, int d, float scale, const int32_t* token_idx, int T, int b_first, int per_head,
+                         float* maps, int accumulate, void* stream) {
   if (!q || !kv_blob || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   if (out_dtype != AGENDA_F32 && out_dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "%s: out_dtype %d", who, out_dtype);
   if (B <= 0 || H <= 0 || N <= 0 || M <= 0 || d <= 0 || B > 65535)
@@ -776,11 +797,11 @@ extern "C" int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob
   case DD:                                                                                                                \
     if (all)                                                                                                              \
       return out_dtype == AGENDA_F32                                                                                      \
-                 ? launch_cross_x3<DD, float, true>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st)  \
-                 : launch_cross_x3<DD, __nv_bfloat16, true>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st); \
+                 ? launch_cross_x3<DD, float, true>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st, q_hm)  \
+                 : launch_cross_x3<DD, __nv_bfloat16, true>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st, q_hm); \
     return out_dtype == AGENDA_F32                                                                                        \
-               ? launch_cross_x3<DD, float, false>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st)   \
-               : launch_cross_x3<DD, __nv_bfloat16, false>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st);
+               ? launch_cross_x3<DD, float, false>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st, q_hm)   \
+               : launch_cross_x3<DD, __nv_bfloat16, false>(q, kv_blob, out, B, H, N, M, scale, tl, b_first, mp, accumulate, st, q_hm);
   switch (d) {
     AGENDA_X3(40)
     AGENDA_X3(64)
@@ -789,4 +810,18 @@ extern "C" int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob
     default: return fail(AGENDA_ERR_UNSUPPORTED, "%s: head dim %d not in {40,64,80,160}", who, d);
   }
 #undef AGENDA_X3
+}
+
+extern "C" int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob, void* out, int out_dtype, int B, int H,
+                                             int N, int M, int d, float scale, const int32_t* token_idx, int T,
+                                             int b_first, int per_head, float* maps, int accumulate, void* stream) {
+  return cross_x3_impl("attn_cross_fwd_heat_x3", 0, q, kv_blob, out, out_dtype, B, H, N, M, d, scale, token_idx, T, b_first,
+                       per_head, maps, accumulate, stream);
+}
+
+extern "C" int agenda_attn_cross_fwd_heat_x3_hm(const float* q_hm, const void* kv_blob, void* out, int out_dtype, int B, int H,
+                                                int N, int M, int d, float scale, const int32_t* token_idx, int T,
+                                                int b_first, int per_head, float* maps, int accumulate, void* stream) {
+  return cross_x3_impl("attn_cross_fwd_heat_x3_hm", 1, q_hm, kv_blob, out, out_dtype, B, H, N, M, d, scale, token_idx, T, b_first,
+                       per_head, maps, accumulate, stream);
 }

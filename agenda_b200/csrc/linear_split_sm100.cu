@@ -52,11 +52,16 @@ __device__ __forceinline__ void st_shared_f4(void* p, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool kLo>
+// kHeads: the output leaves in the chunk-major layout the split-precision cross-attention kernel streams,
+//   out[b][h][c][n][40]   (b = m / rows_per_batch, n = m % rows_per_batch, column h*d + c*40 + j -> (h, c, j)),
+// i.e. every (batch, head, 40-column chunk) is a dense [N, 40] fp32 plane, so the kernel fetches a 128-query chunk with ONE
+// bulk copy of 20 KB instead of a 128-row TMA tensor load (4-5 TMA-engine cycles per row).  A thread owns a row of the tile:
+// 40 contiguous floats per chunk, written straight from the TMEM registers (no staging, no tensor-map store).
+template <bool kLo, bool kHeads>
 __global__ void __launch_bounds__(kLThreads, 1)
 linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out, int M, int K,
-                    int N) {
+                    int N, float* __restrict__ out_hm, int rows_per_batch, int chunks_per_head) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sStage = smem;
@@ -69,7 +74,8 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int n_kb = K / kLBK;
 
   if (tid == 0) {
-    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_out);
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi);
+    if (!kHeads) tma_prefetch_desc(&map_out);
     if (kLo) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < kLStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
@@ -140,6 +146,30 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int ab = it & 1;
       mbar_wait(&bars->acc_full[ab], (it >> 1) & 1);
       tc_fence_after();
+      if constexpr (kHeads) {
+        const int m = tm * kLBM + row;
+        const int bb = m / rows_per_batch, nn = m - bb * rows_per_batch;
+        const int heads = N / (chunks_per_head * 40);
+        float* base[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = tn * 4 + j, hh = cc / chunks_per_head, c = cc - hh * chunks_per_head;
+          base[j] = out_hm + ((((static_cast<long long>(bb) * heads + hh) * chunks_per_head + c) * rows_per_batch + nn) * 40);
+        }
+#pragma unroll
+        for (int g = 0; g < kLBN / 16; ++g) {
+          float v[16];
+          tmem_ld16(tmem + lane_base + ab * kLBN + g * 16, v);
+          tmem_wait_ld();
+          if (m < M) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = g * 16 + q * 4;   // (compile-time) column of the tile: chunk col / 40, offset col % 40
+              *reinterpret_cast<float4*>(base[col / 40] + (col % 40)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int sub = 0; sub < kLBN / 32; ++sub) {
         float v[32];
@@ -166,10 +196,11 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           }
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(&bars->acc_empty[ab]);
     }
-    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (!kHeads && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -216,14 +247,21 @@ static int make_matrix_map(CUtensorMap* map, const void* base, CUtensorMapDataTy
 
 using namespace agenda;
 
-extern "C" int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
-                                       void* stream) {
-  const char* who = "linear_split_f32";
+static int linear_split_impl(const char* who, const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                             int rows_per_batch, int heads, void* stream) {
   if (!x || !w_hi || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   if (M <= 0 || K <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "%s: M=%d K=%d N=%d", who, M, K, N);
   if (K % sm100::kLBK || N % sm100::kLBN)
     return fail(AGENDA_ERR_UNSUPPORTED, "%s: K=%d must be a multiple of %d and N=%d a multiple of %d", who, K, sm100::kLBK, N,
                 sm100::kLBN);
+  const bool hm = heads > 0;
+  int chunks_per_head = 0;
+  if (hm) {
+    if (rows_per_batch <= 0 || M % rows_per_batch || N % heads || (N / heads) % 40)
+      return fail(AGENDA_ERR_UNSUPPORTED, "%s: head-major output needs M %% rows_per_batch == 0 and a head dim that is a multiple "
+                  "of 40 (M=%d rows_per_batch=%d N=%d heads=%d)", who, M, rows_per_batch, N, heads);
+    chunks_per_head = N / heads / 40;
+  }
   const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) |
                        reinterpret_cast<uintptr_t>(out);
   if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: x / w_hi / w_lo / out must be 16-byte aligned", who);
@@ -232,20 +270,32 @@ extern "C" int agenda_linear_split_f32(const void* x, const void* w_hi, const vo
   if ((rc = make_matrix_map(&mx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, sm100::kLBK, sm100::kLBM)) != AGENDA_OK) return rc;
   if ((rc = make_matrix_map(&mh, w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
   if ((rc = make_matrix_map(&ml, w_lo ? w_lo : w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
-  if ((rc = make_matrix_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, 32, sm100::kLBM)) != AGENDA_OK) return rc;
+  if (hm) mo = mx;   // (not used by the head-major epilogue; any valid descriptor)
+  else if ((rc = make_matrix_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, 32, sm100::kLBM)) != AGENDA_OK) return rc;
   const int n_tiles = ((M + sm100::kLBM - 1) / sm100::kLBM) * (N / sm100::kLBN);
   const int grid = n_tiles < num_sms() ? n_tiles : num_sms();
   constexpr size_t smem = sm100::l_smem_bytes();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (w_lo) {
-    auto kern = sm100::linear_split_kernel<true>;
-    AGENDA_DYN_SMEM(kern, smem);
-    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N);
-  } else {
-    auto kern = sm100::linear_split_kernel<false>;
-    AGENDA_DYN_SMEM(kern, smem);
-    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N);
-  }
+#define AGENDA_LSPLIT(LO, HM)                                                                                  \
+  do {                                                                                                         \
+    auto kern = sm100::linear_split_kernel<LO, HM>;                                                            \
+    AGENDA_DYN_SMEM(kern, smem);                                                                               \
+    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N, out, rows_per_batch, chunks_per_head); \
+  } while (0)
+  if (w_lo) { if (hm) AGENDA_LSPLIT(true, true); else AGENDA_LSPLIT(true, false); }
+  else { if (hm) AGENDA_LSPLIT(false, true); else AGENDA_LSPLIT(false, false); }
+#undef AGENDA_LSPLIT
   AGENDA_LAUNCH_CHECK("linear_split_kernel");
   return AGENDA_OK;
+}
+
+extern "C" int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                                       void* stream) {
+  return linear_split_impl("linear_split_f32", x, w_hi, w_lo, out, M, K, N, 0, 0, stream);
+}
+
+extern "C" int agenda_linear_split_f32_heads(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                                             int rows_per_batch, int heads, void* stream) {
+  if (heads <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "linear_split_f32_heads: heads=%d", heads);
+  return linear_split_impl("linear_split_f32_heads", x, w_hi, w_lo, out, M, K, N, rows_per_batch, heads, stream);
 }

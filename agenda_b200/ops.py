@@ -254,6 +254,44 @@ def linear_split_f32(x: torch.Tensor, w_hi: torch.Tensor, w_lo: Optional[torch.T
     return out
 
 
+class QueryChunks:
+    """An fp32 query projection in the chunk-major layout [B][H][d/40][N][40] (agenda_linear_split_f32_heads), the form
+    agenda_attn_cross_fwd_heat_x3_hm streams with one bulk copy per 128-query chunk.  `to_rows()` gives [B,N,H*d] back."""
+
+    def __init__(self, buf: torch.Tensor, B: int, N: int, heads: int, d: int):
+        self.buf, self.B, self.N, self.heads, self.d = buf, B, N, heads, d
+
+    @property
+    def shape(self):
+        return (self.B, self.N, self.heads * self.d)
+
+    def to_rows(self) -> torch.Tensor:
+        B, N, H, d = self.B, self.N, self.heads, self.d
+        return self.buf.view(B, H, d // 40, N, 40).permute(0, 3, 1, 2, 4).reshape(B, N, H * d)
+
+
+@_on_tensor_device
+def linear_split_f32_heads(x: torch.Tensor, w_hi: torch.Tensor, w_lo: Optional[torch.Tensor], heads: int) -> QueryChunks:
+    """linear_split_f32 for x bf16 [B, N, K] with the fp32 result in the chunk-major layout of the cross-attention kernel
+    (agenda_linear_split_f32_heads); head dim = w.shape[0] / heads must be a multiple of 40."""
+    x = _dev(x, "x", torch.bfloat16)
+    w_hi = _dev(w_hi, "w_hi", torch.bfloat16)
+    if w_lo is not None:
+        w_lo = _dev(w_lo, "w_lo", torch.bfloat16)
+        if w_lo.shape != w_hi.shape:
+            raise ValueError("w_lo must have the shape of w_hi")
+    if x.dim() != 3:
+        raise ValueError("x must be [B, N, K]")
+    B, Nq, K = x.shape
+    Nout = w_hi.shape[0]
+    if w_hi.shape[1] != K or Nout % heads or (Nout // heads) % 40:
+        raise ValueError(f"weight {tuple(w_hi.shape)} does not give {heads} heads of a multiple of 40 columns from K={K}")
+    buf = torch.empty(B * Nq * Nout, dtype=torch.float32, device=x.device)
+    _lib.call("agenda_linear_split_f32_heads", x.data_ptr(), w_hi.data_ptr(), None if w_lo is None else w_lo.data_ptr(),
+              buf.data_ptr(), B * Nq, K, Nout, Nq, heads, _stream())
+    return QueryChunks(buf, B, Nq, heads, Nout // heads)
+
+
 class ContextKV:
     """The prompt side of the split-precision cross-attention, packed for the tensor cores (agenda_pack_context_kv):
     `blob` u8 [B, H, block] with K_hi | K_lo | V of every (batch, head) in the kernel's shared-memory layout."""
@@ -297,7 +335,14 @@ def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Ten
     q fp32 [B,N,H*d] (to_q output with fp32 accumulation); ctx = pack_context_kv(K fp32, V).  maps / token_idx / b_first
     / accumulate / per_head as in attn_cross_heat (token_idx None = all prompt tokens; per_head takes at most 8).
     Returns out [B,N,H*d] in `out_dtype` (bf16 or fp32)."""
-    q = _dev(q, "q", torch.float32)
+    chunked = isinstance(q, QueryChunks)
+    if chunked:
+        if q.heads != ctx.heads or q.d != ctx.d:
+            raise ValueError("the chunk-major query was projected for another head layout than the packed context")
+        qbuf = q.buf
+    else:
+        q = _dev(q, "q", torch.float32)
+        qbuf = q
     B, N, C = q.shape
     heads, M, d = ctx.heads, ctx.M, ctx.d
     if ctx.B != B or heads * d != C or not ctx.blob.is_cuda:
@@ -305,7 +350,7 @@ def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Ten
     scale = float(d ** -0.5 if scale is None else scale)
     if out_dtype not in (torch.bfloat16, torch.float32):
         raise TypeError("out_dtype must be bfloat16 or float32")
-    out = torch.empty((B, N, C), dtype=out_dtype, device=q.device)
+    out = torch.empty((B, N, C), dtype=out_dtype, device=qbuf.device)
     if maps is not None:
         maps = _dev(maps, "maps", torch.float32)
         T = M if token_idx is None else len(token_idx)
@@ -322,7 +367,8 @@ def attn_cross_heat_x3(q: torch.Tensor, ctx: ContextKV, maps: Optional[torch.Ten
         mp = maps.data_ptr()
     else:
         T, idx, mp = 0, None, None
-    _lib.call("agenda_attn_cross_fwd_heat_x3", q.data_ptr(), ctx.blob.data_ptr(), out.data_ptr(),
+    _lib.call("agenda_attn_cross_fwd_heat_x3_hm" if chunked else "agenda_attn_cross_fwd_heat_x3", qbuf.data_ptr(),
+              ctx.blob.data_ptr(), out.data_ptr(),
               _lib.BF16 if out_dtype == torch.bfloat16 else _lib.F32, B, heads, N, M, d, scale, idx, T,
               int(b_first), int(bool(per_head)), mp, int(bool(accumulate)), _stream())
     return out

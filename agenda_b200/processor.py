@@ -226,7 +226,7 @@ class UNetCrossAttentionHooker:
             self._ctx_kv[mod_id] = (ehs, new_state, tensors, attn)
 
     @staticmethod
-    def _query_fp32(attn, hidden_states):
+    def _query_fp32(attn, hidden_states, chunk_major: bool = False):
         """to_q (hook.py:93) with an fp32 result.  fp32 activations: the module's own fp32 GEMM (what the reference
         runs).  bf16 activations: agenda_linear_split_f32 — one tcgen05 GEMM with fp32 accumulation and fp32 OUTPUT
         (products of 16-bit values are exact, so this is the fp32 projection of those activations and weights) that
@@ -241,6 +241,9 @@ class UNetCrossAttentionHooker:
         lo = getattr(lin, "weight_lo", None)
         if lin.bias is None and ops.linear_split_f32_supported(hidden_states, w) and (lo is None or lo.dtype == w.dtype):
             # one tcgen05 GEMM: both weight halves into the same fp32 accumulator, activations read once, fp32 written once
+            if chunk_major and (w.shape[0] // attn.heads) % 40 == 0 and w.shape[0] % attn.heads == 0:
+                # ... in the chunk-major layout the cross-attention kernel fetches with one bulk copy per 128-query chunk
+                return ops.linear_split_f32_heads(hidden_states, w.detach(), None if lo is None else lo, attn.heads)
             return ops.linear_split_f32(hidden_states, w.detach(), None if lo is None else lo)
         x2 = hidden_states.reshape(B * N, C)
         q = torch.mm(x2, w.t(), out_dtype=torch.float32)
@@ -331,7 +334,10 @@ class UNetCrossAttentionHooker:
         x3 = (is_cross_attn and attention_mask is None and hidden_states.is_cuda
               and self._use_x3(attn, attn.to_q.weight.shape[0], encoder_hidden_states.shape[1]))
         if x3:
-            query = self._query_fp32(attn, hidden_states)
+            # AGENDA_Q_CHUNKS=1: to_q writes the chunk-major layout and the kernel fetches Q by bulk copy.  Measured (DESIGN.md
+            # K2x3): bit-identical, the attention kernel gains 1.3 us of 48 at 64^2 but the GEMM's direct-store epilogue loses
+            # 9.5 us against its staged tensor-map stores, so the row-major form stays the default
+            query = self._query_fp32(attn, hidden_states, chunk_major=os.environ.get("AGENDA_Q_CHUNKS", "0") == "1")
             if self.cache_context_kv and attn.norm_cross is None:
                 kv = self._context_kv(attn, encoder_hidden_states, split=True)
             else:

@@ -478,7 +478,8 @@ def run_ours(args):
     pipe_eager = pipe
     pipe_eager.use_cuda_graph = False
     _lib.event_sink = {"agenda_attn_self_fwd": [], "agenda_attn_self_fwd_strided": [], "agenda_attn_cross_fwd_heat": [],
-                       "agenda_attn_cross_fwd_heat_x3": []}
+                       "agenda_attn_cross_fwd_heat_x3": [], "agenda_attn_cross_fwd_heat_x3_hm": [],
+                       "agenda_linear_split_f32": [], "agenda_linear_split_f32_heads": []}
     pipe_eager.num_steps = 5
     pipe_eager.run_device(hs_dev, ctx_dev)
     torch.cuda.synchronize()
@@ -556,9 +557,12 @@ def run_ours(args):
     def cross_bytes(a):
         B_, H_, N_, M_, d_, T_, bf_ = a[5], a[6], a[7], a[8], a[9], a[12], a[13]
         return 2.0 * B_ * N_ * H_ * d_ * 2 + 2.0 * B_ * M_ * H_ * d_ * 2 + (B_ - bf_) * T_ * N_ * 4.0
-    if sink["agenda_attn_cross_fwd_heat_x3"]:
-        cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat_x3"], cross_bytes_x3, 6, "attn_cross_sm100_x3_kernel"
+    x3_calls = sink["agenda_attn_cross_fwd_heat_x3"] + sink["agenda_attn_cross_fwd_heat_x3_hm"]
+    if x3_calls:
+        cross_calls, cb, n_at, kern = x3_calls, cross_bytes_x3, 6, "attn_cross_sm100_x3_kernel"
         note = "Q fp32 in + O bf16 out + K_hi,K_lo,V in + selected-token heat planes out"
+        if sink["agenda_attn_cross_fwd_heat_x3_hm"]:
+            note += " (Q in the chunk-major layout of the to_q GEMM, fetched by bulk copies)"
     else:
         cross_calls, cb, n_at, kern = sink["agenda_attn_cross_fwd_heat"], cross_bytes, 7, "attn_cross_sm100_res_kernel"
         note = "Q in + O out + K,V in + selected-token heat planes out (bf16)"
@@ -575,6 +579,18 @@ def run_ours(args):
                                          "traffic": 98.5e6 if (kern == "attn_cross_sm100_x3_kernel" and n_img == 8 and not sd21) else None,
                                          "note": "N=%d layers; algorithmic bytes = %s" % (big_n, note)}
 
+    # the fp32-output to_q GEMM of the cross-attention (x, w_hi, w_lo, out, M, K, N, ...): launches at the 64x64 layers
+    ls_calls = sink["agenda_linear_split_f32"] + sink["agenda_linear_split_f32_heads"]
+    ms_l, by_l, n_l = summarize(ls_calls, lambda a: (a[4] * a[5] * 2.0 + a[4] * a[6] * 4.0 + 2.0 * a[5] * a[6] * 2)
+                                if a[4] == 2 * n_img * big_n else None)
+    ms_l_all, _, _ = summarize(ls_calls, lambda a: 1.0)
+    if n_l:
+        extra["to_q_linear_split"] = {"kernel": "linear_split_kernel", "bound": "hbm", "achieved": by_l / (ms_l / 1000.0) / 1e9,
+                                      "peak": hbm_gbs, "unit": "GB/s", "frac": by_l / (ms_l / 1000.0) / 1e9 / hbm_gbs,
+                                      "avg_launch_ms": ms_l / n_l, "launches_timed": n_l,
+                                      "ms_per_denoise_step_all_layers": ms_l_all / 5.0, "traffic": None,
+                                      "note": "N=%d layers; algorithmic bytes = x bf16 in + Q fp32 out + both weight halves; "
+                                              "two MMAs per activation (hi + lo weights)" % big_n}
     extra.update(probe_hbm_kernels(dev, hbm_gbs))
 
     # ---- parity of THIS run's heat maps: images 0 and 1 of the benchmarked batch against the oracle's fp32 evaluation

@@ -110,6 +110,13 @@ int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v
  * K % 64 == 0, N % 160 == 0 (320 / 640 / 1280 in the SD UNets); pointers 16-byte aligned; no bias. */
 int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
                             void* stream);
+/* The same GEMM with the result in the CHUNK-MAJOR layout agenda_attn_cross_fwd_heat_x3_hm streams: x is [B*rows_per_batch, K]
+ * (M = B * rows_per_batch), N = heads * d with d a multiple of 40, and
+ *     out[b][h][c][n][j] = (x W^T)[b * rows_per_batch + n][h * d + c * 40 + j]        (fp32, c < d / 40, j < 40),
+ * so the 128 queries x 40 columns the attention kernel consumes per step are one dense 20 KB block (one bulk copy instead of
+ * a 128-row tensor load) and the GEMM's epilogue writes whole rows of a block straight from its accumulator registers. */
+int agenda_linear_split_f32_heads(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
+                                  int rows_per_batch, int heads, void* stream);
 
 /* ---- prompt side of the split-precision cross-attention: pack K / V once per prompt --------------------------------
  * to_k / to_v of the prompt embedding (hook.py:101-102) do not depend on the latent.  agenda_pack_context_kv turns the
@@ -137,6 +144,12 @@ int agenda_pack_context_kv(const float* k32, const void* v, int v_dtype, void* b
 int agenda_attn_cross_fwd_heat_x3(const float* q, const void* kv_blob, void* out, int out_dtype, int B, int H, int N,
                                   int M, int d, float scale, const int32_t* token_idx, int T, int b_first,
                                   int per_head, float* maps, int accumulate, void* stream);
+/* The same call with q in the chunk-major layout of agenda_linear_split_f32_heads ([B][H][d/40][N][40] fp32; d in
+ * {40,80,160}): identical arithmetic, the Q chunks arrive by bulk copy (a ragged last tile copies its rows, the rest of the
+ * stage is zero-filled, which is what the tensor map's out-of-bounds fill gives the row-major call). */
+int agenda_attn_cross_fwd_heat_x3_hm(const float* q_hm, const void* kv_blob, void* out, int out_dtype, int B, int H, int N,
+                                     int M, int d, float scale, const int32_t* token_idx, int T, int b_first,
+                                     int per_head, float* maps, int accumulate, void* stream);
 
 /* Backward of agenda_attn_cross_fwd_heat (training mode, SURVEY.md §8 f N3: autograd of hook.py:104-115 and of
  * _unravel_attn hook.py:28-56 as exercised by finetune_sd_token.py:1043-1069).  Given d_out [B,N,H*d] (same dtype as

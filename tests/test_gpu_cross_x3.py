@@ -187,3 +187,22 @@ def test_x3_argument_errors(ops):
         ops.pack_context_kv(k.cuda()[..., :48].contiguous(), v.cuda()[..., :48].contiguous(), 2)
     with pytest.raises(ValueError):         # context packed for another batch size
         ops.attn_cross_heat_x3(q.cuda()[:1].contiguous(), ctx, None)
+
+
+@pytest.mark.parametrize("B,N,H,d,T", [(2, 4096, 8, 40, [5, 6, 7]), (3, 100, 8, 80, [1]), (16, 64, 8, 160, [5, 6]),
+                                        (2, 130, 4, 40, [76]), (4, 1024, 8, 80, [7, 9, 11]), (2, 256, 8, 160, None)])
+def test_x3_chunk_major_query_equals_row_major(ops, B, N, H, d, T):
+    """agenda_attn_cross_fwd_heat_x3_hm (Q chunks fetched by bulk copy from the chunk-major layout) gives bit-identical
+    outputs and maps to the row-major call on the same fp32 Q — ragged last tiles, all-token maps, small layers."""
+    M = 77
+    q, k, v = _qkv(B, N, M, H, d, seed=N + d, gain=1.5)
+    out_r, maps_r = _run(ops, q, k, v, H, T, B // 2)
+    qd = q.cuda()
+    buf = qd.view(B, N, H, d // 40, 40).permute(0, 2, 3, 1, 4).contiguous().view(-1)
+    qc = ops.QueryChunks(buf, B, N, H, d)
+    assert torch.equal(qc.to_rows(), qd)
+    ctx = ops.pack_context_kv(k.cuda(), v.cuda().bfloat16(), H)
+    n_tok = M if T is None else len(T)
+    maps_c = torch.full((B - B // 2, n_tok, N), 7.0, device="cuda")
+    out_c = ops.attn_cross_heat_x3(qc, ctx, maps_c, T, B // 2)
+    assert torch.equal(out_c, out_r) and torch.equal(maps_c, maps_r)

@@ -47,3 +47,19 @@ def test_linear_split_f32_argument_errors(ops):
         ops.linear_split_f32(x.float(), torch.zeros(320, 320, device="cuda").bfloat16())
     assert not ops.linear_split_f32_supported(x, torch.zeros(128, 320, device="cuda").bfloat16())
     assert ops.linear_split_f32_supported(x, torch.zeros(320, 320, device="cuda").bfloat16())
+
+
+@pytest.mark.parametrize("B,Nq,K,H,d", [(2, 4096, 320, 8, 40), (3, 100, 640, 8, 80), (16, 64, 1280, 8, 160), (2, 33, 320, 4, 40),
+                                         (5, 256, 1280, 8, 160), (1, 130, 320, 8, 40)])
+def test_linear_split_heads_layout_equals_row_major(ops, B, Nq, K, H, d):
+    """agenda_linear_split_f32_heads: the same numbers as agenda_linear_split_f32, bit for bit, in the chunk-major layout
+    [B][H][d/40][N][40] (tiles that straddle two batch elements, ragged M)."""
+    g = torch.Generator().manual_seed(Nq + d)
+    x = torch.randn(B, Nq, K, generator=g).bfloat16().cuda()
+    w = torch.randn(H * d, K, generator=g) * K ** -0.5
+    w_hi, w_lo = ops.split_bf16(w.cuda())
+    rows = ops.linear_split_f32(x, w_hi, w_lo)
+    chunks = ops.linear_split_f32_heads(x, w_hi, w_lo, H)
+    assert chunks.shape == (B, Nq, H * d) and chunks.buf.numel() == B * Nq * H * d
+    assert torch.equal(chunks.to_rows(), rows)
+    assert torch.equal(ops.linear_split_f32_heads(x, w_hi, None, H).to_rows(), ops.linear_split_f32(x, w_hi, None))
