@@ -52,6 +52,10 @@ _SIGNATURES = {
                               c_void_p],
     "agenda_attn_cross_bwd_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_int, c_int, c_float, ctypes.POINTER(c_int32), c_int, c_int, c_void_p],
+    "agenda_attn_self_fwd_lse": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                 c_void_p],
+    "agenda_attn_self_bwd_lse": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "agenda_attn_self_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_int, c_int, c_int, c_int, c_float, c_void_p],
     "agenda_heat_upsample_accum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -72,7 +76,7 @@ _SIGNATURES = {
 }
 EXPORTS = (["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes",
             "agenda_attn_self_bwd_workspace_bytes", "agenda_groupnorm_workspace_bytes",
-            "agenda_attn_cross_bwd_tc_workspace_bytes"] + list(_SIGNATURES))
+            "agenda_attn_cross_bwd_tc_workspace_bytes", "agenda_attn_self_fwd_emits_lse"] + list(_SIGNATURES))
 
 _lib = None
 
@@ -99,6 +103,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_attn_self_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_attn_cross_bwd_tc_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_attn_cross_bwd_tc_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.agenda_attn_self_fwd_emits_lse.restype = c_int
+    lib.agenda_attn_self_fwd_emits_lse.argtypes = [c_int, c_int]
     lib.agenda_groupnorm_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_groupnorm_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, argtypes in _SIGNATURES.items():

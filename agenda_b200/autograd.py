@@ -44,17 +44,23 @@ class SelfAttentionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, heads: int, scale: float, precision: str):
-        out = ops.attn_self(q, k, v, heads, scale=scale, precision=precision)
-        ctx.save_for_backward(q, k, v, out)
+        lse = None
+        if precision == "bf16" and (q.shape[-1] // heads) in ops.SELF_BWD_HEAD_DIMS:
+            # the forward kernel's softmax epilogue also leaves every row's log-sum-exp: the backward then has no LSE pass
+            out, lse = ops.attn_self_with_lse(q, k, v, heads, scale=scale)
+        else:
+            out = ops.attn_self(q, k, v, heads, scale=scale, precision=precision)
+        ctx.save_for_backward(q, k, v, out, *(() if lse is None else (lse,)))
         ctx.heads, ctx.scale, ctx.precision = heads, scale, precision
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        q, k, v, out = ctx.saved_tensors
+        q, k, v, out = ctx.saved_tensors[:4]
+        lse = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
         d = q.shape[-1] // ctx.heads
         if ctx.precision == "bf16" and d in ops.SELF_BWD_HEAD_DIMS:
-            dq, dk, dv = ops.attn_self_bwd(q, k, v, out, d_out, ctx.heads, scale=ctx.scale)
+            dq, dk, dv = ops.attn_self_bwd(q, k, v, out, d_out, ctx.heads, scale=ctx.scale, lse=lse)
             return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
         return SelfAttentionFn._backward_fp32(q, k, v, d_out, ctx.heads, ctx.scale) + (None, None, None)
 

@@ -653,14 +653,14 @@ static int launch_bwd_mode(const CUtensorMap& r1, const CUtensorMap& r2, const C
 
 template <int D>
 static int attn_self_bwd_d(const void* q, const void* k, const void* v, const void* o, const void* d_o, float* ws, void* dq,
-                           void* dk, void* dv, int B, int H, int N, float scale, cudaStream_t st) {
+                           void* dk, void* dv, int B, int H, int N, float scale, cudaStream_t st, const float* lse_in) {
   CUtensorMap mq, mk, mv, mdo;
   int rc;
   if ((rc = make_head_map(&mq, q, B, H, N, D, 128)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mk, k, B, H, N, D, 128)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mv, v, B, H, N, D, 128)) != AGENDA_OK) return rc;
   if ((rc = make_head_map(&mdo, d_o, B, H, N, D, 128)) != AGENDA_OK) return rc;
-  float* lse2 = ws;
+  float* lse2 = lse_in ? const_cast<float*>(lse_in) : ws;   // (the forward kernel's log-sum-exp, or this call's LSE pass)
   float* delta = ws + static_cast<long long>(B) * H * N;
   {
     const long long warps = static_cast<long long>(B) * N;
@@ -670,7 +670,7 @@ static int attn_self_bwd_d(const void* q, const void* k, const void* v, const vo
                                                              static_cast<const __nv_bfloat16*>(d_o), delta, B, H, N, D);
     AGENDA_LAUNCH_CHECK("attn_bwd_delta_kernel");
   }
-  if ((rc = launch_bwd_mode<D, sm100::kBwdLSE>(mq, mq, mk, mk, lse2, delta, nullptr, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
+  if (!lse_in && (rc = launch_bwd_mode<D, sm100::kBwdLSE>(mq, mq, mk, mk, lse2, delta, nullptr, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
   if ((rc = launch_bwd_mode<D, sm100::kBwdDQ>(mq, mdo, mk, mv, lse2, delta, dq, nullptr, B, H, N, scale, st)) != AGENDA_OK) return rc;
   if constexpr (D <= 64) {   // both accumulators fit TMEM: dK and dV share the recomputed E
     return launch_bwd_mode<D, sm100::kBwdDKV>(mk, mv, mq, mdo, lse2, delta, dk, dv, B, H, N, scale, st);
@@ -770,10 +770,9 @@ extern "C" long long agenda_attn_self_bwd_workspace_bytes(int B, int H, int N) {
   return 2ll * B * H * N * 4;
 }
 
-extern "C" int agenda_attn_self_bwd(const void* q, const void* k, const void* v, const void* out, const void* d_out,
-                                    void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N, int d,
-                                    float scale, void* stream) {
-  const char* who = "attn_self_bwd";
+static int attn_self_bwd_impl(const char* who, const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                              const float* lse, void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N,
+                              int d, float scale, void* stream) {
   if (!q || !k || !v || !out || !d_out || !workspace || !dq || !dk || !dv)
     return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "%s: bf16 only (dtype=1)", who);
@@ -786,10 +785,23 @@ extern "C" int agenda_attn_self_bwd(const void* q, const void* k, const void* v,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(workspace);
   switch (d) {
-    case 40: return attn_self_bwd_d<40>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
-    case 64: return attn_self_bwd_d<64>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
-    case 80: return attn_self_bwd_d<80>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
-    case 160: return attn_self_bwd_d<160>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st);
+    case 40: return attn_self_bwd_d<40>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st, lse);
+    case 64: return attn_self_bwd_d<64>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st, lse);
+    case 80: return attn_self_bwd_d<80>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st, lse);
+    case 160: return attn_self_bwd_d<160>(q, k, v, out, d_out, ws, dq, dk, dv, B, H, N, scale, st, lse);
     default: return fail(AGENDA_ERR_UNSUPPORTED, "%s: head dim %d not in {40,64,80,160}", who, d);
   }
+}
+
+extern "C" int agenda_attn_self_bwd(const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                                    void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N, int d,
+                                    float scale, void* stream) {
+  return attn_self_bwd_impl("attn_self_bwd", q, k, v, out, d_out, nullptr, workspace, dq, dk, dv, dtype, B, H, N, d, scale, stream);
+}
+
+extern "C" int agenda_attn_self_bwd_lse(const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                                        const float* lse, void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H,
+                                        int N, int d, float scale, void* stream) {
+  if (!lse || (reinterpret_cast<uintptr_t>(lse) & 3)) return fail(AGENDA_ERR_NULL_POINTER, "attn_self_bwd_lse: lse is null or misaligned");
+  return attn_self_bwd_impl("attn_self_bwd_lse", q, k, v, out, d_out, lse, workspace, dq, dk, dv, dtype, B, H, N, d, scale, stream);
 }

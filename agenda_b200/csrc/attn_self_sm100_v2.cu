@@ -106,7 +106,7 @@ template <int D, int kEmu, int NT, int BN_, int KS, bool kFast, bool kUnit = fal
 __global__ void __launch_bounds__(NT * KS * 128 + 32 + 32 * NT, 1)
 attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                           const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int H, int N,
-                          float scale_log2, int issue_order) {
+                          float scale_log2, int issue_order, float* __restrict__ lse_out) {
   using C = V2Cfg<D, NT, BN_, KS>;
   constexpr int BN = C::kBlockN;
   constexpr int ST = C::kStages;
@@ -614,6 +614,10 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     __nv_bfloat16* orow = out + (static_cast<long long>(b) * N + n) * (H * D) + h * D;
     // fast pass: was the first tile's maximum a legitimate reference for this row?  (a NaN sum fails both compares)
     if (fast && n < N && !(l_run > 0x1p-80f && l_run < 0x1p100f)) atomicOr(&bars->bad_rows, 1);
+    // training mode: the row's base-2 log-sum-exp of the scaled scores, log2 sum_j 2^(scale log2e s_ij), for the backward
+    // kernels (a row the fast pass got wrong is rewritten by the exact second pass of the same CTA)
+    if (lse_out != nullptr && n < N && (KS == 1 || half == 0))
+      lse_out[(static_cast<long long>(b) * H + h) * N + n] = m_used + log2f(l_run);
 #pragma unroll
     for (int c = 0; c < kOChunks; ++c) {
       if (c >= oc_begin && c < oc_end) {
@@ -649,7 +653,7 @@ attn_self_sm100_v2_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 
 template <int D, int kEmu, int NT, int BN, int KS = 1, bool kFast = false, bool kUnit = false>
 static int launch_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, float scale,
-                     cudaStream_t stream, long long ld) {
+                     cudaStream_t stream, long long ld, float* lse = nullptr) {
   using C = sm100::V2Cfg<D, NT, BN, KS>;
   CUtensorMap mq, mk, mv;
   int rc;
@@ -667,7 +671,7 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
   if (const char* e = knob("AGENDA_V2_SKEW")) stagger = atoi(e);
   issue_order |= stagger << 8;
   kern<<<grid, C::kThreads, smem, stream>>>(mq, mk, mv, static_cast<__nv_bfloat16*>(out), H, N,
-                                            kUnit ? 1.0f : scale * 1.4426950408889634f, issue_order);
+                                            kUnit ? 1.0f : scale * 1.4426950408889634f, issue_order, lse);
   AGENDA_LAUNCH_CHECK("attn_self_sm100_v2_kernel");
   return AGENDA_OK;
 }
@@ -676,14 +680,15 @@ static int launch_v2(const void* q, const void* k, const void* v, void* out, int
 // tiles: 2 = two 128-query tiles per CTA with 128-key tiles (64 for d = 160); 3 = three query tiles with 64-key
 // tiles (d = 40 / 64 only); 4 = two query tiles, each served by two warpgroups owning half a row (d = 40 / 64).
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, int tiles, void* stream, long long ld) {
+                       int emu, int tiles, void* stream, long long ld, float* lse) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ---- shipped configurations (what agenda_attn_self_fwd / _strided dispatch to) ----
-  if (d == 40 && tiles == 203 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true, true>(q, k, v, out, B, H, N, scale, st, ld);
-  if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
-  if (d == 64 && tiles == 102 && emu == 4) return launch_v2<64, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
-  if (d == 80 && tiles == 105 && emu == 4) return launch_v2<80, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld);
-  if (d == 160 && tiles == 2 && emu == 4) return launch_v2<160, 4, 2, 64, 1>(q, k, v, out, B, H, N, scale, st, ld);
+  if (d == 40 && tiles == 203 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true, true>(q, k, v, out, B, H, N, scale, st, ld, lse);
+  if (d == 40 && tiles == 103 && emu == 3) return launch_v2<40, 3, 3, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld, lse);
+  if (d == 64 && tiles == 102 && emu == 4) return launch_v2<64, 4, 2, 128, 1, true>(q, k, v, out, B, H, N, scale, st, ld, lse);
+  if (d == 80 && tiles == 105 && emu == 4) return launch_v2<80, 4, 2, 64, 1, true>(q, k, v, out, B, H, N, scale, st, ld, lse);
+  if (d == 160 && tiles == 2 && emu == 4) return launch_v2<160, 4, 2, 64, 1>(q, k, v, out, B, H, N, scale, st, ld, lse);
+  if (lse != nullptr) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_lse: only the shipped kernel configurations emit the log-sum-exp");
 #ifndef AGENDA_VARIANTS
   return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: kernel variant (d=%d, tiles=%d, emu=%d) exists only in builds with "
               "-DAGENDA_VARIANTS (tests / measurements)", d, tiles, emu);

@@ -401,13 +401,15 @@ int attn_common_checks(const char* who, const void* q, const void* k, const void
                        int H, int N, int M, int d);
 
 int attn_self_sm100_v2(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                       int emu, int tiles, void* stream, long long ld);
+                       int emu, int tiles, void* stream, long long ld, float* lse = nullptr);
 
 // variant: 0 = two query tiles per CTA, ping-pong softmax warpgroups (v2; falls back to variant 1 when N <= 128),
 //          1 = one query tile per CTA, P through TMEM (TS-form PV MMA), 2 = same with P through shared memory (SS)
 // ld: row stride of q/k/v in elements (0 = packed H*d); q_prescaled: q already carries scale * log2(e) (ABI: scale == 0)
+// lse (may be NULL): [B, H, N] fp32, the base-2 log-sum-exp of every row's scaled scores — emitted by the multi-tile kernels
+// only (N > 128, default variant); asking for it elsewhere is AGENDA_ERR_UNSUPPORTED and the caller runs the LSE pass.
 int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int B, int H, int N, int d, float scale,
-                    int variant, void* stream, long long ld = 0, bool q_prescaled = false) {
+                    int variant, void* stream, long long ld = 0, bool q_prescaled = false, float* lse = nullptr) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uintptr_t al = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out);
@@ -448,10 +450,11 @@ int attn_self_sm100(const void* q, const void* k, const void* v, void* out, int 
   if (variant == 0 && N > 128) {
     // (d = 160 only occurs at N <= 256 in the SD UNets: four key tiles do not amortise the fast pass's epilogue)
     // d = 80: 64-key tiles so that P gets its own TMEM columns (0.071 vs 0.076 ms with P aliased onto S at N = 1024)
-    if (d == 80 && fast) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream, ld);
-    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3 + fast, stream, ld)
-                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2 + (d == 160 ? 0 : fast), stream, ld);
+    if (d == 80 && fast) return attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 105, stream, ld, lse);
+    return d == 40 ? attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 3, 3 + fast, stream, ld, lse)
+                   : attn_self_sm100_v2(q, k, v, out, B, H, N, d, scale, 4, 2 + (d == 160 ? 0 : fast), stream, ld, lse);
   }
+  if (lse != nullptr) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_lse: N=%d (<= 128) takes a kernel that does not emit the log-sum-exp", N);
 #define AGENDA_DISPATCH(DD)                                                                                \
   case DD:                                                                                                 \
     return variant <= 1 ? launch_sm100<DD, true>(q, k, v, out, B, H, N, scale, st, ld)                        \
@@ -477,6 +480,19 @@ extern "C" int agenda_attn_self_fwd(const void* q, const void* k, const void* v,
   if (rc != AGENDA_OK) return rc;
   if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd: tensor-core path takes bf16 (dtype=1)");
   return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream);
+}
+
+extern "C" int agenda_attn_self_fwd_emits_lse(int N, int d) {
+  return (N > 128 && (d == 40 || d == 64 || d == 80 || d == 160)) ? 1 : 0;
+}
+
+extern "C" int agenda_attn_self_fwd_lse(const void* q, const void* k, const void* v, void* out, float* lse, int dtype, int B,
+                                        int H, int N, int d, float scale, void* stream) {
+  int rc = attn_common_checks("attn_self_fwd_lse", q, k, v, out, dtype, B, H, N, N, d);
+  if (rc != AGENDA_OK) return rc;
+  if (dtype != AGENDA_BF16) return fail(AGENDA_ERR_UNSUPPORTED, "attn_self_fwd_lse: tensor-core path takes bf16 (dtype=1)");
+  if (!lse || (reinterpret_cast<uintptr_t>(lse) & 3)) return fail(AGENDA_ERR_NULL_POINTER, "attn_self_fwd_lse: lse is null or misaligned");
+  return attn_self_sm100(q, k, v, out, B, H, N, d, scale, 0, stream, 0, false, lse);
 }
 
 extern "C" int agenda_attn_self_fwd_strided(const void* q, const void* k, const void* v, void* out, int dtype, int B,

@@ -200,8 +200,27 @@ SELF_BWD_HEAD_DIMS = (40, 64, 80, 160)
 
 
 @_on_tensor_device
+def attn_self_with_lse(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None):
+    """attn_self on the tensor cores that also returns the rows' base-2 log-sum-exp [B,H,N] fp32 for attn_self_bwd (training
+    mode), or (out, None) where the kernel that runs does not emit it (N <= 128, other head dims)."""
+    q = _dev(q, "q")
+    B, N, C = q.shape
+    d = C // heads
+    if d not in (40, 64, 80, 160) or not _lib.load().agenda_attn_self_fwd_emits_lse(N, d):
+        return attn_self(q, k, v, heads, scale), None
+    scale = float(d ** -0.5 if scale is None else scale)
+    odt = q.dtype
+    qb, kb, vb = (_dev(t, n).to(torch.bfloat16) for t, n in ((q, "q"), (k, "k"), (v, "v")))
+    out = torch.empty_like(qb)
+    lse = torch.empty((B, heads, N), dtype=torch.float32, device=q.device)
+    _lib.call("agenda_attn_self_fwd_lse", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), out.data_ptr(), lse.data_ptr(), _lib.BF16,
+              B, heads, N, d, scale, _stream())
+    return (out if odt == torch.bfloat16 else out.to(odt)), lse
+
+
+@_on_tensor_device
 def attn_self_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor, heads: int,
-                  scale: Optional[float] = None):
+                  scale: Optional[float] = None, lse: Optional[torch.Tensor] = None):
     """Backward of attn_self on the tensor cores (agenda_attn_self_bwd): q/k/v/out/d_out [B,N,H*d] -> (dq, dk, dv) in
     the dtype of q.  Inputs are taken as bf16 (cast if needed); P is recomputed from a log-sum-exp pass."""
     q = _dev(q, "q")
@@ -213,8 +232,16 @@ def attn_self_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.
     scale = float(d ** -0.5 if scale is None else scale)
     ws = torch.empty(_lib.load().agenda_attn_self_bwd_workspace_bytes(B, heads, N) // 4, dtype=torch.float32, device=q.device)
     dq, dk, dv = torch.empty_like(qb), torch.empty_like(qb), torch.empty_like(qb)
-    _lib.call("agenda_attn_self_bwd", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), ob.data_ptr(), gb.data_ptr(),
-              ws.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _lib.BF16, B, heads, N, d, scale, _stream())
+    if lse is not None:   # from attn_self_with_lse: the backward skips its own log-sum-exp pass
+        lse = _dev(lse, "lse", torch.float32)
+        if tuple(lse.shape) != (B, heads, N):
+            raise ValueError(f"lse must be [{B}, {heads}, {N}]")
+        _lib.call("agenda_attn_self_bwd_lse", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), ob.data_ptr(), gb.data_ptr(),
+                  lse.data_ptr(), ws.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _lib.BF16, B, heads, N, d, scale,
+                  _stream())
+    else:
+        _lib.call("agenda_attn_self_bwd", qb.data_ptr(), kb.data_ptr(), vb.data_ptr(), ob.data_ptr(), gb.data_ptr(),
+                  ws.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), _lib.BF16, B, heads, N, d, scale, _stream())
     if odt != torch.bfloat16:
         dq, dk, dv = dq.to(odt), dk.to(odt), dv.to(odt)
     return dq, dk, dv

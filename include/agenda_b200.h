@@ -182,6 +182,17 @@ long long agenda_attn_self_bwd_workspace_bytes(int B, int H, int N);
 int agenda_attn_self_bwd(const void* q, const void* k, const void* v, const void* out, const void* d_out,
                          void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N, int d,
                          float scale, void* stream);
+/* The forward / backward pair that skips the backward's log-sum-exp pass: agenda_attn_self_fwd_lse is agenda_attn_self_fwd
+ * that also writes lse [B,H,N] fp32 = log2 sum_j 2^(scale log2e q_i.k_j) from the softmax epilogue it runs anyway (only the
+ * multi-tile kernels emit it: agenda_attn_self_fwd_emits_lse(N, d) tells; otherwise AGENDA_ERR_UNSUPPORTED), and
+ * agenda_attn_self_bwd_lse is agenda_attn_self_bwd with that vector handed in (four launches instead of five; three at
+ * d <= 64). */
+int agenda_attn_self_fwd_emits_lse(int N, int d);
+int agenda_attn_self_fwd_lse(const void* q, const void* k, const void* v, void* out, float* lse, int dtype, int B, int H,
+                             int N, int d, float scale, void* stream);
+int agenda_attn_self_bwd_lse(const void* q, const void* k, const void* v, const void* out, const void* d_out,
+                             const float* lse, void* workspace, void* dq, void* dk, void* dv, int dtype, int B, int H, int N,
+                             int d, float scale, void* stream);
 
 /* Test hook: same contract, forcing the exact fp32 CUDA-core kernel (bf16 inputs otherwise take the tcgen05
  * tensor-core kernel; fp32 inputs always take the fp32 kernel). */

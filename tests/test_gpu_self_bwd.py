@@ -67,3 +67,30 @@ def test_self_attention_backward_through_autograd_function(ops):
     out32.backward(go.float().cuda())
     for got, ref in ((qf.grad, dq_r), (kf.grad, dk_r), (vf.grad, dv_r)):
         assert (got.cpu() - ref).abs().max().item() < 1e-4 * ref.abs().max().item() + 1e-5
+
+
+@pytest.mark.parametrize("B,N,H,d", [(2, 256, 2, 40), (1, 300, 3, 64), (2, 1024, 4, 80), (1, 4096, 2, 40), (2, 256, 8, 160),
+                                      (1, 130, 2, 40)])
+def test_forward_emitted_lse_matches_and_feeds_the_backward(ops, B, N, H, d):
+    """agenda_attn_self_fwd_lse: same output as agenda_attn_self_fwd bit for bit, lse = log2 sum_j 2^(scale log2e s_ij)
+    against fp32 torch, and agenda_attn_self_bwd_lse with it agrees with the backward that runs its own LSE pass to bf16
+    rounding.  Tolerance of lse: the row sum is the one the forward normalises with — at d = 40 it is accumulated by the PV MMA
+    from the bf16-rounded probabilities, i.e. up to 2^-8 relative on a row one key dominates = 5.6e-3 in log2 units."""
+    g = torch.Generator().manual_seed(N + d)
+    q = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16().cuda()
+    k = (torch.randn(B, N, H * d, generator=g) * 1.5).bfloat16().cuda()
+    v = torch.randn(B, N, H * d, generator=g).bfloat16().cuda()
+    go = torch.randn(B, N, H * d, generator=g).bfloat16().cuda()
+    out, lse = ops.attn_self_with_lse(q, k, v, H)
+    assert lse is not None and lse.shape == (B, H, N)
+    assert torch.equal(out, ops.attn_self(q, k, v, H))
+    qh, kh = (O.head_to_batch_dim(t.float().cpu(), H) for t in (q, k))
+    s = torch.bmm(qh, kh.transpose(1, 2)) * (d ** -0.5) * 1.4426950408889634
+    ref = torch.logsumexp(s * 0.6931471805599453, dim=-1) * 1.4426950408889634
+    assert (lse.cpu().reshape(B * H, N) - ref).abs().max().item() < 8e-3
+    a = ops.attn_self_bwd(q, k, v, out, go, H, lse=lse)
+    b = ops.attn_self_bwd(q, k, v, out, go, H)
+    for x, y in zip(a, b):
+        assert (x.float() - y.float()).abs().max().item() <= 2e-2 * y.float().abs().max().item() + 1e-3
+    small, none = ops.attn_self_with_lse(q[:, :64], k[:, :64], v[:, :64], H)
+    assert none is None and small.shape == (B, 64, H * d)
