@@ -1,4 +1,8 @@
+#!/bin/bash
+# Scratch script of a `gpurun` visit (rewritten per call); this version is the full regression of the round:
+# GPU parity tests, smoke(), the bench line with the reference arm.
 mkdir -p gpurun_out
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"attn_self_bwd_kernel|attn_bwd_delta" -s 4 -c 4 -o gpurun_out/s31_self_bwd_full -f python tools/probe_kernels.py self_bwd > gpurun_out/s31_ncu_a.log 2>&1; echo "ncu a rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"attn_cross_bwd_dq_kernel|attn_self_bwd_kernel" -s 2 -c 2 -o gpurun_out/s31_cross_bwd_full -f python tools/probe_kernels.py cross_bwd_tc > gpurun_out/s31_ncu_b.log 2>&1; echo "ncu b rc=$?"
-timeout 300 ncu --set full --clock-control none -k regex:"gn_stats|gn_apply|layernorm_kernel|geglu_kernel" -s 4 -c 4 -o gpurun_out/s31_glue_full -f python tools/probe_kernels.py glue > gpurun_out/s31_ncu_c.log 2>&1; echo "ncu c rc=$?"
+timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -4 > gpurun_out/final_pytest.log; tail -2 gpurun_out/final_pytest.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/final_smoke.log 2>&1; tail -1 gpurun_out/final_smoke.log
+timeout 500 python bench.py --steps 5 --warmup 3 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; echo "ref rc=$?"
