@@ -220,3 +220,30 @@ def test_empty_batches(ops):
     acc = torch.zeros((0, 3, 64, 64), device=dev)
     ops.heat_upsample_accum(torch.zeros((0, 3, 32, 32), device=dev), acc)
     torch.cuda.synchronize()
+
+
+def test_postprocess_stack_quantisation_boundaries(ops):
+    """The fused K4 kernel on maps built to sit ON the u8 boundaries ((h - min) / range * 255 an integer up to rounding, and one
+    ulp to either side), tiny and huge scales, constant maps, and random ones: byte for byte numpy / PIL.  (A division-free
+    quantisation with an exact fallback passed this test too and bought nothing: the IEEE division is not what bounds K4.)"""
+    rng = np.random.default_rng(5)
+    maps = []
+    for scale in (1.0, 1e-6, 3e4, 0.0149):
+        q = rng.integers(0, 256, (64, 64)).astype(np.float32)
+        base = np.float32(rng.uniform(-1, 1) * scale)
+        m = (base + q * np.float32(scale / 255.0)).astype(np.float32)      # boundaries, exactly representable or one ulp off
+        m.flat[0], m.flat[1] = m.min(), m.max()
+        maps += [m, np.nextafter(m, np.float32(np.inf)), np.nextafter(m, np.float32(-np.inf))]
+    maps += [np.full((64, 64), 0.25, np.float32), np.zeros((64, 64), np.float32)]
+    maps += [(rng.standard_normal((64, 64)) ** 2).astype(np.float32) * np.float32(s) for s in (1.0, 1e-3, 7.0) for _ in range(5)]
+    while len(maps) % 3:
+        maps.append(maps[0])
+    heat = np.stack(maps).reshape(-1, 3, 64, 64)
+    planes, stack, inv = ops.heat_postprocess_stack(cuda(heat), 112)
+    planes, stack, inv = planes.cpu().numpy(), stack.cpu().numpy(), inv.cpu().numpy()
+    for i in range(heat.shape[0]):
+        ref = [O.heat_to_png_array(heat[i, t], 112) for t in range(3)]
+        for t in range(3):
+            assert np.array_equal(planes[i, t], ref[t]), (i, t)
+        rs, ri = O.stack_heatmaps(*ref)
+        assert np.array_equal(stack[i], rs) and np.array_equal(inv[i], ri), i
