@@ -280,8 +280,11 @@ int agenda_layernorm(const void* x, const void* gamma, const void* beta, void* y
  * of each component's first pixel (scipy.ndimage.label numbering); boxes[k] = {x, y, w, h, area}.
  * heat fp32 [n,H,W]; labels int32 [n,H,W] (may be NULL); counts int32 [n] (= K, even when K > max_boxes);
  * boxes int32 [n,max_boxes,5] (only the first min(K,max_boxes) rows are written).
- * One thread-block cluster per map, the map resident in distributed shared memory: H*W*4 bytes must fit
- * 16 CTAs x ~200 KB; otherwise AGENDA_ERR_UNSUPPORTED. */
+ * Default: ONE CTA per map (W % 32 == 0, bit mask <= 12288 words, i.e. up to ~640x600, 16-byte aligned heat / labels,
+ * counts given): the map is streamed once for min / max and a per-word range table, only the words whose range straddles
+ * the threshold are read again, labelling runs on the bit mask in shared memory.  Other shapes, and maps whose pieces
+ * overflow the CTA's table, take one thread-block cluster per map with the fp32 map resident in distributed shared
+ * memory: H*W*4 bytes must fit 16 CTAs x ~200 KB; otherwise AGENDA_ERR_UNSUPPORTED. */
 int agenda_ccl_bbox(const float* heat, float thr, int32_t* labels, int32_t* counts, int32_t* boxes,
                     int max_boxes, int n, int H, int W, void* stream);
 
