@@ -41,6 +41,8 @@ _SIGNATURES = {
     "agenda_attn_fwd_masked": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                c_void_p, c_int, ctypes.POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "agenda_linear_split_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "agenda_linear_split_pack_w": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "agenda_linear_split_f32_packed": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     "agenda_linear_split_f32_heads": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_pack_context_kv": [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "agenda_attn_cross_fwd_heat_x3": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
@@ -76,7 +78,7 @@ _SIGNATURES = {
 }
 EXPORTS = (["agenda_version", "agenda_last_error", "agenda_device_ok", "agenda_context_blob_bytes",
             "agenda_attn_self_bwd_workspace_bytes", "agenda_groupnorm_workspace_bytes",
-            "agenda_attn_cross_bwd_tc_workspace_bytes", "agenda_attn_self_fwd_emits_lse"] + list(_SIGNATURES))
+            "agenda_attn_cross_bwd_tc_workspace_bytes", "agenda_attn_self_fwd_emits_lse", "agenda_linear_split_pack_bytes"] + list(_SIGNATURES))
 
 _lib = None
 
@@ -103,6 +105,8 @@ def load() -> ctypes.CDLL:
     lib.agenda_attn_self_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_attn_cross_bwd_tc_workspace_bytes.restype = ctypes.c_longlong
     lib.agenda_attn_cross_bwd_tc_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.agenda_linear_split_pack_bytes.restype = ctypes.c_longlong
+    lib.agenda_linear_split_pack_bytes.argtypes = [c_int, c_int, c_int]
     lib.agenda_attn_self_fwd_emits_lse.restype = c_int
     lib.agenda_attn_self_fwd_emits_lse.argtypes = [c_int, c_int]
     lib.agenda_groupnorm_workspace_bytes.restype = ctypes.c_longlong

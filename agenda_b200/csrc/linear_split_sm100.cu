@@ -14,6 +14,7 @@
 // tile i overlaps the MMAs of tile i + 1; epilogue warps stage 32-column fp32 sub-tiles in the 128B-swizzled layout
 // (conflict-free stores) and write them with TMA tensor stores (full 128-byte lines, rows clipped by the hardware).
 //   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: epilogue (TMEM lane quadrant = warp % 4)
+#include <algorithm>
 #include <cstdlib>
 
 #include "sm100_common.cuh"
@@ -48,6 +49,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void bulk_load_l(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void st_shared_f4(void* p, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -61,7 +67,8 @@ template <bool kLo, bool kHeads>
 __global__ void __launch_bounds__(kLThreads, 1)
 linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                     const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_out, int M, int K,
-                    int N, float* __restrict__ out_hm, int rows_per_batch, int chunks_per_head) {
+                    int N, float* __restrict__ out_hm, int rows_per_batch, int chunks_per_head,
+                    const unsigned char* __restrict__ w_blob) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sStage = smem;
@@ -74,9 +81,9 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int n_kb = K / kLBK;
 
   if (tid == 0) {
-    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi);
+    tma_prefetch_desc(&map_x);
+    if (w_blob == nullptr) { tma_prefetch_desc(&map_whi); if (kLo) tma_prefetch_desc(&map_wlo); }
     if (!kHeads) tma_prefetch_desc(&map_out);
-    if (kLo) tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < kLStages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -99,8 +106,16 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           unsigned char* a = sStage + s * kLStageBytes;
           mbar_expect_tx(&bars->full[s], kLABytes + (kLo ? 2 : 1) * kLBBytes);
           tma_load_2d(&map_x, &bars->full[s], a, kb * kLBK, tm * kLBM);
-          tma_load_2d(&map_whi, &bars->full[s], a + kLABytes, kb * kLBK, tn * kLBN);
-          if (kLo) tma_load_2d(&map_wlo, &bars->full[s], a + kLABytes + kLBBytes, kb * kLBK, tn * kLBN);
+          if (w_blob != nullptr) {
+            // pre-packed weights (agenda_linear_split_pack_w): the K block's hi | lo tiles are one contiguous image of this
+            // stage's B area -> ONE bulk copy instead of 160 (+160) tensor-map rows (the TMA engine's per-row cost bounds
+            // this kernel: DESIGN.md section 8 item 2)
+            constexpr uint32_t kWBytes = (kLo ? 2 : 1) * kLBBytes;
+            bulk_load_l(a + kLABytes, w_blob + (static_cast<size_t>(tn) * n_kb + kb) * kWBytes, kWBytes, &bars->full[s]);
+          } else {
+            tma_load_2d(&map_whi, &bars->full[s], a + kLABytes, kb * kLBK, tn * kLBN);
+            if (kLo) tma_load_2d(&map_wlo, &bars->full[s], a + kLABytes + kLBBytes, kb * kLBK, tn * kLBN);
+          }
         }
         __syncwarp();
         if (++s == kLStages) { s = 0; ph ^= 1u; }
@@ -209,6 +224,27 @@ linear_split_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   }
 }
 
+// Weight pre-packing for the bulk-copy form: blob[tn][kb] = hi tile | lo tile, each 160 rows x 128 bytes in the 128B-swizzled
+// K-major UMMA layout (16-byte piece p of row r at p ^ (r & 7)) — exactly what the tensor-map loads write into a stage.
+// One thread per 16-byte piece.
+__global__ void linear_split_pack_kernel(const uint4* __restrict__ w_hi, const uint4* __restrict__ w_lo, uint4* __restrict__ blob,
+                                         int N, int K) {
+  const int n_kb = K / kLBK, halves = w_lo ? 2 : 1;
+  const long long total = static_cast<long long>(N / kLBN) * n_kb * halves * kLBN * 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(i & 7);
+    long long rest = i >> 3;
+    const int r = static_cast<int>(rest % kLBN); rest /= kLBN;
+    const int half = static_cast<int>(rest % halves); rest /= halves;
+    const int kb = static_cast<int>(rest % n_kb);
+    const int tn = static_cast<int>(rest / n_kb);
+    const int sp = p ^ (r & 7);   // source piece stored at position p
+    const uint4* src = (half ? w_lo : w_hi) + (static_cast<long long>(tn * kLBN + r) * K + kb * kLBK) / 8 + sp;
+    blob[i] = *src;
+  }
+}
+
 }  // namespace sm100
 
 typedef CUresult (*EncodeTiledFnL)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -247,9 +283,10 @@ static int make_matrix_map(CUtensorMap* map, const void* base, CUtensorMapDataTy
 
 using namespace agenda;
 
+// w_blob != NULL: packed weights (w_hi / w_lo are then not dereferenced; has_lo says whether the blob carries the lo half)
 static int linear_split_impl(const char* who, const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
-                             int rows_per_batch, int heads, void* stream) {
-  if (!x || !w_hi || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+                             int rows_per_batch, int heads, void* stream, const void* w_blob = nullptr, int has_lo = 0) {
+  if (!x || (!w_hi && !w_blob) || !out) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
   if (M <= 0 || K <= 0 || N <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "%s: M=%d K=%d N=%d", who, M, K, N);
   if (K % sm100::kLBK || N % sm100::kLBN)
     return fail(AGENDA_ERR_UNSUPPORTED, "%s: K=%d must be a multiple of %d and N=%d a multiple of %d", who, K, sm100::kLBK, N,
@@ -263,13 +300,17 @@ static int linear_split_impl(const char* who, const void* x, const void* w_hi, c
     chunks_per_head = N / heads / 40;
   }
   const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) |
-                       reinterpret_cast<uintptr_t>(out);
-  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: x / w_hi / w_lo / out must be 16-byte aligned", who);
+                       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w_blob);
+  if (al & 15) return fail(AGENDA_ERR_MISALIGNED, "%s: x / w_hi / w_lo / w_blob / out must be 16-byte aligned", who);
   CUtensorMap mx, mh, ml, mo;
   int rc;
   if ((rc = make_matrix_map(&mx, x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, sm100::kLBK, sm100::kLBM)) != AGENDA_OK) return rc;
-  if ((rc = make_matrix_map(&mh, w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
-  if ((rc = make_matrix_map(&ml, w_lo ? w_lo : w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
+  if (w_blob) { mh = mx; ml = mx; }   // (not used with packed weights; any valid descriptor)
+  else {
+    if ((rc = make_matrix_map(&mh, w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
+    if ((rc = make_matrix_map(&ml, w_lo ? w_lo : w_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, sm100::kLBK, sm100::kLBN)) != AGENDA_OK) return rc;
+  }
+  const bool lo = w_blob ? (has_lo != 0) : (w_lo != nullptr);
   if (hm) mo = mx;   // (not used by the head-major epilogue; any valid descriptor)
   else if ((rc = make_matrix_map(&mo, out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, 32, sm100::kLBM)) != AGENDA_OK) return rc;
   const int n_tiles = ((M + sm100::kLBM - 1) / sm100::kLBM) * (N / sm100::kLBN);
@@ -280,9 +321,10 @@ static int linear_split_impl(const char* who, const void* x, const void* w_hi, c
   do {                                                                                                         \
     auto kern = sm100::linear_split_kernel<LO, HM>;                                                            \
     AGENDA_DYN_SMEM(kern, smem);                                                                               \
-    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N, out, rows_per_batch, chunks_per_head); \
+    kern<<<grid, sm100::kLThreads, smem, st>>>(mx, mh, ml, mo, M, K, N, out, rows_per_batch, chunks_per_head,  \
+                                               static_cast<const unsigned char*>(w_blob));                     \
   } while (0)
-  if (w_lo) { if (hm) AGENDA_LSPLIT(true, true); else AGENDA_LSPLIT(true, false); }
+  if (lo) { if (hm) AGENDA_LSPLIT(true, true); else AGENDA_LSPLIT(true, false); }
   else { if (hm) AGENDA_LSPLIT(false, true); else AGENDA_LSPLIT(false, false); }
 #undef AGENDA_LSPLIT
   AGENDA_LAUNCH_CHECK("linear_split_kernel");
@@ -298,4 +340,32 @@ extern "C" int agenda_linear_split_f32_heads(const void* x, const void* w_hi, co
                                              int rows_per_batch, int heads, void* stream) {
   if (heads <= 0) return fail(AGENDA_ERR_BAD_SHAPE, "linear_split_f32_heads: heads=%d", heads);
   return linear_split_impl("linear_split_f32_heads", x, w_hi, w_lo, out, M, K, N, rows_per_batch, heads, stream);
+}
+
+extern "C" long long agenda_linear_split_pack_bytes(int N, int K, int has_lo) {
+  if (N <= 0 || K <= 0 || K % sm100::kLBK || N % sm100::kLBN)
+    return fail(AGENDA_ERR_UNSUPPORTED, "linear_split_pack_bytes: K=%d must be a multiple of %d and N=%d a multiple of %d", K,
+                sm100::kLBK, N, sm100::kLBN);
+  return static_cast<long long>(N) * K * 2 * (has_lo ? 2 : 1);
+}
+
+extern "C" int agenda_linear_split_pack_w(const void* w_hi, const void* w_lo, void* blob, int N, int K, void* stream) {
+  const char* who = "linear_split_pack_w";
+  if (!w_hi || !blob) return fail(AGENDA_ERR_NULL_POINTER, "%s: null pointer", who);
+  if (N <= 0 || K <= 0 || K % sm100::kLBK || N % sm100::kLBN)
+    return fail(AGENDA_ERR_UNSUPPORTED, "%s: K=%d must be a multiple of %d and N=%d a multiple of %d", who, K, sm100::kLBK, N, sm100::kLBN);
+  if ((reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(w_lo) | reinterpret_cast<uintptr_t>(blob)) & 15)
+    return fail(AGENDA_ERR_MISALIGNED, "%s: w_hi / w_lo / blob must be 16-byte aligned", who);
+  const long long total = static_cast<long long>(N) * K / 8 * (w_lo ? 2 : 1);
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
+  sm100::linear_split_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(w_hi), static_cast<const uint4*>(w_lo), static_cast<uint4*>(blob), N, K);
+  AGENDA_LAUNCH_CHECK("linear_split_pack_kernel");
+  return AGENDA_OK;
+}
+
+extern "C" int agenda_linear_split_f32_packed(const void* x, const void* w_blob, int has_lo, float* out, int M, int K, int N,
+                                              void* stream) {
+  if (!w_blob) return fail(AGENDA_ERR_NULL_POINTER, "linear_split_f32_packed: w_blob is null");
+  return linear_split_impl("linear_split_f32_packed", x, nullptr, nullptr, out, M, K, N, 0, 0, stream, w_blob, has_lo);
 }

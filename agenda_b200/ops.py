@@ -281,6 +281,44 @@ def linear_split_f32(x: torch.Tensor, w_hi: torch.Tensor, w_lo: Optional[torch.T
     return out
 
 
+class PackedSplitWeight:
+    """w_hi | w_lo of a linear layer pre-packed for agenda_linear_split_f32_packed (agenda_linear_split_pack_w)."""
+
+    def __init__(self, blob: torch.Tensor, N: int, K: int, has_lo: bool):
+        self.blob, self.N, self.K, self.has_lo = blob, N, K, has_lo
+
+
+@_on_tensor_device
+def linear_split_pack(w_hi: torch.Tensor, w_lo: Optional[torch.Tensor] = None) -> PackedSplitWeight:
+    """Lay the bf16 weight halves [N, K] out as the GEMM's pipeline-stage images (one bulk copy per K block)."""
+    w_hi = _dev(w_hi, "w_hi", torch.bfloat16)
+    if w_lo is not None:
+        w_lo = _dev(w_lo, "w_lo", torch.bfloat16)
+        if w_lo.shape != w_hi.shape:
+            raise ValueError("w_lo must have the shape of w_hi")
+    N, K = w_hi.shape
+    nbytes = _lib.load().agenda_linear_split_pack_bytes(N, K, int(w_lo is not None))
+    if nbytes < 0:
+        raise _lib.AgendaError(int(nbytes), _lib.load().agenda_last_error().decode("utf-8", "replace"))
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=w_hi.device)
+    _lib.call("agenda_linear_split_pack_w", w_hi.data_ptr(), None if w_lo is None else w_lo.data_ptr(), blob.data_ptr(), N, K,
+              _stream())
+    return PackedSplitWeight(blob, N, K, w_lo is not None)
+
+
+@_on_tensor_device
+def linear_split_f32_packed(x: torch.Tensor, w: PackedSplitWeight) -> torch.Tensor:
+    """linear_split_f32 with pre-packed weights: same numbers, the weights of a K block arrive with one bulk copy."""
+    x = _dev(x, "x", torch.bfloat16)
+    if x.shape[-1] != w.K:
+        raise ValueError(f"x [..., {x.shape[-1]}] does not match the packed weight [{w.N}, {w.K}]")
+    M = x.numel() // w.K
+    out = torch.empty(x.shape[:-1] + (w.N,), dtype=torch.float32, device=x.device)
+    _lib.call("agenda_linear_split_f32_packed", x.data_ptr(), w.blob.data_ptr(), int(w.has_lo), out.data_ptr(), M, w.K, w.N,
+              _stream())
+    return out
+
+
 class QueryChunks:
     """An fp32 query projection in the chunk-major layout [B][H][d/40][N][40] (agenda_linear_split_f32_heads), the form
     agenda_attn_cross_fwd_heat_x3_hm streams with one bulk copy per 128-query chunk.  `to_rows()` gives [B,N,H*d] back."""

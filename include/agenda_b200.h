@@ -110,6 +110,15 @@ int agenda_attn_cross_fwd_heat_heads(const void* q, const void* k, const void* v
  * K % 64 == 0, N % 160 == 0 (320 / 640 / 1280 in the SD UNets); pointers 16-byte aligned; no bias. */
 int agenda_linear_split_f32(const void* x, const void* w_hi, const void* w_lo, float* out, int M, int K, int N,
                             void* stream);
+/* The same GEMM with the weights pre-packed for bulk copies (they are constants of the model): the kernel is bound by the
+ * TMA engine's per-row cost — per 64-wide K block it issues 128 activation rows + 160 (+160) weight rows of 128 bytes — so
+ * agenda_linear_split_pack_w lays w_hi | w_lo out once as blob[N/160][K/64][hi tile | lo tile] (160 rows x 128 bytes each, in
+ * the 128B-swizzled UMMA layout: the exact image of a pipeline stage) and agenda_linear_split_f32_packed fetches a K block's
+ * weights with ONE bulk copy.  agenda_linear_split_pack_bytes gives the blob size.  Same results bit for bit. */
+long long agenda_linear_split_pack_bytes(int N, int K, int has_lo);
+int agenda_linear_split_pack_w(const void* w_hi, const void* w_lo, void* blob, int N, int K, void* stream);
+int agenda_linear_split_f32_packed(const void* x, const void* w_blob, int has_lo, float* out, int M, int K, int N,
+                                   void* stream);
 /* The same GEMM with the result in the CHUNK-MAJOR layout agenda_attn_cross_fwd_heat_x3_hm streams: x is [B*rows_per_batch, K]
  * (M = B * rows_per_batch), N = heads * d with d a multiple of 40, and
  *     out[b][h][c][n][j] = (x W^T)[b * rows_per_batch + n][h * d + c * 40 + j]        (fp32, c < d / 40, j < 40),

@@ -63,3 +63,19 @@ def test_linear_split_heads_layout_equals_row_major(ops, B, Nq, K, H, d):
     assert chunks.shape == (B, Nq, H * d) and chunks.buf.numel() == B * Nq * H * d
     assert torch.equal(chunks.to_rows(), rows)
     assert torch.equal(ops.linear_split_f32_heads(x, w_hi, None, H).to_rows(), ops.linear_split_f32(x, w_hi, None))
+
+
+@pytest.mark.parametrize("M,K,N", [(4096, 320, 320), (1000, 640, 640), (333, 1280, 1280), (65536, 320, 320), (64, 1280, 1280),
+                                    (20000, 64, 160)])
+@pytest.mark.parametrize("with_lo", [True, False])
+def test_linear_split_packed_weights_equal_tensor_map_loads(ops, M, K, N, with_lo):
+    """agenda_linear_split_f32_packed (weights pre-packed into the stage images, one bulk copy per K block) against
+    agenda_linear_split_f32 (tensor-map loads): the same MMAs on the same shared-memory images, so bit for bit."""
+    g = torch.Generator().manual_seed(M + K + 1)
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    w_hi, w_lo = ops.split_bf16(w.cuda())
+    lo = w_lo if with_lo else None
+    packed = ops.linear_split_pack(w_hi, lo)
+    assert packed.blob.numel() == N * K * 2 * (2 if with_lo else 1)
+    assert torch.equal(ops.linear_split_f32_packed(x, packed), ops.linear_split_f32(x, w_hi, lo))

@@ -55,6 +55,8 @@ for N, C in [(4096, 320), (1024, 640), (256, 1280), (64, 1280)]:
     # along N and add the halves: one GEMM, 2x fp32 output
     res["agenda_linear_split_f32 (hi+lo)"] = timed(lambda i: ops.linear_split_f32(xs[i % nbuf], w_hi, w_lo))
     res["agenda_linear_split_f32 (hi)"] = timed(lambda i: ops.linear_split_f32(xs[i % nbuf], w_hi))
+    pk = ops.linear_split_pack(w_hi, w_lo)
+    res["packed weights (hi+lo)"] = timed(lambda i: ops.linear_split_f32_packed(xs[i % nbuf], pk))
     w_cat = torch.cat([w_hi, w_lo], 0)
     res["N-concat GEMM (2C fp32 out)"] = timed(lambda i: torch.mm(xs[i % nbuf], w_cat.t(), out_dtype=torch.float32))
     print(f"M={M} C={C}: " + " | ".join(f"{k}: {v:.1f}" if isinstance(v, float) else f"{k}: {v}" for k, v in res.items()), flush=True)
