@@ -1,7 +1,8 @@
 // K4 + K5: heat-map normalise -> u8 -> PIL-exact bicubic resize (data_generation/data_generation.py:82-85)
 // and invert + channel stack (data_generation/postprocess_heatmap.py:44-46).  Byte/integer results are
-// bit-exact with numpy + PIL.  One CTA per image; everything between the fp32 read and the u8 write lives in
-// shared memory, so HBM traffic is the algorithmic minimum (read Hi*Wi*4 per map, write Ho*Wo per plane).
+// bit-exact with numpy + PIL.  Everything between the fp32 read and the u8 write lives in registers / shared memory, so
+// HBM traffic is the algorithmic minimum (read Hi*Wi*4 per map, write Ho*Wo per plane); the fused kernel runs persistent
+// CTAs that build Pillow's coefficient tables once and walk the images.
 #include <algorithm>
 
 #include "common.cuh"
