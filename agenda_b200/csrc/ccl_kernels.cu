@@ -515,14 +515,19 @@ ccl_bbox_kernel(const float* __restrict__ heat, float thr, int32_t* __restrict__
 // The cluster kernel above keeps the fp32 map resident in distributed shared memory, which caps the number of maps in
 // flight at ~21 per GPU and makes every phase a cluster barrier (46 % of its warp samples, profiles/r01_ccl_*).  Here
 // only the BIT MASK (1 bit per pixel) and a compact piece table live in shared memory:
-//   pass 1  streams the map once for min / max / NaN (float4, 4 loads in flight per thread);
-//   pass 2  re-reads it in REVERSE order — the tail of pass 1 is still in L2 — and thresholds straight into mask words;
+//   pass 1  streams the map once for min / max / NaN (float4, 4 loads in flight per thread) and leaves a 16-bit
+//           (min, max) key pair per 32-pixel word (the range table, see `wtab` in the kernel);
+//   pass 2  fills the mask words from the table and re-reads ONLY the words whose range straddles the threshold (~3 % of
+//           a config-5 map); without the table (cluster split, tiny piece tables, AGENDA_CCL_TAB=0) it re-reads the map in
+//           REVERSE order — the tail of pass 1 is still in L2 — and thresholds straight into mask words;
 //   pieces (runs of set bits inside a word) get compact ids by a block scan (raster order is preserved, so the
 //   smallest id of a component is still its first pixel and scipy's numbering falls out of a second scan);
 //   union-find, root numbering, boxes (shared-memory accumulators) and the label write need __syncthreads only.
-// Extra HBM traffic: the part of pass 2 that misses L2.  Several CTAs per SM, no cluster, no DSMEM.
+// Extra HBM traffic: the straddling words (or, without the table, the part of pass 2 that misses L2).  Several CTAs per SM,
+// no cluster, no DSMEM.
 // A map with more pieces than `cap` is flagged in counts[] and redone by the cluster kernel (second launch).
-// L2 eviction-priority hints: pass 1 asks L2 to keep the map (evict_last), pass 2 releases it (evict_first)
+// L2 eviction-priority hints: with the table everything streams with evict_first; without it pass 1 asks L2 to keep the
+// tail of the map (evict_last) and pass 2 releases it (evict_first)
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
