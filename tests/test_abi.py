@@ -63,3 +63,16 @@ def test_product_has_no_cpu_fallback():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), f
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature in agenda_b200/_lib.py has as many arguments as the prototype in include/agenda_b200.h
+    (a mismatch would not fail at load time: ctypes would silently pass garbage)."""
+    from agenda_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "agenda_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r"\b(agenda_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)}
+    for name, argtypes in _lib._SIGNATURES.items():
+        assert name in protos, name
+        params = [p for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
